@@ -1,0 +1,628 @@
+/*
+ * bee2_oracle.c — plain-C CPU restatement of the bee2 hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see bee2_oracle.h). Written from the algorithm descriptions
+ * in SURVEY.md Appendix A and the cited reference lines; no reference source is copied
+ * (tables such as the belt S-box and the bash round constants are regenerated from
+ * their defining recurrences). Little-endian host assumed (x86-64 / aarch64).
+ *
+ * Parity: PINNED by tests/test_oracle_kat.py (STB annex vectors from the reference's
+ * test/crypto/{bash,belt,bign}_test.c) and by differential runs against
+ * oracle/_ref/libbee2ref_64.so (the unmodified reference compiled by oracle/Makefile).
+ */
+#include "bee2_oracle.h"
+#include <string.h>
+#include <stdlib.h>
+
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef unsigned __int128 u128;
+
+static inline u64 rotl64(u64 x, unsigned n) { return (x << n) | (x >> (64 - n)); }
+static inline u32 rotl32(u32 x, unsigned n) { return (x << n) | (x >> (32 - n)); }
+static inline u32 ld32(const u8* p) { u32 v; memcpy(&v, p, 4); return v; }
+static inline void st32(u8* p, u32 v) { memcpy(p, &v, 4); }
+
+/* ======================================================================= bash */
+
+/* bash_f64.c:32-44 (S-box), :50-57 (constants), :100-112 (P), :126-133 (rotations) */
+void orc_bashF(u8 block[192])
+{
+	u64 s[24], n[24], c = 0x3BF5080AC8BA94B1ull;
+	unsigned rot[8][4] = {{8, 53, 14, 1}};
+	int t, j, x;
+	for (j = 1; j < 8; ++j)
+		for (x = 0; x < 4; ++x)
+			rot[j][x] = 7 * rot[j - 1][x] % 64;
+	memcpy(s, block, 192);
+	for (t = 0; t < 24; ++t)
+	{
+		for (j = 0; j < 8; ++j)
+		{
+			u64 w0 = s[j], w1 = s[8 + j], w2 = s[16 + j], t1, t2, u0, u1, u2;
+			t2 = rotl64(w0, rot[j][0]);
+			w0 ^= w1 ^ w2;
+			t1 = w1 ^ rotl64(w0, rot[j][1]);
+			w1 = t1 ^ t2;
+			w2 ^= rotl64(w2, rot[j][2]) ^ rotl64(t1, rot[j][3]);
+			u0 = ~w2 | w1, u1 = w0 | w2, u2 = w0 & w1;
+			s[j] = w0 ^ u0, s[8 + j] = w1 ^ u1, s[16 + j] = w2 ^ u2;
+		}
+		for (x = 0; x < 24; ++x)
+		{
+			int from = x < 8 ? 8 + (x + 2 * (x & 1) + 7) % 8 :
+				x < 16 ? 8 + (x ^ 1) : (5 * x + 6) % 8;
+			n[x] = s[from];
+		}
+		memcpy(s, n, sizeof s);
+		s[23] ^= c;
+		c = (c >> 1) ^ ((c & 1) ? 0xDC2BE1997FE0D8AEull : 0);
+	}
+	memcpy(block, s, 192);
+}
+
+void orc_bashHashStart(orc_bash_st* st, size_t l)
+{
+	memset(st->s, 0, 192);
+	st->s[184] = (u8)(l / 4);
+	st->rate = 192 - l / 2;
+	st->pos = 0;
+}
+
+void orc_bashHashStepH(const void* buf, size_t n, orc_bash_st* st)
+{
+	const u8* p = (const u8*)buf;
+	while (n)
+	{
+		size_t take = st->rate - st->pos;
+		if (take > n) take = n;
+		memcpy(st->s + st->pos, p, take);   /* overwrite, not XOR: bash_hash.c:59,64,71 */
+		st->pos += take, p += take, n -= take;
+		if (st->pos == st->rate)
+			orc_bashF(st->s), st->pos = 0;
+	}
+}
+
+void orc_bashHashStepG(u8* hash, size_t hash_len, const orc_bash_st* st)
+{
+	u8 s1[192];
+	memcpy(s1, st->s, 192);
+	memset(s1 + st->pos, 0, st->rate - st->pos);  /* pos == 0 -> a whole extra block, :95-99 */
+	s1[st->pos] = 0x40;
+	orc_bashF(s1);
+	memcpy(hash, s1, hash_len);
+}
+
+u32 orc_bashHash(u8* hash, size_t l, const void* src, size_t n)
+{
+	orc_bash_st st;
+	if (l == 0 || l % 16 != 0 || l > 256)
+		return ORC_BAD_PARAMS;
+	orc_bashHashStart(&st, l);
+	orc_bashHashStepH(src, n, &st);
+	orc_bashHashStepG(hash, l / 4, &st);
+	return ORC_OK;
+}
+
+/* ======================================================================= belt */
+
+static u8 H_[256];
+static int H_ready;
+
+/* S-box from its definition (test/crypto/belt_test.c:27-57): H[10]=0,
+   H[(11+x)%256] = 0x8E * z^(116x) in GF(2)[z]/(z^8+z^7+z^6+z+1). */
+const u8* orc_beltH(void)
+{
+	if (!H_ready)
+	{
+		unsigned x, i;
+		H_[10] = 0, H_[11] = 0x8E;
+		for (x = 12; x < 266; ++x)
+		{
+			unsigned t = H_[(x - 1) % 256];
+			for (i = 0; i < 116; ++i)
+				t = (t >> 1) | ((unsigned)__builtin_parity(t & 0x63) << 7);
+			H_[x % 256] = (u8)t;
+		}
+		H_ready = 1;
+	}
+	return H_;
+}
+
+static inline u32 G(u32 x, unsigned r)
+{
+	const u8* H = orc_beltH();
+	u32 v = (u32)H[x & 255] | (u32)H[x >> 8 & 255] << 8 | (u32)H[x >> 16 & 255] << 16 | (u32)H[x >> 24] << 24;
+	return rotl32(v, r);
+}
+
+void orc_beltKeyExpand2(u32 k[8], const u8* key, size_t len)
+{
+	size_t i;
+	for (i = 0; i < len / 4; ++i) k[i] = ld32(key + 4 * i);
+	if (len == 16)
+		for (i = 0; i < 4; ++i) k[4 + i] = k[i];
+	else if (len == 24)
+		k[6] = k[0] ^ k[1] ^ k[2], k[7] = k[3] ^ k[4] ^ k[5];
+}
+
+/* belt_block.c:231-269 */
+void orc_beltBlockEncr2(u32 blk[4], const u32 k[8])
+{
+	u32 a = blk[0], b = blk[1], c = blk[2], d = blk[3], e, t;
+	unsigned i;
+	for (i = 1; i <= 8; ++i)
+	{
+		const unsigned o = 7 * i - 7;
+		b ^= G(a + k[(o + 0) % 8], 5);
+		c ^= G(d + k[(o + 1) % 8], 21);
+		a -= G(b + k[(o + 2) % 8], 13);
+		e = G(b + c + k[(o + 3) % 8], 21) ^ i;
+		b += e, c -= e;
+		d += G(c + k[(o + 4) % 8], 13);
+		b ^= G(a + k[(o + 5) % 8], 21);
+		c ^= G(d + k[(o + 6) % 8], 5);
+		t = a, a = b, b = t;
+		t = c, c = d, d = t;
+		t = b, b = c, c = t;
+	}
+	blk[0] = b, blk[1] = d, blk[2] = a, blk[3] = c;
+}
+
+/* belt_block.c:243,284-295 */
+void orc_beltBlockDecr2(u32 blk[4], const u32 k[8])
+{
+	u32 a = blk[0], b = blk[1], c = blk[2], d = blk[3], e, t;
+	unsigned i;
+	for (i = 8; i >= 1; --i)
+	{
+		const unsigned o = 7 * i - 1;
+		b ^= G(a + k[(o - 0) % 8], 5);
+		c ^= G(d + k[(o - 1) % 8], 21);
+		a -= G(b + k[(o - 2) % 8], 13);
+		e = G(b + c + k[(o - 3) % 8], 21) ^ i;
+		b += e, c -= e;
+		d += G(c + k[(o - 4) % 8], 13);
+		b ^= G(a + k[(o - 5) % 8], 21);
+		c ^= G(d + k[(o - 6) % 8], 5);
+		t = a, a = b, b = t;
+		t = c, c = d, d = t;
+		t = a, a = d, d = t;
+	}
+	blk[0] = c, blk[1] = a, blk[2] = d, blk[3] = b;
+}
+
+static void blk_encr(u8 b[16], const u32 k[8])
+{
+	u32 w[4];
+	memcpy(w, b, 16), orc_beltBlockEncr2(w, k), memcpy(b, w, 16);
+}
+static void blk_decr(u8 b[16], const u32 k[8])
+{
+	u32 w[4];
+	memcpy(w, b, 16), orc_beltBlockDecr2(w, k), memcpy(b, w, 16);
+}
+
+void orc_beltCTRStart(orc_belt_ctr_st* st, const u8* key, size_t len, const u8 iv[16])
+{
+	orc_beltKeyExpand2(st->key, key, len);
+	memcpy(st->ctr, iv, 16);
+	orc_beltBlockEncr2(st->ctr, st->key);
+	st->reserved = 0;
+}
+
+static void ctr_next(orc_belt_ctr_st* st)
+{
+	/* 128-bit little-endian increment, belt_ctr.c:27-35 */
+	if (++st->ctr[0] == 0 && ++st->ctr[1] == 0 && ++st->ctr[2] == 0) ++st->ctr[3];
+	memcpy(st->block, st->ctr, 16);
+	blk_encr(st->block, st->key);
+}
+
+void orc_beltCTRStepE(void* buf, size_t n, orc_belt_ctr_st* st)
+{
+	u8* p = (u8*)buf;
+	size_t i;
+	while (n)
+	{
+		size_t take;
+		if (!st->reserved)
+			ctr_next(st), st->reserved = 16;
+		take = st->reserved < n ? st->reserved : n;
+		for (i = 0; i < take; ++i)
+			p[i] ^= st->block[16 - st->reserved + i];
+		st->reserved -= take, p += take, n -= take;
+	}
+}
+
+u32 orc_beltCTR(void* dst, const void* src, size_t n, const u8* key, size_t len, const u8 iv[16])
+{
+	orc_belt_ctr_st st;
+	if (len != 16 && len != 24 && len != 32)
+		return ORC_BAD_INPUT;
+	orc_beltCTRStart(&st, key, len, iv);
+	memmove(dst, src, n);
+	orc_beltCTRStepE(dst, n, &st);
+	return ORC_OK;
+}
+
+/* full blocks then ciphertext stealing, belt_ecb.c:62-110 */
+static u32 ecb(void* dst, const void* src, size_t n, const u8* key, size_t len, int enc)
+{
+	u32 k[8];
+	u8* p = (u8*)dst;
+	size_t full, r, i;
+	if (n < 16 || (len != 16 && len != 24 && len != 32))
+		return ORC_BAD_INPUT;
+	orc_beltKeyExpand2(k, key, len);
+	memmove(dst, src, n);
+	full = n / 16, r = n % 16;
+	for (i = 0; i < full; ++i)
+		enc ? blk_encr(p + 16 * i, k) : blk_decr(p + 16 * i, k);
+	if (r)
+	{
+		u8 t[16];
+		u8* last = p + 16 * (full - 1);
+		memcpy(t, last + 16, r);
+		memcpy(t + r, last + r, 16 - r);
+		enc ? blk_encr(t, k) : blk_decr(t, k);
+		memcpy(last + 16, last, r);
+		memcpy(last, t, 16);
+	}
+	return ORC_OK;
+}
+u32 orc_beltECBEncr(void* d, const void* s, size_t n, const u8* key, size_t len) { return ecb(d, s, n, key, len, 1); }
+u32 orc_beltECBDecr(void* d, const void* s, size_t n, const u8* key, size_t len) { return ecb(d, s, n, key, len, 0); }
+
+void orc_beltECBEncrMultiKey(u8* blocks, const u8* keys32, size_t count)
+{
+	size_t i;
+	for (i = 0; i < count; ++i)
+	{
+		u32 k[8];
+		orc_beltKeyExpand2(k, keys32 + 32 * i, 32);
+		blk_encr(blocks + 16 * i, k);
+	}
+}
+
+/* sigma1/sigma2 compression, belt_compr.c:27-87. h: 8 words, X: 8 words; s may be NULL. */
+static void belt_compress(u32 s[4], u32 h[8], const u32 X[8])
+{
+	u32 S[4], k1[8], k2[8], y0[4], y1[4];
+	int i;
+	for (i = 0; i < 4; ++i) S[i] = h[i] ^ h[4 + i];
+	orc_beltBlockEncr2(S, X);
+	for (i = 0; i < 4; ++i) S[i] ^= h[i] ^ h[4 + i];
+	if (s)
+		for (i = 0; i < 4; ++i) s[i] ^= S[i];
+	for (i = 0; i < 4; ++i)
+		k1[i] = S[i], k1[4 + i] = h[4 + i], k2[i] = ~S[i], k2[4 + i] = h[i];
+	memcpy(y0, X, 16), memcpy(y1, X + 4, 16);
+	orc_beltBlockEncr2(y0, k1);
+	orc_beltBlockEncr2(y1, k2);
+	for (i = 0; i < 4; ++i)
+		h[i] = y0[i] ^ X[i], h[4 + i] = y1[i] ^ X[4 + i];
+}
+
+/* belt_hash.c:43-190 */
+void orc_beltHash(u8 hash[32], const void* src, size_t n)
+{
+	const u8* p = (const u8*)src;
+	u32 ls[8] = {0}, h[8], X[8];
+	u64 bits_lo = (u64)n << 3, bits_hi = (u64)n >> 61;
+	size_t i;
+	memcpy(h, orc_beltH(), 32);
+	for (i = 0; i + 32 <= n; i += 32)
+		memcpy(X, p + i, 32), belt_compress(ls + 4, h, X);
+	if (i < n)
+	{
+		memset(X, 0, 32), memcpy(X, p + i, n - i);
+		belt_compress(ls + 4, h, X);
+	}
+	ls[0] = (u32)bits_lo, ls[1] = (u32)(bits_lo >> 32), ls[2] = (u32)bits_hi, ls[3] = (u32)(bits_hi >> 32);
+	belt_compress(0, h, ls);
+	memcpy(hash, h, 32);
+}
+
+/* wide-block encryption of exactly 32 bytes: 4 rounds, belt_wbl.c:50-82 with n = 2 */
+static void belt_wbl32(u8 buf[32], const u32 key[8])
+{
+	u64 round;
+	for (round = 1; round <= 4; ++round)
+	{
+		u8 e[16], r1[16];
+		int i;
+		memcpy(r1, buf, 16), memcpy(e, buf, 16);
+		blk_encr(e, key);
+		for (i = 0; i < 8; ++i) e[i] ^= (u8)(round >> (8 * i));
+		for (i = 0; i < 16; ++i) buf[i] = buf[16 + i] ^ e[i];
+		memcpy(buf + 16, r1, 16);
+	}
+}
+
+/* ======================================================================= GF(p), p = 2^256 - 189 */
+
+typedef struct { u64 w[4]; } fe;
+#define PC 189u  /* p = 2^256 - 189: bign_params.c:36-41; Crandall reduction zz_red.c:71-105 */
+static const fe FP = {{0xFFFFFFFFFFFFFF43ull, ~0ull, ~0ull, ~0ull}};
+/* q: bign_params.c:61-66 (little-endian octets) */
+static const fe FQ = {{0x7E5ABF99263D6607ull, 0xD95C8ED60DFB4DFCull, ~0ull, ~0ull}};
+static const u8 B_LE[32] = { /* coefficient b, bign_params.c:50-55 */
+	0xF1, 0x03, 0x9C, 0xD6, 0x6B, 0x7D, 0x2E, 0xB2, 0x53, 0x92, 0x8B, 0x97, 0x69, 0x50, 0xF5, 0x4C,
+	0xBE, 0xFB, 0xD8, 0xE4, 0xAB, 0x3A, 0xC1, 0xD2, 0xED, 0xA8, 0xF3, 0x15, 0x15, 0x6C, 0xCE, 0x77};
+static const u8 YG_LE[32] = { /* base point G = (0, yG), bign_params.c:68-73 */
+	0x93, 0x6A, 0x51, 0x04, 0x18, 0xCF, 0x29, 0x1E, 0x52, 0xF6, 0x08, 0xC4, 0x66, 0x39, 0x91, 0x78,
+	0x5D, 0x83, 0xD6, 0x51, 0xA3, 0xC9, 0xE4, 0x5C, 0x9F, 0xD6, 0x16, 0xFB, 0x3C, 0xFC, 0xF7, 0x6B};
+
+static fe fe_from(const u8 b[32]) { fe r; memcpy(r.w, b, 32); return r; }
+static void fe_to(u8 b[32], fe a) { memcpy(b, a.w, 32); }
+static int fe_cmp(fe a, fe b)
+{
+	int i;
+	for (i = 3; i >= 0; --i)
+		if (a.w[i] != b.w[i]) return a.w[i] < b.w[i] ? -1 : 1;
+	return 0;
+}
+static int fe_is0(fe a) { return (a.w[0] | a.w[1] | a.w[2] | a.w[3]) == 0; }
+static u64 raw_add(fe* r, fe a, fe b)
+{
+	u128 c = 0; int i;
+	for (i = 0; i < 4; ++i) c += (u128)a.w[i] + b.w[i], r->w[i] = (u64)c, c >>= 64;
+	return (u64)c;
+}
+static u64 raw_sub(fe* r, fe a, fe b)
+{
+	u64 br = 0; int i;
+	for (i = 0; i < 4; ++i)
+	{
+		u128 d = (u128)a.w[i] - b.w[i] - br;
+		r->w[i] = (u64)d, br = (u64)(d >> 64) & 1;
+	}
+	return br;
+}
+/* (a + b) mod m, a, b < m (zz_mod.c:42) */
+static fe addmod(fe a, fe b, fe m)
+{
+	fe r, t;
+	u64 c = raw_add(&r, a, b);
+	if (c || fe_cmp(r, m) >= 0) raw_sub(&t, r, m), r = t;
+	return r;
+}
+static fe submod(fe a, fe b, fe m)
+{
+	fe r, t;
+	if (raw_sub(&r, a, b)) raw_add(&t, r, m), r = t;
+	return r;
+}
+static fe fp_add(fe a, fe b) { return addmod(a, b, FP); }
+static fe fp_sub(fe a, fe b) { return submod(a, b, FP); }
+
+static void mul_wide(u64 r[8], const u64* a, const u64* b)
+{
+	int i, j;
+	memset(r, 0, 64);
+	for (i = 0; i < 4; ++i)
+	{
+		u64 carry = 0;
+		for (j = 0; j < 4; ++j)
+		{
+			u128 t = (u128)a[i] * b[j] + r[i + j] + carry;
+			r[i + j] = (u64)t, carry = (u64)(t >> 64);
+		}
+		r[i + 4] = carry;
+	}
+}
+
+/* x (8 words) mod (2^256 - c), c given as 4 words with c < 2^128: fold hi*c into lo until hi = 0 */
+static fe fold_mod(const u64 x[8], fe m)
+{
+	u64 c[4], cur[8], hc[8];
+	fe lo, hi, t;
+	int i;
+	/* c = 2^256 - m */
+	{
+		fe z = {{0, 0, 0, 0}}, cc;
+		raw_sub(&cc, z, m);
+		memcpy(c, cc.w, 32);
+	}
+	memcpy(cur, x, 64);
+	for (;;)
+	{
+		u64 carry;
+		memcpy(lo.w, cur, 32), memcpy(hi.w, cur + 4, 32);
+		if (fe_is0(hi)) break;
+		mul_wide(hc, hi.w, c);
+		/* cur = hc + lo */
+		{
+			u128 acc = 0;
+			for (i = 0; i < 8; ++i)
+			{
+				acc += (u128)hc[i] + (i < 4 ? lo.w[i] : 0);
+				cur[i] = (u64)acc, acc >>= 64;
+			}
+			carry = (u64)acc;
+			(void)carry;
+		}
+	}
+	while (fe_cmp(lo, m) >= 0) raw_sub(&t, lo, m), lo = t;
+	return lo;
+}
+
+static fe fp_mul(fe a, fe b)
+{
+	u64 r[8];
+	mul_wide(r, a.w, b.w);
+	return fold_mod(r, FP);
+}
+static fe fp_sqr(fe a) { return fp_mul(a, a); }
+/* a^(p-2), gfp.c:33-44 */
+static fe fp_inv(fe a)
+{
+	fe e = FP, r = {{1, 0, 0, 0}};
+	int i;
+	e.w[0] -= 2;
+	for (i = 255; i >= 0; --i)
+	{
+		r = fp_sqr(r);
+		if (e.w[i / 64] >> (i % 64) & 1) r = fp_mul(r, a);
+	}
+	return r;
+}
+
+void orc_gfpMul(u8 c[32], const u8 a[32], const u8 b[32]) { fe_to(c, fp_mul(fe_from(a), fe_from(b))); }
+void orc_gfpInv(u8 c[32], const u8 a[32]) { fe_to(c, fp_inv(fe_from(a))); }
+
+/* ======================================================================= curve y^2 = x^3 - 3x + b */
+
+typedef struct { fe X, Y, Z; } pt;  /* Jacobian, O <=> Z = 0 (ecp_j.c) */
+
+static pt pt_dbl(pt P)
+{
+	pt R;
+	fe d, g, bt, al, t, u;
+	if (fe_is0(P.Z) || fe_is0(P.Y)) { memset(&R, 0, sizeof R); R.X.w[0] = R.Y.w[0] = 1; return R; }
+	d = fp_sqr(P.Z), g = fp_sqr(P.Y), bt = fp_mul(P.X, g);
+	t = fp_sub(P.X, d), u = fp_add(P.X, d), al = fp_mul(t, u);
+	al = fp_add(fp_add(al, al), al);                      /* 3(X - Z^2)(X + Z^2), a = -3 */
+	t = fp_add(bt, bt), t = fp_add(t, t);                 /* 4 beta */
+	R.X = fp_sub(fp_sqr(al), fp_add(t, t));
+	u = fp_add(P.Y, P.Z), R.Z = fp_sub(fp_sub(fp_sqr(u), g), d);
+	g = fp_sqr(g), g = fp_add(g, g), g = fp_add(g, g), g = fp_add(g, g);  /* 8 gamma^2 */
+	R.Y = fp_sub(fp_mul(al, fp_sub(t, R.X)), g);
+	return R;
+}
+
+static pt pt_add(pt P, pt Q)
+{
+	pt R;
+	fe z1z1, z2z2, u1, u2, s1, s2, h, r, hh, hhh, v;
+	if (fe_is0(P.Z)) return Q;
+	if (fe_is0(Q.Z)) return P;
+	z1z1 = fp_sqr(P.Z), z2z2 = fp_sqr(Q.Z);
+	u1 = fp_mul(P.X, z2z2), u2 = fp_mul(Q.X, z1z1);
+	s1 = fp_mul(P.Y, fp_mul(Q.Z, z2z2)), s2 = fp_mul(Q.Y, fp_mul(P.Z, z1z1));
+	h = fp_sub(u2, u1), r = fp_sub(s2, s1);
+	if (fe_is0(h))
+	{
+		if (fe_is0(r)) return pt_dbl(P);
+		memset(&R, 0, sizeof R); R.X.w[0] = R.Y.w[0] = 1; return R;
+	}
+	hh = fp_sqr(h), hhh = fp_mul(h, hh), v = fp_mul(u1, hh);
+	R.X = fp_sub(fp_sub(fp_sqr(r), hhh), fp_add(v, v));
+	R.Y = fp_sub(fp_mul(r, fp_sub(v, R.X)), fp_mul(s1, hhh));
+	R.Z = fp_mul(fp_mul(P.Z, Q.Z), h);
+	return R;
+}
+
+/* scalar given as little-endian octets of any length */
+static pt pt_mul(pt A, const u8* d, size_t d_len)
+{
+	pt R;
+	long i;
+	memset(&R, 0, sizeof R); R.X.w[0] = R.Y.w[0] = 1;
+	for (i = (long)d_len * 8 - 1; i >= 0; --i)
+	{
+		R = pt_dbl(R);
+		if (d[i / 8] >> (i % 8) & 1) R = pt_add(R, A);
+	}
+	return R;
+}
+
+static int pt_to_affine(fe* x, fe* y, pt P)
+{
+	fe zi, zi2;
+	if (fe_is0(P.Z)) return 0;
+	zi = fp_inv(P.Z), zi2 = fp_sqr(zi);
+	*x = fp_mul(P.X, zi2), *y = fp_mul(P.Y, fp_mul(zi2, zi));
+	return 1;
+}
+
+static pt pt_affine(fe x, fe y)
+{
+	pt P;
+	P.X = x, P.Y = y, memset(&P.Z, 0, sizeof P.Z), P.Z.w[0] = 1;
+	return P;
+}
+static pt pt_base(void)
+{
+	fe zero = {{0, 0, 0, 0}};
+	return pt_affine(zero, fe_from(YG_LE));
+}
+
+int orc_ecMulA128(u8 b[64], const u8 a[64], const u8* d, size_t d_len)
+{
+	fe x, y;
+	(void)B_LE;
+	if (!pt_to_affine(&x, &y, pt_mul(pt_affine(fe_from(a), fe_from(a + 32)), d, d_len)))
+		return 0;
+	fe_to(b, x), fe_to(b + 32, y);
+	return 1;
+}
+
+/* bign_sign.c:268-347 with l = 128 (no = 32) */
+u32 orc_bignVerify128(const u8* oid_der, size_t oid_len, const u8 hash[32], const u8 sig[48], const u8 pubkey[64])
+{
+	fe Qx = fe_from(pubkey), Qy = fe_from(pubkey + 32), s1 = fe_from(sig + 16), Hh = fe_from(hash), t, x, y;
+	u8 s0[17], s1b[32], buf[256], hv[32];
+	pt R;
+	if (oid_len > 128) return ORC_BAD_INPUT;
+	if (fe_cmp(Qx, FP) >= 0 || fe_cmp(Qy, FP) >= 0) return ORC_BAD_PUBKEY;
+	if (fe_cmp(s1, FQ) >= 0) return ORC_BAD_SIG;
+	if (fe_cmp(Hh, FQ) >= 0) raw_sub(&t, Hh, FQ), Hh = t;
+	s1 = addmod(s1, Hh, FQ);
+	memcpy(s0, sig, 16), s0[16] = 1;
+	fe_to(s1b, s1);
+	R = pt_add(pt_mul(pt_base(), s1b, 32), pt_mul(pt_affine(Qx, Qy), s0, 17));
+	if (!pt_to_affine(&x, &y, R)) return ORC_BAD_SIG;
+	memcpy(buf, oid_der, oid_len), fe_to(buf + oid_len, x), memcpy(buf + oid_len + 32, hash, 32);
+	orc_beltHash(hv, buf, oid_len + 64);
+	return memcmp(hv, sig, 16) == 0 ? ORC_OK : ORC_BAD_SIG;
+}
+
+u32 orc_bignPubkeyCalc128(u8 pubkey[64], const u8 privkey[32])
+{
+	fe d = fe_from(privkey), x, y;
+	if (fe_is0(d) || fe_cmp(d, FQ) >= 0) return ORC_BAD_PRIVKEY;
+	if (!pt_to_affine(&x, &y, pt_mul(pt_base(), privkey, 32))) return ORC_BAD_PARAMS;
+	fe_to(pubkey, x), fe_to(pubkey + 32, y);
+	return ORC_OK;
+}
+
+/* bign_sign.c:140-245 with l = 128 */
+u32 orc_bignSign2_128(u8 sig[48], const u8* oid_der, size_t oid_len, const u8 hash[32],
+	const u8 privkey[32], const void* t, size_t t_len)
+{
+	fe d = fe_from(privkey), k, x, y, s0d, s1, Hh;
+	u8* buf;
+	u8 theta[32], kb[32], hv[32];
+	u32 tk[8];
+	u64 prod[8], s0w[4];
+	if (fe_is0(d) || fe_cmp(d, FQ) >= 0) return ORC_BAD_PRIVKEY;
+	buf = (u8*)malloc(oid_len + 64 + t_len + 1);
+	if (!buf) return 110u;
+	/* theta = belt-hash(oid || d || t) */
+	memcpy(buf, oid_der, oid_len), memcpy(buf + oid_len, privkey, 32);
+	if (t) memcpy(buf + oid_len + 32, t, t_len);
+	orc_beltHash(theta, buf, oid_len + 32 + (t ? t_len : 0));
+	orc_beltKeyExpand2(tk, theta, 32);
+	/* k = H; k = WBL(k) until 0 < k < q */
+	memcpy(kb, hash, 32);
+	do belt_wbl32(kb, tk), k = fe_from(kb);
+	while (fe_is0(k) || fe_cmp(k, FQ) >= 0);
+	if (!pt_to_affine(&x, &y, pt_mul(pt_base(), kb, 32))) { free(buf); return ORC_BAD_PARAMS; }
+	/* s0 = belt-hash(oid || R.x || H)[0..16) */
+	memcpy(buf, oid_der, oid_len), fe_to(buf + oid_len, x), memcpy(buf + oid_len + 32, hash, 32);
+	orc_beltHash(hv, buf, oid_len + 64);
+	free(buf);
+	memcpy(sig, hv, 16);
+	/* s1 = (k - (s0 + 2^128) d - H) mod q */
+	memcpy(s0w, hv, 16), s0w[2] = 1, s0w[3] = 0;
+	mul_wide(prod, s0w, d.w);
+	s0d = fold_mod(prod, FQ);
+	s1 = submod(k, s0d, FQ);
+	Hh = fe_from(hash);           /* not reduced first: bign_sign.c:236-237 */
+	s1 = submod(s1, Hh, FQ);
+	fe_to(sig + 16, s1);
+	return ORC_OK;
+}

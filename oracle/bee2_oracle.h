@@ -1,0 +1,70 @@
+/*
+ * bee2_oracle.h — CPU restatement of the bee2 hot path (TEST INFRASTRUCTURE ONLY).
+ *
+ * This is the checker, not the product: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it. The shipped library
+ * (bee2_b200/csrc) never links, loads or calls anything in oracle/.
+ *
+ * Every function names the reference file:line (agievich/bee2 @ d9e689a0) it follows.
+ * Parity is PINNED: tests/test_oracle_kat.py checks this file against every STB annex
+ * vector the reference's own tests hold for the path (tests/golden/kat.json) and, where
+ * oracle/_ref/libbee2ref_64.so is present, against the unmodified reference on seeded
+ * random inputs.
+ */
+#ifndef BEE2_ORACLE_H
+#define BEE2_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* err_t values, include/bee2/core/err.h:72,132,180,184,186,196 */
+#define ORC_OK 0u
+#define ORC_BAD_INPUT 109u
+#define ORC_BAD_PARAMS 502u
+#define ORC_BAD_PRIVKEY 504u
+#define ORC_BAD_PUBKEY 505u
+#define ORC_BAD_SIG 510u
+
+/* ---- bash (STB 34.101.77) ---- */
+void orc_bashF(uint8_t block[192]);                                         /* bash_f64.c:142-187 */
+uint32_t orc_bashHash(uint8_t* hash, size_t l, const void* src, size_t n);  /* bash_hash.c:118-137 */
+/* streaming: state = 192 s | 8 rate | 8 pos (own layout; bash_hash.c:25-31 semantics) */
+typedef struct { uint8_t s[192]; size_t rate; size_t pos; } orc_bash_st;
+void orc_bashHashStart(orc_bash_st* st, size_t l);                          /* bash_hash.c:38-50 */
+void orc_bashHashStepH(const void* buf, size_t n, orc_bash_st* st);         /* bash_hash.c:52-79 */
+void orc_bashHashStepG(uint8_t* hash, size_t hash_len, const orc_bash_st*); /* bash_hash.c:81-109 */
+
+/* ---- belt (STB 34.101.31) ---- */
+const uint8_t* orc_beltH(void);                                             /* belt_block.c:43-65 */
+void orc_beltKeyExpand2(uint32_t key_[8], const uint8_t* key, size_t len);  /* belt_block.c:88-106 */
+void orc_beltBlockEncr2(uint32_t block[4], const uint32_t key[8]);          /* belt_block.c:324-328 */
+void orc_beltBlockDecr2(uint32_t block[4], const uint32_t key[8]);          /* belt_block.c:362-366 */
+typedef struct { uint32_t key[8]; uint32_t ctr[4]; uint8_t block[16]; size_t reserved; } orc_belt_ctr_st; /* belt_lcl.h:135-141 */
+void orc_beltCTRStart(orc_belt_ctr_st* st, const uint8_t* key, size_t len, const uint8_t iv[16]); /* belt_ctr.c:55-64 */
+void orc_beltCTRStepE(void* buf, size_t n, orc_belt_ctr_st* st);            /* belt_ctr.c:66-111 */
+uint32_t orc_beltCTR(void* dst, const void* src, size_t n, const uint8_t* key, size_t len, const uint8_t iv[16]); /* belt_ctr.c:113-135 */
+uint32_t orc_beltECBEncr(void* dst, const void* src, size_t n, const uint8_t* key, size_t len);  /* belt_ecb.c:112-134 */
+uint32_t orc_beltECBDecr(void* dst, const void* src, size_t n, const uint8_t* key, size_t len);  /* belt_ecb.c:136-158 */
+void orc_beltHash(uint8_t hash[32], const void* src, size_t n);             /* belt_hash.c:174-190 */
+/* key-agility batch: block i under key i (config 5) */
+void orc_beltECBEncrMultiKey(uint8_t* blocks, const uint8_t* keys32, size_t count);
+
+/* ---- bign on bign-curve256v1 (STB 34.101.45, l = 128) ---- */
+uint32_t orc_bignVerify128(const uint8_t* oid_der, size_t oid_len, const uint8_t hash[32],
+	const uint8_t sig[48], const uint8_t pubkey[64]);                       /* bign_sign.c:268-347 */
+uint32_t orc_bignSign2_128(uint8_t sig[48], const uint8_t* oid_der, size_t oid_len,
+	const uint8_t hash[32], const uint8_t privkey[32], const void* t, size_t t_len); /* bign_sign.c:140-245 */
+uint32_t orc_bignPubkeyCalc128(uint8_t pubkey[64], const uint8_t privkey[32]); /* bign_misc.c:369-412 */
+/* d * A on the curve; returns 1, or 0 when the result is the point at infinity. ec.c:497-525 */
+int orc_ecMulA128(uint8_t b[64], const uint8_t a[64], const uint8_t* d, size_t d_len);
+/* field helpers exposed for unit tests of the device field layer (zm.c:214-253, gfp.c:33-44) */
+void orc_gfpMul(uint8_t c[32], const uint8_t a[32], const uint8_t b[32]);
+void orc_gfpInv(uint8_t c[32], const uint8_t a[32]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
