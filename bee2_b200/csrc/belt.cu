@@ -1,0 +1,290 @@
+// belt.cu — belt-CTR / belt-ECB / belt-hash batch kernels for sm_100a + C-ABI launchers.
+//
+// Replaces beltCTRStepE's block loop (belt_ctr.c:85-97), beltECBStepE/D's block loop
+// (belt_ecb.c:68-75, :92-99) and beltHash (belt_hash.c) on batches.
+//
+// Work decomposition: one 16-octet block per thread per step, BELT_ILP independent
+// blocks in flight per thread, persistent grid of one 1024-thread CTA per SM (the
+// 128 KiB bank-replicated T-tables are built once per CTA), grid-stride over blocks
+// so that each warp stores 512 contiguous octets (4 full 128-B lines) per STG.128.
+#include "belt_dev.cuh"
+
+#define BELT_THREADS 1024
+#define BELT_ILP 2
+
+// ---------------------------------------------------------------- CTR
+// counter block for keystream block n (n = first_block + j): s + n + 1 mod 2^128
+// (belt_ctr.c:27-35: 128-bit little-endian increment applied before each encryption)
+__device__ __forceinline__ uint4 ctr_block(const uint4 s, u64 n)
+{
+	const u64 inc = n + 1;              // callers keep first_block + nblocks < 2^64
+	const u64 lo = ((u64)s.y << 32 | s.x) + inc;
+	const u64 hi = ((u64)s.w << 32 | s.z) + (lo < inc ? 1 : 0);
+	return make_uint4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32));
+}
+
+template <bool XOR_SRC>
+__global__ void __launch_bounds__(BELT_THREADS, 1)
+belt_ctr_kernel(uint4* dst, const uint4* src, u64 nblocks, u32 tail,
+	const BeltKey key, const uint4 s, u64 first)
+{
+	extern __shared__ __align__(1024) u8 sm[];
+	BeltBigT::fill(sm);
+	__syncthreads();
+	const BeltBigT S(sm);
+	const u64 step = (u64)gridDim.x * BELT_THREADS;
+	// blocks that can be stored as whole uint4 (a ragged last block is handled apart)
+	const u64 nfull = tail ? nblocks - 1 : nblocks;
+	for (u64 j0 = (u64)blockIdx.x * BELT_THREADS + threadIdx.x; j0 < nblocks; j0 += step * BELT_ILP)
+	{
+		uint4 v[BELT_ILP];
+#pragma unroll
+		for (int u = 0; u < BELT_ILP; ++u)
+			v[u] = ctr_block(s, first + j0 + u * step);
+#pragma unroll
+		for (int u = 0; u < BELT_ILP; ++u)
+			belt_encr(S, v[u].x, v[u].y, v[u].z, v[u].w, key.k);
+#pragma unroll
+		for (int u = 0; u < BELT_ILP; ++u)
+		{
+			const u64 j = j0 + u * step;
+			if (j < nfull)
+			{
+				if (XOR_SRC)
+				{
+					const uint4 d = ldg_stream(src + j);
+					v[u].x ^= d.x, v[u].y ^= d.y, v[u].z ^= d.z, v[u].w ^= d.w;
+				}
+				stg_stream(dst + j, v[u]);
+			}
+			else if (j < nblocks)
+			{
+				// ragged tail: `tail` octets of the last keystream block (belt_ctr.c:99-110)
+				const u32 w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+				u8* d8 = reinterpret_cast<u8*>(dst + j);
+				const u8* s8 = reinterpret_cast<const u8*>(src + j);
+				for (u32 i = 0; i < tail; ++i)
+				{
+					u8 g = (u8)(w[i >> 2] >> (8 * (i & 3)));
+					if (XOR_SRC)
+						g ^= s8[i];
+					d8[i] = g;
+				}
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------- ECB
+// MULTIKEY: block j is encrypted under its own 32-octet key keys[2j..2j+1] (config 5).
+template <bool DEC, bool MULTIKEY>
+__global__ void __launch_bounds__(BELT_THREADS, 1)
+belt_ecb_kernel(uint4* dst, const uint4* src, const uint4* __restrict__ keys, u64 nblocks,
+	const BeltKey key)
+{
+	extern __shared__ __align__(1024) u8 sm[];
+	BeltBigT::fill(sm);
+	__syncthreads();
+	const BeltBigT S(sm);
+	const u64 step = (u64)gridDim.x * BELT_THREADS;
+	for (u64 j0 = (u64)blockIdx.x * BELT_THREADS + threadIdx.x; j0 < nblocks; j0 += step * BELT_ILP)
+	{
+		uint4 v[BELT_ILP];
+		u32 k[BELT_ILP][8];
+#pragma unroll
+		for (int u = 0; u < BELT_ILP; ++u)
+		{
+			const u64 j = j0 + u * step;
+			if (j < nblocks)
+			{
+				v[u] = ldg_stream(src + j);
+				if (MULTIKEY)
+				{
+					const uint4 k0 = ldg_stream(keys + 2 * j), k1 = ldg_stream(keys + 2 * j + 1);
+					k[u][0] = k0.x, k[u][1] = k0.y, k[u][2] = k0.z, k[u][3] = k0.w;
+					k[u][4] = k1.x, k[u][5] = k1.y, k[u][6] = k1.z, k[u][7] = k1.w;
+				}
+			}
+			else
+				v[u] = make_uint4(0, 0, 0, 0);
+			if (!MULTIKEY || j >= nblocks)
+			{
+#pragma unroll
+				for (int i = 0; i < 8; ++i)
+					k[u][i] = key.k[i];
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < BELT_ILP; ++u)
+		{
+			if (DEC)
+				belt_decr(S, v[u].x, v[u].y, v[u].z, v[u].w, k[u]);
+			else
+				belt_encr(S, v[u].x, v[u].y, v[u].z, v[u].w, k[u]);
+		}
+#pragma unroll
+		for (int u = 0; u < BELT_ILP; ++u)
+		{
+			const u64 j = j0 + u * step;
+			if (j < nblocks)
+				stg_stream(dst + j, v[u]);
+		}
+	}
+}
+
+// ---------------------------------------------------------------- belt-hash batch
+// One message per thread; messages of equal length msg_len at msgs + i*stride.
+__global__ void __launch_bounds__(256)
+belt_hash_kernel(u8* __restrict__ hashes, const u8* __restrict__ msgs, u64 msg_len, u64 stride,
+	u64 count)
+{
+	__shared__ u32 tab[256];
+	BeltSmallT::fill(tab);
+	__syncthreads();
+	const BeltSmallT S(tab);
+	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+		return;
+	const u8* m = msgs + i * stride;
+	const bool al4 = (((uintptr_t)msgs | stride) & 3) == 0;
+	u32 h[8], ls[8] = {0, 0, 0, 0, 0, 0, 0, 0}, X[8];
+	belt_hash_init(h);
+	u64 off = 0;
+#pragma unroll 1
+	for (; off < msg_len; off += 32)
+	{
+		if (al4 && off + 32 <= msg_len)
+		{
+#pragma unroll
+			for (int j = 0; j < 8; ++j)
+				X[j] = reinterpret_cast<const u32*>(m + off)[j];
+		}
+		else
+		{
+#pragma unroll
+			for (int j = 0; j < 8; ++j)
+			{
+				u32 w = 0;
+#pragma unroll
+				for (int b = 0; b < 4; ++b)
+				{
+					const u64 p = off + 4 * j + b;
+					if (p < msg_len)
+						w |= (u32)m[p] << (8 * b);
+				}
+				X[j] = w;
+			}
+		}
+		belt_compress(S, ls + 4, h, X);
+	}
+	// length in bits as a 128-bit LE integer (belt_lcl.c:25-48)
+	ls[0] = (u32)(msg_len << 3), ls[1] = (u32)(msg_len >> 29), ls[2] = (u32)(msg_len >> 61), ls[3] = 0;
+	belt_compress(S, (u32*)0, h, ls);
+	u8* o = hashes + 32 * i;
+#pragma unroll
+	for (int j = 0; j < 8; ++j)
+		reinterpret_cast<u32*>(o)[j] = h[j];
+}
+
+// ---------------------------------------------------------------- launchers (C ABI)
+static u32 belt_grid(u64 nblocks)
+{
+	const u64 sms = (u64)b2g_sm_count();
+	const u64 want = (nblocks + (u64)BELT_THREADS * BELT_ILP - 1) / ((u64)BELT_THREADS * BELT_ILP);
+	return (u32)(want < sms ? (want ? want : 1) : sms);
+}
+
+// opt every big-table kernel in to 128 KiB of dynamic shared memory (once, at bring-up)
+static u32 belt_optin_all(void)
+{
+	const void* ks[] = {(const void*)belt_ctr_kernel<true>, (const void*)belt_ctr_kernel<false>,
+		(const void*)belt_ecb_kernel<false, false>, (const void*)belt_ecb_kernel<true, false>,
+		(const void*)belt_ecb_kernel<false, true>};
+	for (size_t i = 0; i < sizeof ks / sizeof ks[0]; ++i)
+		if (cudaFuncSetAttribute(ks[i], cudaFuncAttributeMaxDynamicSharedMemorySize, BELT_BIGT_BYTES) != cudaSuccess)
+			return b2g_check_launch("cudaFuncSetAttribute(belt)");
+	return B2G_OK;
+}
+
+extern "C" u32 b2g_belt_upload_tables(const u8 H[256])
+{
+	const u32 e = belt_upload_H(H);
+	return e ? e : belt_optin_all();
+}
+
+extern "C" u32 b2g_beltCTR_dev(void* d_dest, const void* d_src, size_t count, const u32 key[8],
+	const u32 ctr0[4], u64 first_block, void* stream)
+{
+	u32 e = b2g_ensure_device();
+	if (e) return e;
+	if (count == 0) return B2G_OK;
+	if (((uintptr_t)d_dest & 15) || ((uintptr_t)d_src & 15)) return B2G_BAD_INPUT;
+	const u64 nblocks = ((u64)count + 15) / 16;
+	const u32 tail = (u32)(count & 15);
+	BeltKey k;
+	for (int i = 0; i < 8; ++i) k.k[i] = key[i];
+	const uint4 s = make_uint4(ctr0[0], ctr0[1], ctr0[2], ctr0[3]);
+	cudaStream_t st = (cudaStream_t)stream;
+	if (d_src)
+	{
+		belt_ctr_kernel<true><<<belt_grid(nblocks), BELT_THREADS, BELT_BIGT_BYTES, st>>>(
+			(uint4*)d_dest, (const uint4*)d_src, nblocks, tail, k, s, first_block);
+	}
+	else
+	{
+		belt_ctr_kernel<false><<<belt_grid(nblocks), BELT_THREADS, BELT_BIGT_BYTES, st>>>(
+			(uint4*)d_dest, (const uint4*)0, nblocks, tail, k, s, first_block);
+	}
+	b2g_note_launch();
+	return b2g_check_launch("belt_ctr_kernel");
+}
+
+extern "C" u32 b2g_beltECB_dev(void* d_dest, const void* d_src, size_t nblocks, const u32 key[8],
+	int decrypt, void* stream)
+{
+	u32 e = b2g_ensure_device();
+	if (e) return e;
+	if (nblocks == 0) return B2G_OK;
+	if (((uintptr_t)d_dest & 15) || ((uintptr_t)d_src & 15)) return B2G_BAD_INPUT;
+	BeltKey k;
+	for (int i = 0; i < 8; ++i) k.k[i] = key[i];
+	cudaStream_t st = (cudaStream_t)stream;
+	if (decrypt)
+	{
+		belt_ecb_kernel<true, false><<<belt_grid(nblocks), BELT_THREADS, BELT_BIGT_BYTES, st>>>(
+			(uint4*)d_dest, (const uint4*)d_src, (const uint4*)0, nblocks, k);
+	}
+	else
+	{
+		belt_ecb_kernel<false, false><<<belt_grid(nblocks), BELT_THREADS, BELT_BIGT_BYTES, st>>>(
+			(uint4*)d_dest, (const uint4*)d_src, (const uint4*)0, nblocks, k);
+	}
+	b2g_note_launch();
+	return b2g_check_launch("belt_ecb_kernel");
+}
+
+extern "C" u32 b2g_beltECBEncrBatch_dev(void* d_blocks, const void* d_keys32, size_t count, void* stream)
+{
+	u32 e = b2g_ensure_device();
+	if (e) return e;
+	if (count == 0) return B2G_OK;
+	if (((uintptr_t)d_blocks & 15) || ((uintptr_t)d_keys32 & 15)) return B2G_BAD_INPUT;
+	BeltKey k = {};
+	belt_ecb_kernel<false, true><<<belt_grid(count), BELT_THREADS, BELT_BIGT_BYTES, (cudaStream_t)stream>>>(
+		(uint4*)d_blocks, (const uint4*)d_blocks, (const uint4*)d_keys32, count, k);
+	b2g_note_launch();
+	return b2g_check_launch("belt_ecb_kernel<multikey>");
+}
+
+extern "C" u32 b2g_beltHashBatch_dev(void* d_hashes, const void* d_msgs, size_t msg_len, size_t stride,
+	size_t count, void* stream)
+{
+	u32 e = b2g_ensure_device();
+	if (e) return e;
+	if (count == 0) return B2G_OK;
+	if ((uintptr_t)d_hashes & 3) return B2G_BAD_INPUT;
+	const u32 grid = (u32)((count + 255) / 256);
+	belt_hash_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((u8*)d_hashes, (const u8*)d_msgs, msg_len, stride, count);
+	b2g_note_launch();
+	return b2g_check_launch("belt_hash_kernel");
+}

@@ -1,0 +1,43 @@
+// common.cuh — shared device/host helpers for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+// err_t values mirrored from include/bee2_b200.h (reference include/bee2/core/err.h)
+#define B2G_OK 0u
+#define B2G_BAD_INPUT 109u
+#define B2G_BAD_PARAMS 502u
+#define B2G_BAD_PRIVKEY 504u
+#define B2G_BAD_PUBKEY 505u
+#define B2G_BAD_SIG 510u
+#define B2G_ERR_NO_DEVICE 9001u
+#define B2G_ERR_CUDA 9002u
+
+extern "C" {
+// engine.c
+int b2g_sm_count(void);
+void b2g_note_launch(void);
+u32 b2g_check_launch(const char* what);   // cudaGetLastError -> err_t, records text
+u32 b2g_ensure_device(void);
+}
+
+__device__ __forceinline__ u32 rotl32(u32 x, int n) { return __funnelshift_l(x, x, n); }
+
+// 128-bit streaming global accesses (data touched once: keep it out of L1)
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p)
+{
+	uint4 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+		: "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ void stg_stream(uint4* p, uint4 v)
+{
+	asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+		:: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}

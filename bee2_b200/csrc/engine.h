@@ -1,0 +1,52 @@
+/* engine.h — internal host-side plumbing shared by host_*.c (C, not exported as API). */
+#ifndef B2G_ENGINE_H
+#define B2G_ENGINE_H
+
+#include <cuda_runtime_api.h>
+#include "../../include/bee2_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* lazy per-process initialisation: device check, constant tables. 0 or an err_t. */
+u32 b2g_ensure_device(void);
+void b2g_note_launch(void);
+u32 b2g_check_launch(const char* what);
+u32 b2g_cuda_fail(cudaError_t e, const char* what);   /* records text, returns ERR_B2G_CUDA (or OOM) */
+void b2g_die(const char* fn, u32 code);              /* void drop-ins: print + abort() */
+
+/* One big lock around the host-pointer entry points (they share the workspace). */
+void b2g_lock(void);
+void b2g_unlock(void);
+
+/* Pipelined workspace: NSLOT slots, each a stream + growable device buffers. */
+#define B2G_NSLOT 2
+#define B2G_NBUF 3
+typedef struct
+{
+	cudaStream_t stream;
+	void* buf[B2G_NBUF];
+	size_t cap[B2G_NBUF];
+} b2g_slot;
+b2g_slot* b2g_slot_get(int i);
+/* device buffer `which` of slot `s` with at least `bytes` capacity (grown if needed) */
+u32 b2g_slot_buf(b2g_slot* s, int which, size_t bytes, void** out);
+
+/* kernels' device-level launchers that are not part of the public header */
+u32 b2g_belt_upload_tables(const octet H[256]);
+u32 b2g_bash_upload_tables(void);
+u32 b2g_bign_upload_tables(const octet H[256]);
+u32 b2g_bignSign2Batch_t_dev(void* d_status, void* d_sigs, const octet oid_der[], size_t oid_len,
+	const void* d_hashes, const void* d_privkeys, size_t count, const void* t, size_t t_len, void* stream);
+u32 b2g_bashSponge_dev(const void* d_msgs, size_t stride, size_t msg_len, size_t count,
+	size_t l, const void* d_states_in, void* d_states_out, void* d_hashes, size_t hash_len,
+	int pre_f, void* stream);
+
+/* units per pipeline chunk so that one chunk moves about `target_bytes` */
+size_t b2g_chunk_units(size_t unit_bytes, size_t target_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,196 @@
+/*
+ * host_bash.c — host side (C) of the bash path: the reference's bash.h surface
+ * (bash_hash.c:25-137, bash_f.c:26-44) and the host-pointer batch entry points, all
+ * implemented by staging buffers to the GPU and launching the sm_100a kernels in bash.cu.
+ * Buffer bookkeeping only — every bash-f evaluation happens on the device.
+ */
+#include "engine.h"
+#include <string.h>
+
+const char bash_platform[] = "BASH_CUDA_SM100A";
+
+/* same layout as the reference's bash_hash_st (bash_hash.c:25-31); bashF_deep() == 0 */
+typedef struct
+{
+	octet s[192];
+	octet s1[192];
+	size_t buf_len;
+	size_t pos;
+} bash_hash_st;
+
+size_t bashF_deep(void) { return 0; }
+size_t bashHash_keep(void) { return sizeof(bash_hash_st); }
+
+#define CU(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { code = b2g_cuda_fail(e_, what); goto done; } } while (0)
+
+err_t bashFBatch(octet* blocks, size_t count)
+{
+	err_t code;
+	b2g_slot* sl;
+	void* d;
+	if (count && !blocks)
+		return ERR_BAD_INPUT;
+	if ((code = b2g_ensure_device()))
+		return code;
+	if (!count)
+		return ERR_OK;
+	b2g_lock();
+	sl = b2g_slot_get(0);
+	if ((code = b2g_slot_buf(sl, 0, 192 * count, &d)))
+		goto done;
+	CU(cudaMemcpyAsync(d, blocks, 192 * count, cudaMemcpyHostToDevice, sl->stream), "H2D(bashF)");
+	if ((code = b2g_bashFBatch_dev(d, count, sl->stream)))
+		goto done;
+	CU(cudaMemcpyAsync(blocks, d, 192 * count, cudaMemcpyDeviceToHost, sl->stream), "D2H(bashF)");
+	CU(cudaStreamSynchronize(sl->stream), "sync(bashF)");
+done:
+	b2g_unlock();
+	return code;
+}
+
+void bashF(octet block[192], void* stack)
+{
+	err_t code = bashFBatch(block, 1);
+	(void)stack;
+	if (code)
+		b2g_die("bashF", code);
+}
+
+err_t bashHashBatch(octet* hashes, size_t l, const void* msgs, size_t msg_len, size_t stride,
+	size_t count)
+{
+	err_t code;
+	size_t hl, pitch, chunk, done_units, c;
+	int contiguous;
+	if (l == 0 || l % 16 != 0 || l > 256)
+		return ERR_BAD_PARAMS;
+	if (count && (!hashes || (msg_len && !msgs) || (count > 1 && stride < msg_len)))
+		return ERR_BAD_INPUT;
+	if ((code = b2g_ensure_device()))
+		return code;
+	if (!count)
+		return ERR_OK;
+	hl = l / 4;
+	contiguous = (stride == msg_len || count == 1) && msg_len % 16 == 0;
+	pitch = contiguous ? msg_len : (msg_len + 15) & ~(size_t)15;
+	chunk = b2g_chunk_units(pitch + hl, (size_t)64 << 20);
+	b2g_lock();
+	for (done_units = 0, c = 0; done_units < count; done_units += chunk, ++c)
+	{
+		const size_t n = count - done_units < chunk ? count - done_units : chunk;
+		b2g_slot* sl = b2g_slot_get((int)c);
+		const octet* src = (const octet*)msgs + done_units * stride;
+		void *d_in, *d_out;
+		if ((code = b2g_slot_buf(sl, 0, n * pitch, &d_in)) || (code = b2g_slot_buf(sl, 1, n * hl, &d_out)))
+			goto done;
+		if (msg_len)
+		{
+			if (contiguous)
+				CU(cudaMemcpyAsync(d_in, src, n * msg_len, cudaMemcpyHostToDevice, sl->stream), "H2D(bash msgs)");
+			else
+				CU(cudaMemcpy2DAsync(d_in, pitch, src, n > 1 ? stride : msg_len, msg_len, n,
+					cudaMemcpyHostToDevice, sl->stream), "H2D2D(bash msgs)");
+		}
+		if ((code = b2g_bashHashBatch_dev(d_out, l, d_in, msg_len, pitch, n, sl->stream)))
+			goto done;
+		CU(cudaMemcpyAsync(hashes + done_units * hl, d_out, n * hl, cudaMemcpyDeviceToHost, sl->stream), "D2H(bash digests)");
+	}
+	for (c = 0; c < B2G_NSLOT; ++c)
+		CU(cudaStreamSynchronize(b2g_slot_get((int)c)->stream), "sync(bash)");
+done:
+	if (code)
+		for (c = 0; c < B2G_NSLOT; ++c)
+			cudaStreamSynchronize(b2g_slot_get((int)c)->stream);
+	b2g_unlock();
+	return code;
+}
+
+err_t bashHash(octet hash[], size_t l, const void* src, size_t count)
+{
+	if (l == 0 || l % 16 != 0 || l > 256)
+		return ERR_BAD_PARAMS;
+	if ((count && !src) || !hash)
+		return ERR_BAD_INPUT;
+	return bashHashBatch(hash, l, src, count, count, 1);
+}
+
+void bashHashStart(void* state, size_t l)
+{
+	bash_hash_st* st = (bash_hash_st*)state;
+	memset(st->s, 0, sizeof st->s);
+	st->s[192 - 8] = (octet)(l / 4);
+	st->buf_len = 192 - l / 2;
+	st->pos = 0;
+}
+
+/* absorb: run F on the (already merged) state, then `nfull` further rate blocks from buf */
+static err_t sponge_absorb(bash_hash_st* st, const octet* buf, size_t nfull)
+{
+	err_t code;
+	b2g_slot* sl;
+	void *d_state, *d_msg;
+	const size_t bytes = nfull * st->buf_len, l = 2 * (192 - st->buf_len);
+	if ((code = b2g_ensure_device()))
+		return code;
+	b2g_lock();
+	sl = b2g_slot_get(0);
+	if ((code = b2g_slot_buf(sl, 0, bytes, &d_msg)) || (code = b2g_slot_buf(sl, 1, 192, &d_state)))
+		goto done;
+	CU(cudaMemcpyAsync(d_state, st->s, 192, cudaMemcpyHostToDevice, sl->stream), "H2D(bash state)");
+	if (bytes)
+		CU(cudaMemcpyAsync(d_msg, buf, bytes, cudaMemcpyHostToDevice, sl->stream), "H2D(bash data)");
+	if ((code = b2g_bashSponge_dev(d_msg, bytes, bytes, 1, l, d_state, d_state, 0, 0, 1, sl->stream)))
+		goto done;
+	CU(cudaMemcpyAsync(st->s, d_state, 192, cudaMemcpyDeviceToHost, sl->stream), "D2H(bash state)");
+	CU(cudaStreamSynchronize(sl->stream), "sync(bash absorb)");
+done:
+	b2g_unlock();
+	return code;
+}
+
+void bashHashStepH(const void* buf, size_t count, void* state)
+{
+	bash_hash_st* st = (bash_hash_st*)state;
+	const octet* p = (const octet*)buf;
+	size_t nfull;
+	err_t code;
+	if (count < st->buf_len - st->pos)
+	{
+		memcpy(st->s + st->pos, p, count);
+		st->pos += count;
+		return;
+	}
+	memcpy(st->s + st->pos, p, st->buf_len - st->pos);
+	p += st->buf_len - st->pos, count -= st->buf_len - st->pos;
+	nfull = count / st->buf_len;
+	if ((code = sponge_absorb(st, p, nfull)))
+		b2g_die("bashHashStepH", code);
+	p += nfull * st->buf_len, count -= nfull * st->buf_len;
+	st->pos = count;
+	if (count)
+		memcpy(st->s, p, count);
+}
+
+static void sponge_final(bash_hash_st* st)
+{
+	err_t code;
+	memcpy(st->s1, st->s, 192);
+	memset(st->s1 + st->pos, 0, st->buf_len - st->pos);
+	st->s1[st->pos] = 0x40;
+	if ((code = bashFBatch(st->s1, 1)))
+		b2g_die("bashHashStepG", code);
+}
+
+void bashHashStepG(octet hash[], size_t hash_len, void* state)
+{
+	bash_hash_st* st = (bash_hash_st*)state;
+	sponge_final(st);
+	memmove(hash, st->s1, hash_len);
+}
+
+bool_t bashHashStepV(const octet hash[], size_t hash_len, void* state)
+{
+	bash_hash_st* st = (bash_hash_st*)state;
+	sponge_final(st);
+	return memcmp(hash, st->s1, hash_len) == 0;
+}

@@ -1,0 +1,117 @@
+// microbench.cu — measured integer-issue peaks of the device (denominators for the
+// "issue roofline" bench.py reports next to the HBM roofline: bash/belt/bign are bound by
+// the ALU / FMA-integer / shared-memory pipes).
+//
+// Each kernel runs ILP independent dependency chains per thread of one instruction kind,
+// 1024 threads x (2 x SM count) CTAs, and reports lane-operations per second from CUDA
+// events. The multipliers / shift amounts come from kernel arguments so ptxas cannot fold
+// or strength-reduce the chains.
+#include "common.cuh"
+
+#define MB_ILP 8
+#define MB_UNROLL 32
+
+enum { MB_LOP3 = 0, MB_SHF = 1, MB_PRMT = 2, MB_IADD3 = 3, MB_IMAD = 4, MB_IMAD_WIDE = 5, MB_LDS = 6, MB_MIX_LOP3_IMADW = 7 };
+
+template <int KIND>
+__global__ void __launch_bounds__(1024) mb_kernel(u32* out, u32 iters, u32 a, u32 b, u32 sh)
+{
+	__shared__ u32 sm[32 * 64];
+	u32 x[MB_ILP];
+	u64 w[MB_ILP];
+#pragma unroll
+	for (int i = 0; i < MB_ILP; ++i)
+	{
+		x[i] = KIND == MB_LDS ? ((threadIdx.x + i) & 63u) << 5 : threadIdx.x * 2654435761u + i * a;
+		w[i] = ((u64)x[i] << 32) | (b + i);
+	}
+	for (u32 i = threadIdx.x; i < 32 * 64; i += blockDim.x)
+		sm[i] = (i * 7 + a) & (63u << 5);   // next index: keeps the lane's own bank (multiple of 32 words)
+	__syncthreads();
+	const u32 lane = threadIdx.x & 31;
+#pragma unroll 1
+	for (u32 it = 0; it < iters; ++it)
+	{
+#pragma unroll
+		for (int u = 0; u < MB_UNROLL; ++u)
+		{
+#pragma unroll
+			for (int i = 0; i < MB_ILP; ++i)
+			{
+				if (KIND == MB_LOP3)
+					asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(a), "r"(b));
+				else if (KIND == MB_SHF)
+					asm volatile("shf.l.wrap.b32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(b), "r"(sh));
+				else if (KIND == MB_PRMT)
+					asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(b), "r"(sh));
+				else if (KIND == MB_IADD3)
+					asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(a));
+				else if (KIND == MB_IMAD)
+					asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
+				else if (KIND == MB_IMAD_WIDE)
+					asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(x[i]), "r"(a));
+				else if (KIND == MB_LDS)
+					x[i] = sm[x[i] + lane];
+				else if (KIND == MB_MIX_LOP3_IMADW)
+				{
+					asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(a), "r"(b));
+					asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(sh), "r"(a));
+				}
+			}
+		}
+	}
+	u32 acc = 0;
+#pragma unroll
+	for (int i = 0; i < MB_ILP; ++i)
+		acc ^= x[i] ^ (u32)w[i] ^ (u32)(w[i] >> 32);
+	if (acc == 0x12345678u)
+		out[0] = acc;
+}
+
+template <int KIND> static double mb_run(u32 iters, u32* d_out)
+{
+	const int grid = 2 * b2g_sm_count();
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0), cudaEventCreate(&e1);
+	const u32 sh = KIND == MB_PRMT ? 0x2103u : 7u;
+	mb_kernel<KIND><<<grid, 1024>>>(d_out, 4, 0x9E3779B1u, 0x85EBCA6Bu, sh);   // warm-up
+	cudaEventRecord(e0);
+	mb_kernel<KIND><<<grid, 1024>>>(d_out, iters, 0x9E3779B1u, 0x85EBCA6Bu, sh);
+	cudaEventRecord(e1);
+	cudaEventSynchronize(e1);
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e0, e1);
+	cudaEventDestroy(e0), cudaEventDestroy(e1);
+	b2g_note_launch(), b2g_note_launch();
+	if (b2g_check_launch("mb_kernel") || ms <= 0)
+		return -1.0;
+	const double per_thread = (double)iters * MB_UNROLL * MB_ILP * (KIND == MB_MIX_LOP3_IMADW ? 2 : 1);
+	return per_thread * 1024.0 * grid / (ms * 1e-3);
+}
+
+// lane-operations per second of one instruction kind on the whole chip (or < 0 on error)
+extern "C" double b2g_microbench(int kind, unsigned iters)
+{
+	if (b2g_ensure_device())
+		return -1.0;
+	u32* d_out = 0;
+	if (cudaMalloc(&d_out, 64) != cudaSuccess)
+		return -1.0;
+	double r = -1.0;
+	if (iters == 0)
+		iters = 2000;
+	switch (kind)
+	{
+	case MB_LOP3: r = mb_run<MB_LOP3>(iters, d_out); break;
+	case MB_SHF: r = mb_run<MB_SHF>(iters, d_out); break;
+	case MB_PRMT: r = mb_run<MB_PRMT>(iters, d_out); break;
+	case MB_IADD3: r = mb_run<MB_IADD3>(iters, d_out); break;
+	case MB_IMAD: r = mb_run<MB_IMAD>(iters, d_out); break;
+	case MB_IMAD_WIDE: r = mb_run<MB_IMAD_WIDE>(iters, d_out); break;
+	case MB_LDS: r = mb_run<MB_LDS>(iters, d_out); break;
+	case MB_MIX_LOP3_IMADW: r = mb_run<MB_MIX_LOP3_IMADW>(iters, d_out); break;
+	default: break;
+	}
+	cudaFree(d_out);
+	return r;
+}

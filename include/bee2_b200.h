@@ -1,0 +1,199 @@
+/*
+ * bee2_b200.h — C ABI of the B200-native batch engine for the bee2 hot path.
+ *
+ * Three groups of entry points, all `extern "C"`, plain pointers and sizes:
+ *
+ *  1. DROP-IN symbols: same names, prototypes, state layouts and err_t behaviour as
+ *     the reference headers (include/bee2/crypto/{bash,belt,bign}.h). A program that
+ *     links libbee2_b200.so in place of libbee2 for these symbols gets the GPU path.
+ *     Each declaration cites the reference declaration it replaces.
+ *  2. BATCH symbols (`...Batch`): host pointers in/out, many independent units per
+ *     call — what the reference-side binding calls for throughput.
+ *  3. DEVICE symbols (`b2g_*_dev`): the same work on buffers already resident in HBM,
+ *     on a caller-supplied CUDA stream (NULL = default stream). Used by bench.py and
+ *     by multi-GPU drivers that keep data on the device.
+ *
+ * Every function here runs on the GPU. There is no CPU fallback: if no CUDA device
+ * is usable, `err_t` functions return ERR_B2G_NO_DEVICE and `void` functions abort()
+ * with a message on stderr.
+ *
+ * Conventions (identical to the reference): all multi-byte integers are
+ * little-endian octet strings; the caller owns every buffer; streaming states are
+ * caller-allocated flat structs of exactly X_keep() bytes and may be memcpy'd; every
+ * function is re-entrant on distinct states (the engine serialises device access with
+ * an internal mutex).
+ */
+#ifndef BEE2_B200_H
+#define BEE2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- basic types: include/bee2/defs.h:269,372,441,463 ---- */
+typedef uint8_t octet;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef uint64_t word;
+typedef int bool_t;
+typedef u32 err_t;
+
+/* ---- error codes: include/bee2/core/err.h:72,74,92,112,132,180,184,186,196 ---- */
+#define ERR_OK 0u
+#define ERR_BAD_INPUT 109u
+#define ERR_OUTOFMEMORY 110u
+#define ERR_NOT_IMPLEMENTED 119u
+#define ERR_FILE_NOT_FOUND 202u
+#define ERR_BAD_OID 301u
+#define ERR_BAD_PARAMS 502u
+#define ERR_BAD_PRIVKEY 504u
+#define ERR_BAD_PUBKEY 505u
+#define ERR_BAD_SIG 510u
+/* engine-specific (outside the reference's ranges) */
+#define ERR_B2G_NO_DEVICE 9001u   /* no usable CUDA device / driver */
+#define ERR_B2G_CUDA 9002u        /* a CUDA call failed; see b2g_last_error() */
+
+/* ======================================================================= engine */
+/* Select the CUDA device for this process (default: current device). Idempotent. */
+err_t b2g_init(int device);
+/* Human-readable text of the last CUDA failure on this thread ("" if none). */
+const char* b2g_last_error(void);
+/* Number of SMs of the active device (grid sizing is a multiple of it). */
+int b2g_sm_count(void);
+/* Pinned host memory for full-rate PCIe transfers through the Batch entry points. */
+void* b2g_host_alloc(size_t bytes);
+void b2g_host_free(void* p);
+/* Plain device memory helpers for callers without their own allocator. */
+void* b2g_dev_alloc(size_t bytes);
+void b2g_dev_free(void* p);
+err_t b2g_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes);
+err_t b2g_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes);
+err_t b2g_sync(void);
+/* How many kernels this library has launched in this process (for gpu_launches). */
+u64 b2g_launch_count(void);
+/* Measured issue peak of one instruction kind, lane-operations per second on the whole chip:
+   0 LOP3, 1 SHF, 2 PRMT, 3 IADD, 4 IMAD, 5 IMAD.WIDE, 6 LDS.32 (conflict-free), 7 LOP3+IMAD.WIDE
+   co-issued. iters = 0 picks a default. < 0 on failure. Denominators of the issue roofline. */
+double b2g_microbench(int kind, unsigned iters);
+
+/* ======================================================================= bash (STB 34.101.77) */
+/* drop-in: include/bee2/crypto/bash.h:127-139 (bash_f64.c:174-192) */
+extern const char bash_platform[];                       /* bash_f.c:28-43 -> "BASH_CUDA_SM100A" */
+size_t bashF_deep(void);
+void bashF(octet block[192], void* stack);
+/* drop-in: bash.h:152-225 (bash_hash.c:25-137); state layout = bash_hash_st */
+size_t bashHash_keep(void);
+void bashHashStart(void* state, size_t l);
+void bashHashStepH(const void* buf, size_t count, void* state);
+void bashHashStepG(octet hash[], size_t hash_len, void* state);
+bool_t bashHashStepV(const octet hash[], size_t hash_len, void* state);
+err_t bashHash(octet hash[], size_t l, const void* src, size_t count);
+/* batch: `count` messages of msg_len octets, message i at msgs + i*stride; digest i
+   (l/4 octets) at hashes + i*(l/4). Same checks as bashHash. */
+err_t bashHashBatch(octet* hashes, size_t l, const void* msgs, size_t msg_len,
+	size_t stride, size_t count);
+/* batch: bashF on `count` independent 192-octet states, in place */
+err_t bashFBatch(octet* blocks, size_t count);
+/* device */
+err_t b2g_bashHashBatch_dev(void* d_hashes, size_t l, const void* d_msgs, size_t msg_len,
+	size_t stride, size_t count, void* stream);
+err_t b2g_bashFBatch_dev(void* d_blocks, size_t count, void* stream);
+
+/* ======================================================================= belt (STB 34.101.31) */
+/* drop-in: include/bee2/crypto/belt.h:148-257 (belt_block.c) */
+const octet* beltH(void);
+void beltKeyExpand(octet key_[32], const octet key[], size_t len);
+void beltKeyExpand2(u32 key_[8], const octet key[], size_t len);
+void beltBlockEncr(octet block[16], const u32 key[8]);
+void beltBlockEncr2(u32 block[4], const u32 key[8]);
+void beltBlockEncr3(u32* a, u32* b, u32* c, u32* d, const u32 key[8]);
+void beltBlockDecr(octet block[16], const u32 key[8]);
+void beltBlockDecr2(u32 block[4], const u32 key[8]);
+void beltBlockDecr3(u32* a, u32* b, u32* c, u32* d, const u32 key[8]);
+/* drop-in: belt.h:401-487 (belt_ecb.c:44-158); state layout = belt_ecb_st */
+size_t beltECB_keep(void);
+void beltECBStart(void* state, const octet key[], size_t len);
+void beltECBStepE(void* buf, size_t count, void* state);
+void beltECBStepD(void* buf, size_t count, void* state);
+err_t beltECBEncr(void* dest, const void* src, size_t count, const octet key[], size_t len);
+err_t beltECBDecr(void* dest, const void* src, size_t count, const octet key[], size_t len);
+/* drop-in: belt.h:692-743 (belt_ctr.c:55-135); state layout = belt_ctr_st (belt_lcl.h:135-141) */
+size_t beltCTR_keep(void);
+void beltCTRStart(void* state, const octet key[], size_t len, const octet iv[16]);
+void beltCTRStepE(void* buf, size_t count, void* state);
+#define beltCTRStepD beltCTRStepE
+err_t beltCTR(void* dest, const void* src, size_t count, const octet key[], size_t len,
+	const octet iv[16]);
+/* drop-in: belt.h (belt_hash.c:174-190) one-shot only */
+err_t beltHash(octet hash[32], const void* src, size_t count);
+/* batch: pure keystream (beltCTR of zeros) */
+err_t beltCTRKeystream(void* dest, size_t count, const octet key[], size_t len,
+	const octet iv[16]);
+/* batch: key agility — block i (16 octets, in place) under 32-octet key i */
+err_t beltECBEncrBatch(void* blocks, const octet* keys32, size_t count);
+/* batch: belt-hash of `count` messages of msg_len octets (message i at msgs+i*stride) */
+err_t beltHashBatch(octet* hashes, const void* msgs, size_t msg_len, size_t stride, size_t count);
+/* device: dest[0..count) = src[0..count) XOR keystream blocks first_block.. of the stream
+   whose encrypted iv is ctr0 = E_K(iv) (as produced by beltCTRStart); src may be NULL
+   (keystream only) or equal to dest. key = expanded key (beltKeyExpand2). */
+err_t b2g_beltCTR_dev(void* d_dest, const void* d_src, size_t count, const u32 key[8],
+	const u32 ctr0[4], u64 first_block, void* stream);
+err_t b2g_beltECB_dev(void* d_dest, const void* d_src, size_t nblocks, const u32 key[8],
+	int decrypt, void* stream);
+err_t b2g_beltECBEncrBatch_dev(void* d_blocks, const void* d_keys32, size_t count, void* stream);
+err_t b2g_beltHashBatch_dev(void* d_hashes, const void* d_msgs, size_t msg_len, size_t stride,
+	size_t count, void* stream);
+
+/* ======================================================================= bign (STB 34.101.45) */
+/* include/bee2/crypto/bign.h:65-74 */
+typedef struct
+{
+	size_t l;
+	octet p[64];
+	octet a[64];
+	octet b[64];
+	octet q[64];
+	octet yG[64];
+	octet seed[8];
+} bign_params;
+
+/* drop-in: bign.h (bign_params.c:197-236); only "1.2.112.0.2.0.34.101.45.3.1"
+   (bign-curve256v1) is known to this engine, other names -> ERR_FILE_NOT_FOUND */
+err_t bignParamsStd(bign_params* params, const char* name);
+/* drop-in: bign.h:370-402 (bign_sign.c:349-361, :247-260). Parameter blocks other than
+   bign-curve256v1 return ERR_NOT_IMPLEMENTED (after the reference's structural checks,
+   bign_params.c:244-280). */
+err_t bignVerify(const bign_params* params, const octet oid_der[], size_t oid_len,
+	const octet hash[], const octet sig[], const octet pubkey[]);
+err_t bignSign2(octet sig[], const bign_params* params, const octet oid_der[], size_t oid_len,
+	const octet hash[], const octet privkey[], const void* t, size_t t_len);
+err_t bignPubkeyCalc(octet pubkey[], const bign_params* params, const octet privkey[]);
+/* batch: item i uses hashes+32i, sigs+48i, pubkeys+64i; status[i] = the err_t the
+   reference's bignVerify would return for that item. Return value: ERR_OK when the batch
+   ran (look at status[]), else the parameter/OID/device error. */
+err_t bignVerifyBatch(err_t* status, const bign_params* params, const octet oid_der[],
+	size_t oid_len, const octet* hashes, const octet* sigs, const octet* pubkeys, size_t count);
+err_t bignSign2Batch(err_t* status, octet* sigs, const bign_params* params, const octet oid_der[],
+	size_t oid_len, const octet* hashes, const octet* privkeys, size_t count);
+err_t bignPubkeyCalcBatch(err_t* status, octet* pubkeys, const bign_params* params,
+	const octet* privkeys, size_t count);
+/* batch ecMulA on bign-curve256v1 (ec.c:497-525): b_i = d_i * a_i; scalars are d_len octets
+   each (LE, <= 32); ok[i] = 0 iff the result is the point at infinity. */
+err_t ecMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d_len, size_t count);
+/* device */
+err_t b2g_bignVerifyBatch_dev(void* d_status, const octet oid_der[], size_t oid_len,
+	const void* d_hashes, const void* d_sigs, const void* d_pubkeys, size_t count, void* stream);
+err_t b2g_bignSign2Batch_dev(void* d_status, void* d_sigs, const octet oid_der[], size_t oid_len,
+	const void* d_hashes, const void* d_privkeys, size_t count, void* stream);
+err_t b2g_bignPubkeyCalcBatch_dev(void* d_status, void* d_pubkeys, const void* d_privkeys,
+	size_t count, void* stream);
+err_t b2g_ecMulABatch_dev(void* d_b, void* d_ok, const void* d_a, const void* d_d, size_t d_len,
+	size_t count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEE2_B200_H */

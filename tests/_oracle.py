@@ -1,0 +1,204 @@
+"""Loaders for the CHECKERS used by the tests: oracle/_ref/libbee2oracle.so (our C restatement)
+and, when present, oracle/_ref/libbee2ref_64.so (the unmodified reference built by oracle/Makefile).
+Test infrastructure only."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+OID = bytes.fromhex("06092A7000020022651F51")
+sz = C.c_size_t
+
+_port = None
+_ref = None
+
+
+def port():
+    global _port
+    if _port is None:
+        L = C.CDLL(os.path.join(REF_DIR, "libbee2oracle.so"))
+        L.orc_beltH.restype = C.c_void_p
+        for n in ("orc_bashHash", "orc_beltCTR", "orc_beltECBEncr", "orc_beltECBDecr", "orc_bignVerify128",
+                  "orc_bignSign2_128", "orc_bignPubkeyCalc128"):
+            getattr(L, n).restype = C.c_uint32
+        L.orc_ecMulA128.restype = C.c_int
+        _port = L
+    return _port
+
+
+def ref():
+    """The unmodified reference, or None when it was not built (no /root/reference at build time)."""
+    global _ref
+    if _ref is None:
+        p = os.path.join(REF_DIR, "libbee2ref_64.so")
+        if not os.path.exists(p):
+            return None
+        L = C.CDLL(p)
+        L.beltH.restype = C.c_void_p
+        for n in ("bashHash", "beltCTR", "beltECBEncr", "beltECBDecr", "beltHash", "bignVerify", "bignSign2",
+                  "bignParamsStd", "bignPubkeyCalc"):
+            getattr(L, n).restype = C.c_uint32
+        _ref = L
+    return _ref
+
+
+def beltH() -> bytes:
+    return bytes((C.c_ubyte * 256).from_address(port().orc_beltH()))
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return a
+
+
+# ---- oracle (port) wrappers, bytes in / bytes out
+def bashF(block: bytes) -> bytes:
+    b = C.create_string_buffer(bytes(block), 192)
+    port().orc_bashF(b)
+    return b.raw
+
+
+def bashHash(l: int, src: bytes) -> bytes:
+    out = C.create_string_buffer(64)
+    code = port().orc_bashHash(out, sz(l), bytes(src), sz(len(src)))
+    assert code == 0, code
+    return out.raw[: l // 4]
+
+
+def bashHashBatch(l: int, msgs: np.ndarray) -> np.ndarray:
+    out = np.zeros((msgs.shape[0], l // 4), dtype=np.uint8)
+    for i in range(msgs.shape[0]):
+        out[i] = np.frombuffer(bashHash(l, msgs[i].tobytes()), dtype=np.uint8)
+    return out
+
+
+def beltBlockEncr(block: bytes, key: bytes) -> bytes:
+    k = (C.c_uint32 * 8)()
+    port().orc_beltKeyExpand2(k, bytes(key), sz(len(key)))
+    b = C.create_string_buffer(bytes(block), 16)
+    port().orc_beltBlockEncr2(b, k)
+    return b.raw
+
+
+def beltBlockDecr(block: bytes, key: bytes) -> bytes:
+    k = (C.c_uint32 * 8)()
+    port().orc_beltKeyExpand2(k, bytes(key), sz(len(key)))
+    b = C.create_string_buffer(bytes(block), 16)
+    port().orc_beltBlockDecr2(b, k)
+    return b.raw
+
+
+def beltCTR(src: bytes, key: bytes, iv: bytes) -> bytes:
+    out = C.create_string_buffer(max(len(src), 1))
+    assert port().orc_beltCTR(out, bytes(src), sz(len(src)), bytes(key), sz(len(key)), bytes(iv)) == 0
+    return out.raw[: len(src)]
+
+
+def beltECBEncr(src: bytes, key: bytes) -> bytes:
+    out = C.create_string_buffer(max(len(src), 1))
+    assert port().orc_beltECBEncr(out, bytes(src), sz(len(src)), bytes(key), sz(len(key))) == 0
+    return out.raw[: len(src)]
+
+
+def beltECBDecr(src: bytes, key: bytes) -> bytes:
+    out = C.create_string_buffer(max(len(src), 1))
+    assert port().orc_beltECBDecr(out, bytes(src), sz(len(src)), bytes(key), sz(len(key))) == 0
+    return out.raw[: len(src)]
+
+
+def beltECBEncrMultiKey(blocks: np.ndarray, keys: np.ndarray) -> np.ndarray:
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).copy()
+    k = np.ascontiguousarray(keys, dtype=np.uint8)
+    port().orc_beltECBEncrMultiKey(_p(b), _p(k), sz(b.size // 16))
+    return b
+
+
+def beltHash(src: bytes) -> bytes:
+    out = C.create_string_buffer(32)
+    port().orc_beltHash(out, bytes(src), sz(len(src)))
+    return out.raw
+
+
+def bignVerify(hash_: bytes, sig: bytes, pub: bytes, oid: bytes = OID) -> int:
+    return port().orc_bignVerify128(oid, sz(len(oid)), bytes(hash_), bytes(sig), bytes(pub))
+
+
+def bignSign2(hash_: bytes, priv: bytes, t: bytes = None, oid: bytes = OID):
+    sig = C.create_string_buffer(48)
+    code = port().orc_bignSign2_128(sig, oid, sz(len(oid)), bytes(hash_), bytes(priv), t, sz(len(t) if t else 0))
+    return code, sig.raw
+
+
+def bignPubkeyCalc(priv: bytes):
+    pub = C.create_string_buffer(64)
+    code = port().orc_bignPubkeyCalc128(pub, bytes(priv))
+    return code, pub.raw
+
+
+def ecMulA(a: bytes, d: bytes):
+    out = C.create_string_buffer(64)
+    ok = port().orc_ecMulA128(out, bytes(a), bytes(d), sz(len(d)))
+    return ok, out.raw
+
+
+# ---- reference wrappers (only where ref() is not None)
+class RefParams(C.Structure):
+    _fields_ = [("l", sz), ("p", C.c_ubyte * 64), ("a", C.c_ubyte * 64), ("b", C.c_ubyte * 64),
+                ("q", C.c_ubyte * 64), ("yG", C.c_ubyte * 64), ("seed", C.c_ubyte * 8)]
+
+
+_rp = None
+
+
+def ref_params():
+    global _rp
+    if _rp is None:
+        _rp = RefParams()
+        assert ref().bignParamsStd(C.byref(_rp), b"1.2.112.0.2.0.34.101.45.3.1") == 0
+    return _rp
+
+
+def ref_bashHash(l: int, src: bytes) -> bytes:
+    out = C.create_string_buffer(64)
+    assert ref().bashHash(out, sz(l), bytes(src), sz(len(src))) == 0
+    return out.raw[: l // 4]
+
+
+def ref_beltCTR(src: bytes, key: bytes, iv: bytes) -> bytes:
+    out = C.create_string_buffer(max(len(src), 1))
+    assert ref().beltCTR(out, bytes(src), sz(len(src)), bytes(key), sz(len(key)), bytes(iv)) == 0
+    return out.raw[: len(src)]
+
+
+def ref_beltECBEncr(src: bytes, key: bytes) -> bytes:
+    out = C.create_string_buffer(max(len(src), 1))
+    assert ref().beltECBEncr(out, bytes(src), sz(len(src)), bytes(key), sz(len(key))) == 0
+    return out.raw[: len(src)]
+
+
+def ref_beltHash(src: bytes) -> bytes:
+    out = C.create_string_buffer(32)
+    assert ref().beltHash(out, bytes(src), sz(len(src))) == 0
+    return out.raw
+
+
+def ref_bignVerify(hash_: bytes, sig: bytes, pub: bytes, oid: bytes = OID) -> int:
+    return ref().bignVerify(C.byref(ref_params()), oid, sz(len(oid)), bytes(hash_), bytes(sig), bytes(pub))
+
+
+def ref_bignSign2(hash_: bytes, priv: bytes, t: bytes = None, oid: bytes = OID):
+    sig = C.create_string_buffer(48)
+    code = ref().bignSign2(sig, C.byref(ref_params()), oid, sz(len(oid)), bytes(hash_), bytes(priv), t,
+                           sz(len(t) if t else 0))
+    return code, sig.raw
+
+
+def ref_bignPubkeyCalc(priv: bytes):
+    pub = C.create_string_buffer(64)
+    code = ref().bignPubkeyCalc(pub, C.byref(ref_params()), bytes(priv))
+    return code, pub.raw

@@ -1,0 +1,94 @@
+"""GPU parity: bash-f / bash-hash through the C ABI vs the STB vectors, the reference fixtures
+and the oracle (bit-exact). Mirrors test/crypto/bash_test.c:41-154."""
+import numpy as np
+import pytest
+
+import _oracle as o
+import _vectors as v
+import bee2_b200 as b
+
+pytestmark = pytest.mark.gpu
+KAT = v.load("kat.json")
+REF = v.load("ref_vectors.json")
+H = o.beltH()
+
+
+def test_bashF_A2_and_platform():
+    t = KAT["bashF"][0]
+    assert b.bashF(H[:192]).hex().upper() == t["out"]
+    assert b.lib().bashF_deep() == 0
+
+
+@pytest.mark.parametrize("t", KAT["bashHash"], ids=lambda t: t["id"])
+def test_bashHash_A3_oneshot_and_streaming(t):
+    l, n = t["l"], t["len"]
+    assert b.bashHash(l, H[:n]).hex().upper() == t["out"]
+    # Start/StepH/StepG equivalence (bash_test.c:64-68) with ragged splits, hash-and-continue
+    for cuts in ([n], [0, n], [n // 3, n - n // 3], [1] * min(n, 5) + [max(n - 5, 0)]):
+        st = b.BashHash(l)
+        pos = 0
+        for c in cuts:
+            st.step_h(H[pos:pos + c])
+            pos += c
+        assert pos == n
+        assert st.step_g(l // 4).hex().upper() == t["out"]
+        assert st.step_g(l // 8).hex().upper() == t["out"][: l // 4]      # StepG leaves the state usable
+        assert st.step_v(bytes.fromhex(t["out"])) and not st.step_v(bytes(l // 4))
+        st2 = st.copy()                                                  # states are memcpy-able
+        st.step_h(b"xyz"), st2.step_h(b"xyz")
+        assert st.step_g(l // 4) == st2.step_g(l // 4) == o.bashHash(l, H[:n] + b"xyz")
+
+
+def test_bashHash_errors_match_reference():
+    for l in (0, 8, 17, 272):
+        with pytest.raises(b.Bee2Error) as e:
+            b.bashHash(l, b"abc")
+        assert e.value.code == b.ERR_BAD_PARAMS       # bash_hash.c:122-123
+
+
+def test_reference_fixtures():
+    for t in REF["bashHash"]:
+        assert b.bashHash(t["l"], bytes.fromhex(t["in"])).hex() == t["out"]
+
+
+@pytest.mark.parametrize("l", [16 * i for i in range(1, 17)])
+def test_batch_every_level_random_lengths(l):
+    rng = np.random.default_rng(l)
+    rate = 192 - l // 2
+    for msg_len in sorted({0, 1, rate - 1, rate, rate + 1, 3 * rate, int(rng.integers(1, 900))}):
+        for stride in {msg_len, msg_len + 3, (msg_len + 15) // 16 * 16 + 16}:
+            cnt = 37
+            buf = rng.integers(0, 256, size=(cnt, stride), dtype=np.uint8)
+            got = b.bashHashBatch(l, buf, msg_len=msg_len, stride=stride, count=cnt)
+            want = o.bashHashBatch(l, np.ascontiguousarray(buf[:, :msg_len]))
+            assert np.array_equal(got, want), (l, msg_len, stride)
+
+
+def test_bashFBatch_random():
+    rng = np.random.default_rng(1)
+    st = rng.integers(0, 256, size=(300, 192), dtype=np.uint8)
+    got = b.bashFBatch(st)
+    for i in range(0, 300, 7):
+        assert got[i].tobytes() == o.bashF(st[i].tobytes())
+    assert b.bashFBatch(np.zeros((0, 192), dtype=np.uint8)).size == 0
+
+
+def test_config3_shape_device_level():
+    """BASELINE config 3 shape (4 KiB messages, bash-512) on device-resident data: sampled digests
+    against the oracle, and sharding invariance (any split of the batch gives the same digests)."""
+    torch = pytest.importorskip("torch")
+    cnt, n = 1 << 15, 4096
+    g = torch.Generator(device="cuda").manual_seed(3)
+    msgs = torch.randint(0, 256, (cnt, n), dtype=torch.uint8, device="cuda", generator=g)
+    out = torch.empty((cnt, 64), dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    b.bashHashBatch_dev(out.data_ptr(), 256, msgs.data_ptr(), n, n, cnt, s)
+    out2 = torch.empty_like(out)
+    cut = 12345
+    b.bashHashBatch_dev(out2.data_ptr(), 256, msgs.data_ptr(), n, n, cut, s)
+    b.bashHashBatch_dev(out2[cut:].data_ptr(), 256, msgs[cut:].data_ptr(), n, n, cnt - cut, s)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    host, hmsg = out.cpu().numpy(), msgs.cpu().numpy()
+    for i in list(range(0, cnt, 997)) + [cnt - 1]:
+        assert host[i].tobytes() == o.bashHash(256, hmsg[i].tobytes())

@@ -1,0 +1,176 @@
+"""GPU parity: belt block / ECB / CTR / hash through the C ABI vs the STB vectors, the reference
+fixtures and the oracle (bit-exact). Mirrors test/crypto/belt_test.c:174-215, :288-339, :423-448, :593-631."""
+import numpy as np
+import pytest
+
+import _oracle as o
+import _vectors as v
+import bee2_b200 as b
+
+pytestmark = pytest.mark.gpu
+KAT = v.load("kat.json")
+REF = v.load("ref_vectors.json")
+H = o.beltH()
+R = lambda e: v.resolve(e, H, o.beltHash)  # noqa: E731
+
+
+def test_beltH():
+    assert b.beltH() == H
+
+
+def test_block_A1_A4_all_flavours():
+    for t in KAT["beltBlock"]:
+        f = b.beltBlockEncr if t["op"] == "encr" else b.beltBlockDecr
+        for flavour in (1, 2, 3):
+            assert f(R(t["in"]), R(t["key"]), flavour).hex().upper() == t["out"]
+    t = KAT["beltBlock"][0]
+    assert b.beltBlockDecr(bytes.fromhex(t["out"]), R(t["key"])) == R(t["in"])
+    # 16- and 24-octet keys go through beltKeyExpand2 (belt_block.c:88-106)
+    for klen in (16, 24):
+        assert b.beltBlockEncr(H[:16], H[128:128 + klen]) == o.beltBlockEncr(H[:16], H[128:128 + klen])
+
+
+def test_zerosum():
+    x = np.zeros((128, 4), dtype=np.uint32)
+    x[:, 0] = KAT["beltZerosum"]["x"]
+    st = b.BeltECB(bytes(32))
+    buf = x.view(np.uint8).reshape(-1).copy()
+    st.step_e(buf)
+    acc = np.bitwise_xor.reduce(x ^ buf.view(np.uint32).reshape(128, 4), axis=0)
+    assert not acc.any()
+
+
+def test_ecb_A9_A10_split_calls_and_stealing():
+    for t in KAT["beltECB"]:
+        src, key = R(t["in"]), R(t["key"])
+        one = (b.beltECBEncr if t["op"] == "encr" else b.beltECBDecr)(src, key)
+        assert one.hex().upper() == t["out"], t["id"]
+        st = b.BeltECB(key)
+        buf = np.frombuffer(src, dtype=np.uint8).copy()
+        pos = 0
+        for c in t["split"]:
+            (st.step_e if t["op"] == "encr" else st.step_d)(buf[pos:pos + c])
+            pos += c
+        assert buf.tobytes() == one
+    with pytest.raises(b.Bee2Error) as e:
+        b.beltECBEncr(H[:15], H[128:160])
+    assert e.value.code == b.ERR_BAD_INPUT             # belt_ecb.c:117-118
+
+
+def test_ctr_A15_A16_split_calls():
+    for t in KAT["beltCTR"]:
+        src, key, iv = R(t["in"]), R(t["key"]), R(t["iv"])
+        assert b.beltCTR(src, key, iv).hex().upper() == t["out"], t["id"]
+        st = b.BeltCTR(key, iv)
+        buf = np.frombuffer(src, dtype=np.uint8).copy()
+        pos = 0
+        for c in t["split"]:
+            st.step_e(buf[pos:pos + c])
+            pos += c
+        assert buf.tobytes().hex().upper() == t["out"]
+    with pytest.raises(b.Bee2Error) as e:
+        b.beltCTR(H[:16], H[128:145], H[192:208])
+    assert e.value.code == b.ERR_BAD_INPUT
+
+
+def test_hash_A23():
+    for t in KAT["beltHash"]:
+        assert b.beltHash(R(t["in"])).hex().upper() == t["out"]
+
+
+def test_reference_fixtures():
+    for t in REF["beltCTR"]:
+        assert b.beltCTR(bytes.fromhex(t["in"]), bytes.fromhex(t["key"]), bytes.fromhex(t["iv"])).hex() == t["out"]
+    for t in REF["beltECB"]:
+        assert b.beltECBEncr(bytes.fromhex(t["in"]), bytes.fromhex(t["key"])).hex() == t["out"]
+        assert b.beltECBDecr(bytes.fromhex(t["out"]), bytes.fromhex(t["key"])).hex() == t["in"]
+    for t in REF["beltHash"]:
+        assert b.beltHash(bytes.fromhex(t["in"])).hex() == t["out"]
+
+
+def test_ctr_random_lengths_and_streaming():
+    rng = np.random.default_rng(11)
+    for n in [1, 15, 16, 17, 255, 4096, 100_003, (1 << 20) + 5]:
+        key = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+        iv = rng.integers(0, 256, 16, dtype=np.uint8).tobytes()
+        src = rng.integers(0, 256, n, dtype=np.uint8)
+        want = o.beltCTR(src.tobytes(), key, iv)
+        assert b.beltCTR(src.tobytes(), key, iv) == want
+        assert b.beltCTRKeystream(n, key, iv) == o.beltCTR(bytes(n), key, iv)
+        st, buf, pos = b.BeltCTR(key, iv), src.copy(), 0
+        while pos < n:                      # ragged steps exercise the keystream reserve
+            c = min(int(rng.integers(1, max(2, n // 3))), n - pos)
+            st.step_e(buf[pos:pos + c])
+            pos += c
+        assert buf.tobytes() == want
+    # counter carry across 2^32 and 2^64 (belt_ctr.c:27-35)
+    key, n = bytes(range(32)), 16 * 40
+    ks = b.BeltCTR(key, bytes(16))
+    want = o.beltCTR(bytes(n), key, bytes(16))
+    out = np.zeros(n, dtype=np.uint8)
+    ks.step_e(out)
+    assert out.tobytes() == want
+
+
+def test_ctr_counter_wrap_device_level():
+    torch = pytest.importorskip("torch")
+    key = np.arange(8, dtype=np.uint32)
+    for ctr in ([0xFFFFFFF0, 0, 0, 0], [0xFFFFFFF8, 0xFFFFFFFF, 7, 0], [0xFFFFFFFE, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF]):
+        c = np.array(ctr, dtype=np.uint32)
+        n = 16 * 64
+        out = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        b.beltCTR_dev(out.data_ptr(), 0, n, key, c, 0, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        # oracle: encrypt the incremented counters one by one
+        val = int.from_bytes(c.tobytes(), "little")
+        want = b"".join(o.beltBlockEncr(((val + j + 1) % (1 << 128)).to_bytes(16, "little"), key.tobytes())
+                        for j in range(64))
+        assert out.cpu().numpy().tobytes() == want
+
+
+def test_ecb_multikey_batch_config5_shape():
+    rng = np.random.default_rng(3)
+    cnt = 20_011
+    blocks = rng.integers(0, 256, (cnt, 16), dtype=np.uint8)
+    keys = rng.integers(0, 256, (cnt, 32), dtype=np.uint8)
+    assert np.array_equal(b.beltECBEncrBatch(blocks, keys), o.beltECBEncrMultiKey(blocks, keys))
+
+
+def test_hash_batch_random():
+    rng = np.random.default_rng(4)
+    for n in (0, 1, 31, 32, 33, 75, 96, 1001):
+        msgs = rng.integers(0, 256, (50, n), dtype=np.uint8)
+        got = b.beltHashBatch(msgs)
+        for i in range(50):
+            assert got[i].tobytes() == o.beltHash(msgs[i].tobytes())
+
+
+def test_config2_shape_device_level():
+    """BASELINE config 2 shape on device-resident buffers (256 MiB here; bench.py runs the full
+    1 GiB): keystream equals the oracle on the head, offsets are consistent, and E(E(x)) = x."""
+    torch = pytest.importorskip("torch")
+    n = 1 << 28
+    st = b.BeltCTR(H[128:160], H[192:208])
+    key, ctr = st.key_words, st.ctr_words
+    s = torch.cuda.current_stream().cuda_stream
+    ks = torch.empty(n, dtype=torch.uint8, device="cuda")
+    b.beltCTR_dev(ks.data_ptr(), 0, n, key, ctr, 0, s)
+    head = 1 << 22
+    torch.cuda.synchronize()
+    assert ks[:head].cpu().numpy().tobytes() == o.beltCTR(bytes(head), H[128:160], H[192:208])
+    # any shard computed with its block offset equals the same slice of the whole stream
+    off_blocks, m = (n // 16) // 3, 1 << 20
+    part = torch.empty(m, dtype=torch.uint8, device="cuda")
+    b.beltCTR_dev(part.data_ptr(), 0, m, key, ctr, off_blocks, s)
+    torch.cuda.synchronize()
+    assert torch.equal(part, ks[16 * off_blocks:16 * off_blocks + m])
+    # involution on data, in place
+    g = torch.Generator(device="cuda").manual_seed(9)
+    data = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda", generator=g)
+    ref = data.clone()
+    b.beltCTR_dev(data.data_ptr(), data.data_ptr(), n, key, ctr, 0, s)
+    torch.cuda.synchronize()
+    assert torch.equal(data, ref ^ ks)
+    b.beltCTR_dev(data.data_ptr(), data.data_ptr(), n, key, ctr, 0, s)
+    torch.cuda.synchronize()
+    assert torch.equal(data, ref)

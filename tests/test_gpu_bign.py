@@ -1,0 +1,213 @@
+"""GPU parity: bign on bign-curve256v1 through the C ABI vs the STB vectors, the reference fixtures
+and the oracle (bit-exact statuses / signatures / points). Mirrors test/crypto/bign_test.c:303-457 and
+the differential style of test/math/ec_test.c:342-470."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import _oracle as o
+import _vectors as v
+import bee2_b200 as b
+
+pytestmark = pytest.mark.gpu
+KAT = v.load("kat.json")
+REF = v.load("ref_vectors.json")
+H = o.beltH()
+R = lambda e: v.resolve(e, H, o.beltHash)  # noqa: E731
+OID = b.OID_BELT_HASH_DER
+Q = v.Q
+P = (1 << 256) - 189
+
+
+def A(x):
+    return np.frombuffer(bytes(x), dtype=np.uint8).copy()
+
+
+def test_params_std_and_checks():
+    p = b.bignParamsStd()
+    assert p.l == 128 and bytes(p.p)[:32] == P.to_bytes(32, "little") and bytes(p.q)[:32] == Q.to_bytes(32, "little")
+    with pytest.raises(b.Bee2Error) as e:
+        b.bignParamsStd("1.2.3")
+    assert e.value.code == b.ERR_FILE_NOT_FOUND
+    z = bytes(32)
+    bad = b.bignParamsStd()
+    bad.l = 100
+    assert b.bignVerify(bad, OID, z, bytes(48), bytes(64)) == b.ERR_NOT_IMPLEMENTED     # bign_params.c:251-252
+    bad = b.bignParamsStd()
+    bad.p[0] = 0x41
+    assert b.bignVerify(bad, OID, z, bytes(48), bytes(64)) == b.ERR_BAD_PARAMS          # p mod 4 != 3
+    other = b.bignParamsStd()
+    other.b[0] ^= 2                                                                     # a valid-looking other curve
+    assert b.bignVerify(other, OID, z, bytes(48), bytes(64)) == b.ERR_NOT_IMPLEMENTED
+    p = b.bignParamsStd()
+    assert b.bignVerify(p, b"\x06\x02\x80\x01", z, bytes(48), bytes(64)) == b.ERR_BAD_OID
+    assert b.bignVerify(p, b"\x05\x00", z, bytes(48), bytes(64)) == b.ERR_BAD_OID
+
+
+def test_G1_G2_G3_and_negatives():
+    p, k = b.bignParamsStd(), KAT["bign"]
+    priv, pub = bytes.fromhex(k["privkey"]), bytes.fromhex(k["pubkey"])
+    assert b.bignPubkeyCalc(p, priv) == pub                                    # G.1 (bign_test.c:320-327)
+    for t in k["verify"]:
+        h, sig = R(t["hash"]), bytearray(bytes.fromhex(t["sig"]))
+        assert b.bignVerify(p, OID, h, sig, pub) == b.ERR_OK
+        sig[0] ^= 1
+        assert b.bignVerify(p, OID, h, sig, pub) == b.ERR_BAD_SIG              # bign_test.c:349-351
+        sig[0] ^= 1
+        bad = bytearray(pub)
+        bad[0] ^= 1
+        assert b.bignVerify(p, OID, h, sig, bad) == o.bignVerify(h, sig, bad) != b.ERR_OK
+
+
+def test_G6_G7_sign2():
+    p, k = b.bignParamsStd(), KAT["bign"]
+    priv, pub = bytes.fromhex(k["privkey"]), bytes.fromhex(k["pubkey"])
+    for t in k["sign2_nonce"]:
+        h = R(t["hash"])
+        sig = b.bignSign2(p, OID, h, priv, R(t["t"]))
+        assert v.sign2_nonce(sig, priv, h).hex().upper() == t["k"], t["id"]
+        assert (0, sig) == o.bignSign2(h, priv, R(t["t"]))
+        assert b.bignVerify(p, OID, h, sig, pub) == b.ERR_OK
+    with pytest.raises(b.Bee2Error) as e:
+        b.bignSign2(p, OID, bytes(32), bytes(32))                              # d = 0
+    assert e.value.code == b.ERR_BAD_PRIVKEY
+    with pytest.raises(b.Bee2Error) as e:
+        b.bignSign2(p, OID, bytes(32), Q.to_bytes(32, "little"))               # d = q
+    assert e.value.code == b.ERR_BAD_PRIVKEY
+
+
+def test_reference_fixtures():
+    p = b.bignParamsStd()
+    for t in REF["bign"]:
+        priv, pub, h, sig = (bytes.fromhex(t[k]) for k in ("privkey", "pubkey", "hash", "sig"))
+        tt = bytes.fromhex(t["t"]) if t["t"] else None
+        assert b.bignPubkeyCalc(p, priv) == pub
+        assert b.bignSign2(p, OID, h, priv, tt) == sig
+        assert b.bignVerify(p, OID, h, sig, pub) == t["verify"]
+        bad = t["bad"]
+        assert b.bignVerify(p, OID, bytes.fromhex(bad["hash"]), bytes.fromhex(bad["sig"]),
+                            bytes.fromhex(bad["pubkey"])) == bad["verify"]
+
+
+def _corrupt(rng, hashes, sigs, pubs):
+    """~1/3 of the items get one of the SURVEY §8d corruptions."""
+    n = hashes.shape[0]
+    for i in range(n):
+        kind = int(rng.integers(0, 18))
+        if kind == 0:
+            sigs[i, int(rng.integers(0, 16))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:
+            sigs[i, 16 + int(rng.integers(0, 32))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 2:
+            hashes[i, int(rng.integers(0, 32))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 3:
+            pubs[i, int(rng.integers(0, 64))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 4:
+            sigs[i, 16:] = 0xFF                       # s1 >= q
+        elif kind == 5:
+            pubs[i, (0 if i & 1 else 32):][:32] = 0xFF  # Qx or Qy >= p
+
+
+def test_verify_batch_random_vs_oracle():
+    rng = np.random.default_rng(2)
+    p, n = b.bignParamsStd(), 600
+    priv = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    priv[:, 31] &= 0x7F
+    hashes = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    hashes[::5, 16:] = 0xFF                                                    # H >= q path (bign_sign.c:320-326)
+    st, pubs = b.bignPubkeyCalcBatch(p, priv)
+    assert (st == 0).all()
+    st, sigs = b.bignSign2Batch(p, OID, hashes, priv)
+    assert (st == 0).all()
+    for i in range(0, n, 40):
+        assert o.bignPubkeyCalc(priv[i].tobytes()) == (0, pubs[i].tobytes())
+        assert o.bignSign2(hashes[i].tobytes(), priv[i].tobytes()) == (0, sigs[i].tobytes())
+    _corrupt(rng, hashes, sigs, pubs)
+    got = b.bignVerifyBatch(p, OID, hashes, sigs, pubs)
+    want = np.array([o.bignVerify(hashes[i].tobytes(), sigs[i].tobytes(), pubs[i].tobytes()) for i in range(n)],
+                    dtype=np.uint32)
+    assert np.array_equal(got, want)
+    assert {0, 505, 510} <= set(int(x) for x in got)
+
+
+def test_exceptional_points():
+    """Keys that make the two halves of s1 G + s0 Q collide (Q = +-G, +-2G, ...) — SURVEY §7 hard parts."""
+    p = b.bignParamsStd()
+    rng = np.random.default_rng(8)
+    ds = [1, 2, 3, Q - 1, Q - 2, 1 << 128, (1 << 128) + 1, Q - (1 << 128)]
+    priv = np.stack([A(d.to_bytes(32, "little")) for d in ds])
+    hashes = rng.integers(0, 256, (len(ds), 32), dtype=np.uint8)
+    st, pubs = b.bignPubkeyCalcBatch(p, priv)
+    assert (st == 0).all()
+    G = bytes(32) + bytes(b.bignParamsStd().yG)[:32]
+    assert pubs[0].tobytes() == G
+    negG = bytes(32) + (P - int.from_bytes(G[32:], "little")).to_bytes(32, "little")
+    assert pubs[3].tobytes() == negG
+    st, sigs = b.bignSign2Batch(p, OID, hashes, priv)
+    assert (st == 0).all()
+    for i in range(len(ds)):
+        assert o.bignSign2(hashes[i].tobytes(), priv[i].tobytes()) == (0, sigs[i].tobytes())
+        assert o.bignPubkeyCalc(priv[i].tobytes()) == (0, pubs[i].tobytes())
+    assert (b.bignVerifyBatch(p, OID, hashes, sigs, pubs) == 0).all()
+    # R = O: s1 G + s0 Q with Q = G needs s1 + H = -(s0 + 2^128) mod q  -> BAD_SIG (bign_sign.c:332-336)
+    s0 = rng.integers(0, 256, 16, dtype=np.uint8).tobytes()
+    hh = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+    hq = int.from_bytes(hh, "little") % Q if int.from_bytes(hh, "little") >= Q else int.from_bytes(hh, "little")
+    s1 = (-(int.from_bytes(s0, "little") + (1 << 128)) - hq) % Q
+    sig = s0 + s1.to_bytes(32, "little")
+    assert b.bignVerify(p, OID, hh, sig, G) == o.bignVerify(hh, sig, G) == b.ERR_BAD_SIG
+    # same scalars against -G: R = 2 s0' G etc. — just has to agree with the oracle
+    assert b.bignVerify(p, OID, hh, sig, negG) == o.bignVerify(hh, sig, negG)
+    # all-zero inputs: Q = (0,0) is not on the curve; statuses still agree
+    assert b.bignVerify(p, OID, bytes(32), bytes(48), bytes(64)) == o.bignVerify(bytes(32), bytes(48), bytes(64))
+
+
+def test_ecMulA_batch_vs_oracle():
+    rng = np.random.default_rng(6)
+    p, n = b.bignParamsStd(), 48
+    priv = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    priv[:, 31] &= 0x7F
+    _, pts = b.bignPubkeyCalcBatch(p, priv)
+    for d_len in (32, 16, 2):
+        sc = rng.integers(0, 256, (n, d_len), dtype=np.uint8)
+        sc[0] = 0                                        # 0 * A = O -> ok = 0 (ec.c:497-525 returns FALSE)
+        sc[1] = 0
+        sc[1, 0] = 1                                     # 1 * A = A
+        got, ok = b.ecMulABatch(pts, sc)
+        for i in range(n):
+            want_ok, want = o.ecMulA(pts[i].tobytes(), sc[i].tobytes())
+            assert ok[i] == want_ok
+            if want_ok:
+                assert got[i].tobytes() == want
+        assert ok[0] == 0 and got[1].tobytes() == pts[1].tobytes()
+    # q * A = O and (q + 1) * A = A: scalars may exceed the group order
+    sc = np.stack([A(Q.to_bytes(32, "little")), A((Q + 1).to_bytes(32, "little"))])
+    got, ok = b.ecMulABatch(pts[:2].copy(), sc)
+    assert ok[0] == 0 and ok[1] == 1 and got[1].tobytes() == pts[1].tobytes()
+
+
+@pytest.mark.skipif(o.ref() is None, reason="oracle/_ref/libbee2ref_64.so not on this machine")
+def test_config4_shape_vs_reference_harness():
+    """A 2^13 slice of BASELINE config 4 (2^18 sigs): every status equals the unmodified
+    reference's bign128Verify, run multi-threaded through oracle/cpu_harness.c."""
+    rng = np.random.default_rng(4)
+    p, n = b.bignParamsStd(), 1 << 13
+    priv = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    priv[:, 31] &= 0x7F
+    hashes = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    _, pubs = b.bignPubkeyCalcBatch(p, priv)
+    st, sigs = b.bignSign2Batch(p, OID, hashes, priv)
+    assert (st == 0).all()
+    _corrupt(rng, hashes, sigs, pubs)
+    got = b.bignVerifyBatch(p, OID, hashes, sigs, pubs)
+    hs = C.CDLL(os.path.join(o.REF_DIR, "libcpuharness.so"))
+    hs.harness_bign_verify.restype = C.c_double
+    want = np.zeros(n, dtype=np.uint32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    dt = hs.harness_bign_verify(os.path.join(o.REF_DIR, "libbee2ref_64.so").encode(), 0, vp(want), vp(hashes),
+                                vp(sigs), vp(pubs), C.c_size_t(n), os.cpu_count() or 1)
+    assert dt > 0
+    assert np.array_equal(got, want)
+    assert (got == 0).sum() > n // 2

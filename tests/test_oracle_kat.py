@@ -1,0 +1,134 @@
+"""Pins the oracle (oracle/bee2_oracle.c): every STB annex vector the reference's tests hold for
+the hot path, the reference-generated fixtures, and — when oracle/_ref/libbee2ref_64.so exists —
+live differential runs against the unmodified reference. CPU only."""
+import numpy as np
+import pytest
+
+import _oracle as o
+import _vectors as v
+
+KAT = v.load("kat.json")
+REF = v.load("ref_vectors.json")
+H = o.beltH()
+R = lambda e: v.resolve(e, H, o.beltHash)  # noqa: E731
+
+
+def test_beltH_is_the_standard_sbox():
+    # first row of the S-box table (STB 34.101.31), and bijectivity
+    assert H[:16].hex().upper() == "B194BAC80A08F53B366D008E584A5DE4"
+    assert sorted(H) == list(range(256))
+
+
+def test_bashF_A2():
+    for t in KAT["bashF"]:
+        assert o.bashF(R(t["in"])).hex().upper() == t["out"]
+
+
+@pytest.mark.parametrize("t", KAT["bashHash"], ids=lambda t: t["id"])
+def test_bashHash_A3(t):
+    assert o.bashHash(t["l"], H[: t["len"]]).hex().upper() == t["out"]
+
+
+def test_belt_block_A1_A4():
+    for t in KAT["beltBlock"]:
+        f = o.beltBlockEncr if t["op"] == "encr" else o.beltBlockDecr
+        assert f(R(t["in"]), R(t["key"])).hex().upper() == t["out"]
+    t = KAT["beltBlock"][0]
+    assert o.beltBlockDecr(bytes.fromhex(t["out"]), R(t["key"])) == R(t["in"])
+
+
+def test_belt_zerosum():
+    acc = np.zeros(4, dtype=np.uint32)
+    for x in KAT["beltZerosum"]["x"]:
+        blk = np.array([x, 0, 0, 0], dtype=np.uint32)
+        acc ^= blk ^ np.frombuffer(o.beltBlockEncr(blk.tobytes(), bytes(32)), dtype=np.uint32)
+    assert not acc.any()
+
+
+def test_belt_ecb_A9_A10():
+    for t in KAT["beltECB"]:
+        f = o.beltECBEncr if t["op"] == "encr" else o.beltECBDecr
+        assert f(R(t["in"]), R(t["key"])).hex().upper() == t["out"], t["id"]
+
+
+def test_belt_ctr_A15_A16():
+    for t in KAT["beltCTR"]:
+        assert o.beltCTR(R(t["in"]), R(t["key"]), R(t["iv"])).hex().upper() == t["out"], t["id"]
+
+
+def test_belt_hash_A23():
+    for t in KAT["beltHash"]:
+        assert o.beltHash(R(t["in"])).hex().upper() == t["out"], t["id"]
+
+
+def test_bign_G1_G2_G3_and_negatives():
+    b = KAT["bign"]
+    priv, pub = bytes.fromhex(b["privkey"]), bytes.fromhex(b["pubkey"])
+    assert o.bignPubkeyCalc(priv) == (0, pub)
+    for t in b["verify"]:
+        h, sig = R(t["hash"]), bytearray(bytes.fromhex(t["sig"]))
+        assert o.bignVerify(h, sig, pub) == 0
+        sig[0] ^= 1
+        assert o.bignVerify(h, sig, pub) == 510        # bign_test.c:349-351
+        sig[0] ^= 1
+        bad = bytearray(pub)
+        bad[0] ^= 1
+        assert o.bignVerify(h, sig, bad) != 0           # bign_test.c:352-354
+
+
+def test_bign_G6_G7_sign2_nonces():
+    b = KAT["bign"]
+    priv, pub = bytes.fromhex(b["privkey"]), bytes.fromhex(b["pubkey"])
+    for t in b["sign2_nonce"]:
+        h = R(t["hash"])
+        code, sig = o.bignSign2(h, priv, R(t["t"]))
+        assert code == 0
+        assert v.sign2_nonce(sig, priv, h).hex().upper() == t["k"], t["id"]
+        assert o.bignVerify(h, sig, pub) == 0
+
+
+def test_reference_fixtures():
+    for t in REF["bashHash"]:
+        assert o.bashHash(t["l"], bytes.fromhex(t["in"])).hex() == t["out"]
+    for t in REF["beltCTR"]:
+        assert o.beltCTR(bytes.fromhex(t["in"]), bytes.fromhex(t["key"]), bytes.fromhex(t["iv"])).hex() == t["out"]
+    for t in REF["beltECB"]:
+        assert o.beltECBEncr(bytes.fromhex(t["in"]), bytes.fromhex(t["key"])).hex() == t["out"]
+        assert o.beltECBDecr(bytes.fromhex(t["out"]), bytes.fromhex(t["key"])).hex() == t["in"]
+    for t in REF["beltHash"]:
+        assert o.beltHash(bytes.fromhex(t["in"])).hex() == t["out"]
+    for t in REF["bign"]:
+        priv, pub, h = (bytes.fromhex(t[k]) for k in ("privkey", "pubkey", "hash"))
+        tt = bytes.fromhex(t["t"]) if t["t"] else None
+        assert o.bignPubkeyCalc(priv) == (0, pub)
+        assert o.bignSign2(h, priv, tt) == (0, bytes.fromhex(t["sig"]))
+        assert o.bignVerify(h, bytes.fromhex(t["sig"]), pub) == t["verify"] == 0
+        bad = t["bad"]
+        assert o.bignVerify(bytes.fromhex(bad["hash"]), bytes.fromhex(bad["sig"]), bytes.fromhex(bad["pubkey"])) == bad["verify"]
+
+
+@pytest.mark.skipif(o.ref() is None, reason="oracle/_ref/libbee2ref_64.so not built here")
+def test_live_differential_against_reference():
+    rng = np.random.default_rng(5)
+    rb = lambda n: rng.integers(0, 256, size=n, dtype=np.uint8).tobytes()  # noqa: E731
+    for _ in range(40):
+        l = 16 * int(rng.integers(1, 17))
+        m = rb(int(rng.integers(0, 700)))
+        assert o.bashHash(l, m) == o.ref_bashHash(l, m)
+        k, iv = rb(int(rng.choice([16, 24, 32]))), rb(16)
+        assert o.beltCTR(m, k, iv) == o.ref_beltCTR(m, k, iv)
+        assert o.beltHash(m) == o.ref_beltHash(m)
+        if len(m) >= 16:
+            assert o.beltECBEncr(m, k) == o.ref_beltECBEncr(m, k)
+    for i in range(6):
+        d = bytearray(rb(32))
+        d[31] &= 0x7F
+        h = rb(32)
+        code, sig = o.bignSign2(h, bytes(d))
+        assert (code, sig) == o.ref_bignSign2(h, bytes(d))
+        code, pub = o.bignPubkeyCalc(bytes(d))
+        assert (code, pub) == o.ref_bignPubkeyCalc(bytes(d))
+        assert o.bignVerify(h, sig, pub) == o.ref_bignVerify(h, sig, pub) == 0
+        s2 = bytearray(sig)
+        s2[i] ^= 4
+        assert o.bignVerify(h, s2, pub) == o.ref_bignVerify(h, bytes(s2), pub) == 510
