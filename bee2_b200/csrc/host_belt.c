@@ -43,9 +43,13 @@ void beltKeyExpand(octet key_[32], const octet key[], size_t len)
 
 void beltKeyExpand2(u32 key_[8], const octet key[], size_t len)
 {
-	octet t[32];
-	beltKeyExpand(t, key, len);
-	memcpy(key_, t, 32);   /* little-endian host: u32From is a copy (u32.c:233-244) */
+	memcpy(key_, key, len);   /* little-endian host: u32From is a copy (u32.c:233-244) */
+	if (len == 16)
+		key_[4] = key_[0], key_[5] = key_[1], key_[6] = key_[2], key_[7] = key_[3];
+	else if (len == 24)
+		/* word-wise, as STB 34.101.31 defines it; note that the reference's octet variant above
+		   combines 8-octet halves instead (belt_block.c:82-85 vs :101-104) — both are mirrored */
+		key_[6] = key_[0] ^ key_[1] ^ key_[2], key_[7] = key_[3] ^ key_[4] ^ key_[5];
 }
 
 /* ---------------------------------------------------------------- single blocks */
