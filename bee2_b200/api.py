@@ -61,7 +61,8 @@ _LIB: Optional[C.CDLL] = None
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbee2_b200.so")
+    # BEE2_B200_LIB: an alternative build of the same library (kernel-variant experiments)
+    return os.environ.get("BEE2_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbee2_b200.so")
 
 
 def lib() -> C.CDLL:

@@ -19,6 +19,9 @@
 #include "belt_dev.cuh"
 
 #define BIGN_THREADS 128
+#ifndef BIGN_MIN_BLOCKS
+#define BIGN_MIN_BLOCKS 4
+#endif
 #define BIGN_MAX_OID 64
 #define BIGN_MAX_T 64
 
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(BIGN_THREADS) bign_gtab_kernel(uint4* gtab)
 }
 
 // bignVerifyEc per item (bign_sign.c:268-347, l = 128)
-__global__ void __launch_bounds__(BIGN_THREADS)
+__global__ void __launch_bounds__(BIGN_THREADS, BIGN_MIN_BLOCKS)
 bign_verify_kernel(u32* __restrict__ status, const u8* __restrict__ hashes, const u8* __restrict__ sigs,
 	const u8* __restrict__ pubkeys, u64 count, const OidArg oid, const uint4* __restrict__ gtab)
 {
@@ -301,7 +304,7 @@ __device__ __forceinline__ void wbl32(const BeltSmallT& S, u32 (&r)[8], const u3
 }
 
 // bignSign2Ec per item (bign_sign.c:140-245, l = 128)
-__global__ void __launch_bounds__(BIGN_THREADS)
+__global__ void __launch_bounds__(BIGN_THREADS, BIGN_MIN_BLOCKS)
 bign_sign2_kernel(u32* __restrict__ status, u8* __restrict__ sigs, const u8* __restrict__ hashes,
 	const u8* __restrict__ privkeys, u64 count, const OidArg oid, const TArg targ,
 	const uint4* __restrict__ gtab)
@@ -370,7 +373,7 @@ bign_sign2_kernel(u32* __restrict__ status, u8* __restrict__ sigs, const u8* __r
 }
 
 // bignPubkeyCalc per item (bign_misc.c:369-412): Q = d G, 0 < d < q
-__global__ void __launch_bounds__(BIGN_THREADS)
+__global__ void __launch_bounds__(BIGN_THREADS, BIGN_MIN_BLOCKS)
 bign_pubkey_kernel(u32* __restrict__ status, u8* __restrict__ pubkeys, const u8* __restrict__ privkeys,
 	u64 count, const uint4* __restrict__ gtab)
 {
@@ -399,7 +402,7 @@ bign_pubkey_kernel(u32* __restrict__ status, u8* __restrict__ pubkeys, const u8*
 }
 
 // ecMulA per item (ec.c:497-525): b = d * a, affine in/out; ok = 0 iff the result is O
-__global__ void __launch_bounds__(BIGN_THREADS)
+__global__ void __launch_bounds__(BIGN_THREADS, BIGN_MIN_BLOCKS)
 ecp_mul_kernel(u8* __restrict__ out, int* __restrict__ ok, const u8* __restrict__ pts,
 	const u8* __restrict__ scalars, u32 d_len, u64 count)
 {

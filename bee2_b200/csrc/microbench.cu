@@ -11,19 +11,24 @@
 #define MB_ILP 8
 #define MB_UNROLL 32
 
-enum { MB_LOP3 = 0, MB_SHF = 1, MB_PRMT = 2, MB_IADD3 = 3, MB_IMAD = 4, MB_IMAD_WIDE = 5, MB_LDS = 6, MB_MIX_LOP3_IMADW = 7 };
+enum { MB_LOP3 = 0, MB_SHF = 1, MB_PRMT = 2, MB_IADD3 = 3, MB_IMAD = 4, MB_IMAD_WIDE = 5, MB_LDS = 6, MB_MIX_LOP3_IMADW = 7,
+	MB_MIX_LOP3_IMAD = 8, MB_MIX_LOP3_FFMA = 9, MB_IMAD_HI = 10, MB_MIX_LOP3_LDS = 11, MB_FFMA = 12 };
+#define MB_IS_MIX(k) ((k) == MB_MIX_LOP3_IMADW || (k) == MB_MIX_LOP3_IMAD || (k) == MB_MIX_LOP3_FFMA || (k) == MB_MIX_LOP3_LDS)
 
 template <int KIND>
 __global__ void __launch_bounds__(1024) mb_kernel(u32* out, u32 iters, u32 a, u32 b, u32 sh)
 {
 	__shared__ u32 sm[32 * 64];
-	u32 x[MB_ILP];
+	u32 x[MB_ILP], y[MB_ILP];
 	u64 w[MB_ILP];
+	float f[MB_ILP];
+	const float fa = __uint_as_float(0x3F800001u + (a & 1)), fb = __uint_as_float(b & 0x007FFFFFu);
 #pragma unroll
 	for (int i = 0; i < MB_ILP; ++i)
 	{
-		x[i] = KIND == MB_LDS ? ((threadIdx.x + i) & 63u) << 5 : threadIdx.x * 2654435761u + i * a;
+		x[i] = (KIND == MB_LDS || KIND == MB_MIX_LOP3_LDS) ? ((threadIdx.x + i) & 63u) << 5 : threadIdx.x * 2654435761u + i * a;
 		w[i] = ((u64)x[i] << 32) | (b + i);
+		y[i] = x[i] ^ b, f[i] = (float)(threadIdx.x + i);
 	}
 	for (u32 i = threadIdx.x; i < 32 * 64; i += blockDim.x)
 		sm[i] = (i * 7 + a) & (63u << 5);   // next index: keeps the lane's own bank (multiple of 32 words)
@@ -57,13 +62,32 @@ __global__ void __launch_bounds__(1024) mb_kernel(u32* out, u32 iters, u32 a, u3
 					asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(a), "r"(b));
 					asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(sh), "r"(a));
 				}
+				else if (KIND == MB_MIX_LOP3_IMAD)
+				{
+					asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(a), "r"(b));
+					asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(a), "r"(b));
+				}
+				else if (KIND == MB_MIX_LOP3_FFMA)
+				{
+					asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(a), "r"(b));
+					asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(fa), "f"(fb));
+				}
+				else if (KIND == MB_FFMA)
+					asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(fa), "f"(fb));
+				else if (KIND == MB_IMAD_HI)
+					asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
+				else if (KIND == MB_MIX_LOP3_LDS)
+				{
+					asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(y[i]) : "r"(a), "r"(b));
+					x[i] = sm[x[i] + lane];
+				}
 			}
 		}
 	}
 	u32 acc = 0;
 #pragma unroll
 	for (int i = 0; i < MB_ILP; ++i)
-		acc ^= x[i] ^ (u32)w[i] ^ (u32)(w[i] >> 32);
+		acc ^= x[i] ^ y[i] ^ __float_as_uint(f[i]) ^ (u32)w[i] ^ (u32)(w[i] >> 32);
 	if (acc == 0x12345678u)
 		out[0] = acc;
 }
@@ -85,7 +109,7 @@ template <int KIND> static double mb_run(u32 iters, u32* d_out)
 	b2g_note_launch(), b2g_note_launch();
 	if (b2g_check_launch("mb_kernel") || ms <= 0)
 		return -1.0;
-	const double per_thread = (double)iters * MB_UNROLL * MB_ILP * (KIND == MB_MIX_LOP3_IMADW ? 2 : 1);
+	const double per_thread = (double)iters * MB_UNROLL * MB_ILP * (MB_IS_MIX(KIND) ? 2 : 1);
 	return per_thread * 1024.0 * grid / (ms * 1e-3);
 }
 
@@ -110,6 +134,11 @@ extern "C" double b2g_microbench(int kind, unsigned iters)
 	case MB_IMAD_WIDE: r = mb_run<MB_IMAD_WIDE>(iters, d_out); break;
 	case MB_LDS: r = mb_run<MB_LDS>(iters, d_out); break;
 	case MB_MIX_LOP3_IMADW: r = mb_run<MB_MIX_LOP3_IMADW>(iters, d_out); break;
+	case MB_MIX_LOP3_IMAD: r = mb_run<MB_MIX_LOP3_IMAD>(iters, d_out); break;
+	case MB_MIX_LOP3_FFMA: r = mb_run<MB_MIX_LOP3_FFMA>(iters, d_out); break;
+	case MB_IMAD_HI: r = mb_run<MB_IMAD_HI>(iters, d_out); break;
+	case MB_MIX_LOP3_LDS: r = mb_run<MB_MIX_LOP3_LDS>(iters, d_out); break;
+	case MB_FFMA: r = mb_run<MB_FFMA>(iters, d_out); break;
 	default: break;
 	}
 	cudaFree(d_out);

@@ -75,8 +75,10 @@ err_t b2g_sync(void);
 /* How many kernels this library has launched in this process (for gpu_launches). */
 u64 b2g_launch_count(void);
 /* Measured issue peak of one instruction kind, lane-operations per second on the whole chip:
-   0 LOP3, 1 SHF, 2 PRMT, 3 IADD, 4 IMAD, 5 IMAD.WIDE, 6 LDS.32 (conflict-free), 7 LOP3+IMAD.WIDE
-   co-issued. iters = 0 picks a default. < 0 on failure. Denominators of the issue roofline. */
+   0 LOP3, 1 SHF, 2 PRMT, 3 IADD, 4 IMAD, 5 IMAD.WIDE, 6 LDS.32 (conflict-free), 10 IMAD.HI, 12 FFMA;
+   co-issue mixes (two independent chains, both counted): 7 LOP3+IMAD.WIDE, 8 LOP3+IMAD,
+   9 LOP3+FFMA, 11 LOP3+LDS.32. iters = 0 picks a default. < 0 on failure.
+   Denominators of the issue roofline. */
 double b2g_microbench(int kind, unsigned iters);
 
 /* ======================================================================= bash (STB 34.101.77) */
