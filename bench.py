@@ -296,9 +296,16 @@ def main():
         run_reference(args, rank)
         return
 
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner)
+    # are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import bee2_b200 as b
+    from bee2_b200 import shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -313,11 +320,6 @@ def main():
     peak, peak_src = hbm_peak()
     sampler = ClockSampler(local_rank)
     sampler.start()
-
-    def bcast(t):
-        if world > 1:
-            dist.broadcast(t, src=0)
-        return t
 
     def barrier():
         if world > 1:
@@ -345,11 +347,7 @@ def main():
         sampler.active.clear()
         launches = b.b2g_launch_count() - l0
         barrier()
-        total = sum(s.elapsed_time(e) for s, e in ev) * 1e-3
-        if world > 1:
-            t = torch.tensor([total], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total = float(t.item())
+        total = shard.max_over_ranks(sum(s.elapsed_time(e) for s, e in ev) * 1e-3, device=dev)
         return total, launches
 
     def timed_host(fn, steps, warmup):
@@ -362,11 +360,7 @@ def main():
         torch.cuda.synchronize()
         total = time.perf_counter() - t0
         barrier()
-        if world > 1:
-            t = torch.tensor([total], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total = float(t.item())
-        return total
+        return shard.max_over_ranks(total, device=dev)
 
     results = {}
     issue = {}
@@ -385,10 +379,8 @@ def main():
         e2e_steps = max(1, min(args.steps, 3))
         r = {"metric": cfg["metric"], "unit": cfg["unit"], "workload": cfg["workload"]}
         if path == "belt_ctr":
-            kiv = torch.zeros(48, dtype=torch.uint8, device=dev)
-            if rank == 0:
-                kiv = torch.from_numpy(np.random.default_rng(10).integers(0, 256, 48, dtype=np.uint8)).to(dev)
-            kiv = bcast(kiv).cpu().numpy().tobytes()
+            secret = np.random.default_rng(10).integers(0, 256, 48, dtype=np.uint8).tobytes() if rank == 0 else None
+            kiv = shard.broadcast_bytes(secret, 48, device=dev)        # one NCCL broadcast of key || iv
             st = b.BeltCTR(kiv[:32], kiv[32:])
             key, ctr = st.key_words, st.ctr_words
             nbytes = units * 16
@@ -451,10 +443,7 @@ def main():
             assert not st1.any() and not st2.any()
             bad = np.arange(0, units, 16)
             sigs[bad, bad % 48] ^= 1
-            oid_t = torch.zeros(len(OID), dtype=torch.uint8, device=dev)
-            if rank == 0:
-                oid_t = torch.from_numpy(np.frombuffer(OID, dtype=np.uint8).copy()).to(dev)
-            oid = bcast(oid_t).cpu().numpy().tobytes()
+            oid = shard.broadcast_bytes(OID if rank == 0 else None, len(OID), device=dev)
             d_h, d_s, d_p = (torch.from_numpy(x).to(dev) for x in (hashes, sigs, pubs))
             d_st = torch.empty(units, dtype=torch.int32, device=dev)
             fn = lambda: b.bignVerifyBatch_dev(d_st.data_ptr(), oid, d_h.data_ptr(), d_s.data_ptr(), d_p.data_ptr(), units, stream)  # noqa: E731
@@ -524,7 +513,8 @@ def main():
             "cpu_baseline": h.get("cpu_baseline"), "e2e": h.get("e2e"), "gpu_launches": h["gpu_launches"],
             "clocks": clocks, "issue_peaks_Tops": issue,
             "paths": {k: v for k, v in results.items() if k != head}}
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
