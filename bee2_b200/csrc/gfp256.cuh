@@ -188,26 +188,30 @@ __device__ __forceinline__ void fe_reduce_wide(fe& r, const u32 (&t)[16])
 	for (int i = 0; i < 8; ++i) r.v[i] = s[i];
 }
 
-// The multiplication is a real (non-inlined) function: a verify executes ~2300 of them, and with
-// every one inlined the kernel grows to ~350 KB of SASS and stalls on instruction fetch (ncu r01:
-// 34% "no instruction"). Operands and result travel in registers (by-value struct ABI).
+// Two forms of the multiplication:
+//   fe_mul_i — inlined body (~130 SASS instructions), used inside the out-of-line point
+//              operations of ecp256.cuh;
+//   fe_mul   — a call to one shared copy (by-value register ABI), used everywhere else
+//              (inversion chain, conversions).
+// With every one of the ~100 call sites inlined the verify kernel was 350 KB of SASS and
+// stalled on instruction fetch (ncu r01: 34 % "no instruction").
+__device__ __forceinline__ void fe_mul_i(fe& r, const fe& a, const fe& b)
+{
+	u32 t[16];
+	fe_mul_wide(t, a, b);
+	fe_reduce_wide(r, t);
+}
+__device__ __forceinline__ void fe_sqr_i(fe& r, const fe& a) { fe_mul_i(r, a, a); }
 #ifndef FE_MUL_INLINE
 __device__ __noinline__ fe fe_mul_fn(const fe a, const fe b)
 {
-	u32 t[16];
 	fe r;
-	fe_mul_wide(t, a, b);
-	fe_reduce_wide(r, t);
+	fe_mul_i(r, a, b);
 	return r;
 }
 __device__ __forceinline__ void fe_mul(fe& r, const fe& a, const fe& b) { r = fe_mul_fn(a, b); }
 #else
-__device__ __forceinline__ void fe_mul(fe& r, const fe& a, const fe& b)
-{
-	u32 t[16];
-	fe_mul_wide(t, a, b);
-	fe_reduce_wide(r, t);
-}
+__device__ __forceinline__ void fe_mul(fe& r, const fe& a, const fe& b) { fe_mul_i(r, a, b); }
 #endif
 __device__ __forceinline__ void fe_sqr(fe& r, const fe& a) { fe_mul(r, a, a); }
 

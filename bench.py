@@ -41,6 +41,11 @@ CFG = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the bench
+# configuration, from the committed `ncu --set full` captures (profiles/r01_ncu_raw_*.csv)
+NCU_TRAFFIC = {"belt_ctr": 0.13e6 + 1.0142e9, "bash512": 4.4244e9 + 14.5e6, "bign_verify": 151.7e6 + 340.8e6}
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -467,7 +472,8 @@ def main():
         r["gpu_launches"] = int(launches)
         ach = algo_bytes / (total / args.steps) / 1e9
         r["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": NCU_TRAFFIC.get(path), "traffic_source": "profiles/r01_ncu_raw_*.csv (bytes per launch)",
+                         "algorithmic_bytes": algo_bytes, "peak_source": peak_src,
                          "note": "integer-issue bound, not HBM bound (SURVEY §8d): see issue_roofline"}
         results[path] = r
 
