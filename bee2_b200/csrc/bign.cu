@@ -9,9 +9,9 @@
 // Work decomposition: ONE THREAD PER ITEM (signature / key / scalar-point pair), field
 // elements as 8 x u32 in registers. Scalar multiplication is REGULAR so that all lanes of a
 // warp execute the same doublings and additions in lock-step:
-//   * fixed base G: 8-bit windows over a device-resident table GTAB[32][256] of affine
-//     multiples j * 2^(8i) * G (512 KiB, L2-resident; generated once per process by
-//     bign_gtab_kernel with the same point code) -> 32 mixed additions, no doublings;
+//   * fixed base G: BIGN_GW-bit windows (13) over a device-resident table GTAB[20][8192] of
+//     affine multiples j * 2^(13 i) * G (10 MiB, L2-resident; generated once per process by
+//     bign_gtab_kernel with the same point code) -> 20 mixed additions, no doublings;
 //   * variable base Q: 4-bit windows, per-thread table {1..15}Q in local memory
 //     -> 4 doublings + 1 addition per nibble.
 // The reference's interleaved wNAF (ec.c:1206-1268) is irregular and would diverge.
@@ -22,6 +22,11 @@
 #ifndef BIGN_MIN_BLOCKS
 #define BIGN_MIN_BLOCKS 4
 #endif
+#ifndef BIGN_GW
+#define BIGN_GW 13                                  // fixed-base window width in bits (<= 16)
+#endif
+#define BIGN_GN ((256 + BIGN_GW - 1) / BIGN_GW)     // number of windows
+#define BIGN_GE (1 << BIGN_GW)                      // entries per window (entry 0 unused)
 #define BIGN_MAX_OID 64
 #define BIGN_MAX_T 64
 
@@ -32,7 +37,7 @@ __constant__ u32 c_q[8] = {0x263D6607u, 0x7E5ABF99u, 0x0DFB4DFCu, 0xD95C8ED6u,
 __constant__ u32 c_yG[8] = {0x04516A93u, 0x1E29CF18u, 0xC408F652u, 0x78913966u,
 	0x51D6835Du, 0x5CE4C9A3u, 0xFB16D69Fu, 0x6BF7FC3Cu};
 
-static uint4* g_gtab;          // device: 32 * 256 entries of 64 octets (x || y); entry j = 0 unused
+static uint4* g_gtab;          // device: BIGN_GN * BIGN_GE entries of 64 octets (x || y); entry j = 0 unused
 
 struct OidArg { u8 der[BIGN_MAX_OID]; u32 len; };
 struct TArg { u8 t[BIGN_MAX_T]; u32 len; };
@@ -120,16 +125,18 @@ __device__ __forceinline__ void load_u256(u32* r, const u8* p)
 }
 
 // ---------------------------------------------------------------- scalar multiplication
-// acc += k * G for a 256-bit k (little-endian limbs) through the 8-bit window table
+// acc += k * G for a 256-bit k (little-endian limbs) through the fixed-base window table
 __device__ __forceinline__ void pt_add_mul_base(pt& acc, const u32* k, const uint4* __restrict__ gtab)
 {
 #pragma unroll 1
-	for (int i = 0; i < 32; ++i)
+	for (int i = 0; i < BIGN_GN; ++i)
 	{
-		const u32 d = (k[i >> 2] >> (8 * (i & 3))) & 255u;
+		const int bit = BIGN_GW * i, limb = bit >> 5;
+		const u64 w = (u64)k[limb] | (limb < 7 ? (u64)k[limb + 1] << 32 : 0);
+		const u32 d = (u32)(w >> (bit & 31)) & (BIGN_GE - 1);
 		if (d)
 		{
-			const uint4* e = gtab + ((size_t)(i * 256 + (int)d) << 2);
+			const uint4* e = gtab + ((size_t)(i * BIGN_GE + (int)d) << 2);
 			const uint4 a0 = __ldg(e), a1 = __ldg(e + 1), a2 = __ldg(e + 2), a3 = __ldg(e + 3);
 			fe x, y;
 			x.v[0] = a0.x, x.v[1] = a0.y, x.v[2] = a0.z, x.v[3] = a0.w;
@@ -155,9 +162,17 @@ __device__ __forceinline__ void pt_mul_var(pt& acc, const u32* k, int nbits, con
 		else
 			pt_dbl(T[j], T[j >> 1]);
 	}
-	pt_set_inf(acc);
+	// the top window only selects (no doublings of O)
+	{
+		const int i = nbits / 4 - 1;
+		const u32 d = (k[i >> 3] >> (4 * (i & 7))) & 15u;
+		if (d)
+			acc = T[d];
+		else
+			pt_set_inf(acc);
+	}
 #pragma unroll 1
-	for (int i = nbits / 4 - 1; i >= 0; --i)
+	for (int i = nbits / 4 - 2; i >= 0; --i)
 	{
 #pragma unroll 1
 		for (int s = 0; s < 4; ++s)
@@ -187,21 +202,29 @@ __device__ __forceinline__ void hash_oid_2x32(const BeltSmallT& S, u32 (&out)[8]
 }
 
 // ---------------------------------------------------------------- kernels
-// Table of fixed-base multiples: entry (i, j) = j * 2^(8i) * G, affine.
+// Table of fixed-base multiples: entry (i, j) = j * 2^(BIGN_GW i) * G, affine.
 __global__ void __launch_bounds__(BIGN_THREADS) bign_gtab_kernel(uint4* gtab)
 {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= 32 * 256)
+	if (idx >= BIGN_GN * BIGN_GE)
 		return;
-	const int i = idx >> 8, j = idx & 255;
+	const int i = idx / BIGN_GE, j = idx % BIGN_GE;
 	uint4* e = gtab + ((size_t)idx << 2);
 	if (j == 0)
 	{
 		e[0] = e[1] = e[2] = e[3] = make_uint4(0, 0, 0, 0);
 		return;
 	}
+	// k = j << (BIGN_GW * i); bits past 2^256 cannot occur for the digits a 256-bit scalar has,
+	// such entries are never read
 	u32 k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-	k[i >> 2] = (u32)j << (8 * (i & 3));
+	{
+		const int bit = BIGN_GW * i, limb = bit >> 5;
+		const u64 w = (u64)j << (bit & 31);
+		k[limb] = (u32)w;
+		if (limb < 7)
+			k[limb + 1] = (u32)(w >> 32);
+	}
 	fe gx, gy, x, y;
 	fe_set_u32(gx, 0);
 #pragma unroll
@@ -436,9 +459,9 @@ static u32 bign_ensure_gtab(cudaStream_t st)
 	if (g_gtab)
 		return B2G_OK;
 	uint4* p = 0;
-	if (cudaMalloc(&p, (size_t)32 * 256 * 64) != cudaSuccess)
+	if (cudaMalloc(&p, (size_t)BIGN_GN * BIGN_GE * 64) != cudaSuccess)
 		return b2g_check_launch("cudaMalloc(gtab)");
-	bign_gtab_kernel<<<(32 * 256 + BIGN_THREADS - 1) / BIGN_THREADS, BIGN_THREADS, 0, st>>>(p);
+	bign_gtab_kernel<<<(BIGN_GN * BIGN_GE + BIGN_THREADS - 1) / BIGN_THREADS, BIGN_THREADS, 0, st>>>(p);
 	b2g_note_launch();
 	u32 e = b2g_check_launch("bign_gtab_kernel");
 	if (e)
