@@ -21,7 +21,7 @@ __all__ = [
     "beltH", "beltKeyExpand2", "beltBlockEncr", "beltBlockDecr", "beltECBEncr", "beltECBDecr",
     "beltECBEncrBatch", "BeltECB", "BeltCTR", "beltCTR", "beltCTRKeystream", "beltHash", "beltHashBatch",
     "bignParamsStd", "bignVerify", "bignVerifyBatch", "bignSign2", "bignSign2Batch",
-    "bignPubkeyCalc", "bignPubkeyCalcBatch", "ecMulABatch", "OID_BELT_HASH_DER",
+    "bignPubkeyCalc", "bignPubkeyCalcBatch", "ecMulABatch", "ecAddMulABatch", "OID_BELT_HASH_DER",
     "bashHashBatch_dev", "bashFBatch_dev", "beltCTR_dev", "beltECB_dev", "beltECBEncrBatch_dev",
     "beltHashBatch_dev", "bignVerifyBatch_dev", "bignSign2Batch_dev", "bignPubkeyCalcBatch_dev",
     "ecMulABatch_dev", "pinned_empty",
@@ -114,6 +114,8 @@ def _declare(L: C.CDLL) -> None:
         "b2g_bignSign2Batch_dev": (u32, [vp, vp, vp, sz, vp, vp, sz, vp]),
         "b2g_bignPubkeyCalcBatch_dev": (u32, [vp, vp, vp, sz, vp]),
         "b2g_ecMulABatch_dev": (u32, [vp, vp, vp, vp, sz, sz, vp]),
+        "ecAddMulABatch": (u32, [vp, vp, vp, vp, sz, vp, sz]),
+        "b2g_ecAddMulABatch_dev": (u32, [vp, vp, vp, vp, sz, vp, sz, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -452,6 +454,16 @@ def ecMulABatch(points: np.ndarray, scalars: np.ndarray):
     ok = np.zeros(count, dtype=np.int32)
     _chk("ecMulABatch", lib().ecMulABatch(out.ctypes.data, ok.ctypes.data, points.ctypes.data, scalars.ctypes.data,
                                           d_len, count))
+    return out, ok
+
+
+def ecAddMulABatch(points: np.ndarray, scalars: np.ndarray, kbase: np.ndarray):
+    """d_i * A_i + k_i * G: points [count,64], scalars [count,d_len], kbase [count,32]"""
+    count, d_len = scalars.shape
+    out = np.zeros((count, 64), dtype=np.uint8)
+    ok = np.zeros(count, dtype=np.int32)
+    _chk("ecAddMulABatch", lib().ecAddMulABatch(out.ctypes.data, ok.ctypes.data, points.ctypes.data,
+                                                scalars.ctypes.data, d_len, kbase.ctypes.data, count))
     return out, ok
 
 

@@ -159,8 +159,11 @@ __device__ __forceinline__ void belt_hash_init(u32 (&h)[8])
 
 // Hash of a message held as zero-padded 32-bit words (nwords32 = 8 * ceil(len/32)).
 // `msg` may live in local or global memory. out = 8 words (32 octets).
-template <class SB> __device__ __noinline__ void belt_hash_words(const SB& S, const u32* msg, u32 len_bytes, u32 (&out)[8])
+struct belt_digest { u32 w[8]; };
+// (result by value: callers keep no address-taken output buffer, cf. sc256 in bign.cu)
+template <class SB> __device__ __noinline__ belt_digest belt_hash_words(const SB S, const u32* msg, u32 len_bytes)
 {
+	belt_digest out;
 	u32 h[8], ls[8] = {0, 0, 0, 0, 0, 0, 0, 0}, X[8];
 	belt_hash_init(h);
 	const u32 nblk = (len_bytes + 31u) >> 5;
@@ -176,5 +179,6 @@ template <class SB> __device__ __noinline__ void belt_hash_words(const SB& S, co
 	belt_compress(S, (u32*)0, h, ls);
 #pragma unroll
 	for (int j = 0; j < 8; ++j)
-		out[j] = h[j];
+		out.w[j] = h[j];
+	return out;
 }

@@ -40,6 +40,10 @@ __constant__ u32 c_yG[8] = {0x04516A93u, 0x1E29CF18u, 0xC408F652u, 0x78913966u,
 static uint4* g_gtab;          // device: BIGN_GN * BIGN_GE entries of 64 octets (x || y); entry j = 0 unused
 
 struct OidArg { u8 der[BIGN_MAX_OID]; u32 len; };
+// a scalar handed BY VALUE to the out-of-line multiplication routines: the kernels keep no
+// address-taken locals besides the accumulator (nvcc 12.9 was seen to overlap the stack slots of
+// two live address-taken locals of bign_verify_kernel — see DESIGN.md §4.3)
+struct sc256 { u32 w[8]; };
 struct TArg { u8 t[BIGN_MAX_T]; u32 len; };
 
 // ---------------------------------------------------------------- small helpers
@@ -124,10 +128,26 @@ __device__ __forceinline__ void load_u256(u32* r, const u8* p)
 	for (int i = 0; i < 8; ++i) r[i] = t.v[i];
 }
 
+// d_len <= 32 little-endian octets -> limbs, without dynamic indexing of the destination
+__device__ __forceinline__ void load_scalar(sc256& k, const u8* s, u32 d_len)
+{
+#pragma unroll
+	for (int l = 0; l < 8; ++l)
+	{
+		u32 w = 0;
+#pragma unroll
+		for (int b = 0; b < 4; ++b)
+			if ((u32)(4 * l + b) < d_len)
+				w |= (u32)s[4 * l + b] << (8 * b);
+		k.w[l] = w;
+	}
+}
+
 // ---------------------------------------------------------------- scalar multiplication
 // acc += k * G for a 256-bit k (little-endian limbs) through the fixed-base window table
-__device__ __forceinline__ void pt_add_mul_base(pt& acc, const u32* k, const uint4* __restrict__ gtab)
+__device__ __noinline__ void pt_add_mul_base(pt& acc, const sc256 ks, const uint4* __restrict__ gtab)
 {
+	const u32* k = ks.w;
 #pragma unroll 1
 	for (int i = 0; i < BIGN_GN; ++i)
 	{
@@ -150,8 +170,9 @@ __device__ __forceinline__ void pt_add_mul_base(pt& acc, const u32* k, const uin
 
 // acc = k * (x, y) for a scalar of nbits bits (little-endian limbs; nbits multiple of 4,
 // bits above nbits ignored), 4-bit fixed windows, most significant first
-__device__ __forceinline__ void pt_mul_var(pt& acc, const u32* k, int nbits, const fe& x, const fe& y)
+__device__ __noinline__ void pt_mul_var(pt& acc, const sc256 ks, int nbits, const fe x, const fe y)
 {
+	const u32* k = ks.w;
 	pt T[16];   // T[j] = j * (x, y); T[0] unused. Dynamic indexing -> local memory.
 	pt_set_affine(T[1], x, y);
 #pragma unroll 1
@@ -198,7 +219,9 @@ __device__ __forceinline__ void hash_oid_2x32(const BeltSmallT& S, u32 (&out)[8]
 	if (b)
 		for (u32 i = 0; i < 32; ++i) m8[pos++] = (u8)(b[i >> 2] >> (8 * (i & 3)));
 	for (u32 i = 0; i < extra_len; ++i) m8[pos++] = extra[i];
-	belt_hash_words(S, msg, pos, out);
+	const belt_digest dg = belt_hash_words(S, msg, pos);
+#pragma unroll
+	for (int i = 0; i < 8; ++i) out[i] = dg.w[i];
 }
 
 // ---------------------------------------------------------------- kernels
@@ -217,13 +240,13 @@ __global__ void __launch_bounds__(BIGN_THREADS) bign_gtab_kernel(uint4* gtab)
 	}
 	// k = j << (BIGN_GW * i); bits past 2^256 cannot occur for the digits a 256-bit scalar has,
 	// such entries are never read
-	u32 k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	sc256 k = {{0, 0, 0, 0, 0, 0, 0, 0}};
 	{
 		const int bit = BIGN_GW * i, limb = bit >> 5;
 		const u64 w = (u64)j << (bit & 31);
-		k[limb] = (u32)w;
-		if (limb < 7)
-			k[limb + 1] = (u32)(w >> 32);
+#pragma unroll
+		for (int l = 0; l < 8; ++l)
+			k.w[l] = l == limb ? (u32)w : (l == limb + 1 ? (u32)(w >> 32) : 0u);
 	}
 	fe gx, gy, x, y;
 	fe_set_u32(gx, 0);
@@ -291,12 +314,15 @@ bign_verify_kernel(u32* __restrict__ status, const u8* __restrict__ hashes, cons
 	pt R;
 	{
 		// 129-bit scalar: the top bit is always 1 -> start from Q and consume 32 nibbles
-		u32 k5[5];
-#pragma unroll
-		for (int k = 0; k < 5; ++k) k5[k] = s0[k];
+		sc256 k5 = {{s0[0], s0[1], s0[2], s0[3], 1u, 0u, 0u, 0u}};
 		pt_mul_var(R, k5, 132, qx, qy);
 	}
-	pt_add_mul_base(R, s1, gtab);
+	{
+		sc256 ks;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) ks.w[k] = s1[k];
+		pt_add_mul_base(R, ks, gtab);
+	}
 	if (pt_is_inf(R))
 	{
 		status[i] = B2G_BAD_SIG;
@@ -358,7 +384,12 @@ bign_sign2_kernel(u32* __restrict__ status, u8* __restrict__ sigs, const u8* __r
 	// R <- k G (:219-224)
 	pt R;
 	pt_set_inf(R);
-	pt_add_mul_base(R, k, gtab);
+	{
+		sc256 ks;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) ks.w[j] = k[j];
+		pt_add_mul_base(R, ks, gtab);
+	}
 	if (pt_is_inf(R))
 	{
 		status[i] = B2G_BAD_PARAMS;
@@ -412,7 +443,12 @@ bign_pubkey_kernel(u32* __restrict__ status, u8* __restrict__ pubkeys, const u8*
 	}
 	pt R;
 	pt_set_inf(R);
-	pt_add_mul_base(R, d, gtab);
+	{
+		sc256 ks;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) ks.w[j] = d[j];
+		pt_add_mul_base(R, ks, gtab);
+	}
 	if (pt_is_inf(R))
 	{
 		status[i] = B2G_BAD_PARAMS;
@@ -434,12 +470,37 @@ ecp_mul_kernel(u8* __restrict__ out, int* __restrict__ ok, const u8* __restrict_
 		return;
 	fe x, y;
 	fe_load(x, pts + 64 * i), fe_load(y, pts + 64 * i + 32);
-	u32 k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-	const u8* s = scalars + (u64)d_len * i;
-	for (u32 j = 0; j < d_len; ++j)
-		k[j >> 2] |= (u32)s[j] << (8 * (j & 3));
+	sc256 k;
+	load_scalar(k, scalars + (u64)d_len * i, d_len);
 	pt R;
 	pt_mul_var(R, k, (int)(8 * d_len), x, y);
+	if (pt_is_inf(R))
+	{
+		ok[i] = 0;
+		return;
+	}
+	pt_to_affine(x, y, R);
+	fe_store(out + 64 * i, x), fe_store(out + 64 * i + 32, y);
+	ok[i] = 1;
+}
+
+// ecAddMulA with the base point (ec.c:1183-1273): b = d * a + k * G; ok = 0 iff the result is O
+__global__ void __launch_bounds__(BIGN_THREADS, BIGN_MIN_BLOCKS)
+ecp_addmul_kernel(u8* __restrict__ out, int* __restrict__ ok, const u8* __restrict__ pts,
+	const u8* __restrict__ scalars, u32 d_len, const u8* __restrict__ kbase, u64 count,
+	const uint4* __restrict__ gtab)
+{
+	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+		return;
+	fe x, y;
+	fe_load(x, pts + 64 * i), fe_load(y, pts + 64 * i + 32);
+	sc256 k, kg;
+	load_scalar(k, scalars + (u64)d_len * i, d_len);
+	load_u256(kg.w, kbase + 32 * i);
+	pt R;
+	pt_mul_var(R, k, (int)(8 * d_len), x, y);
+	pt_add_mul_base(R, kg, gtab);
 	if (pt_is_inf(R))
 	{
 		ok[i] = 0;
@@ -562,4 +623,20 @@ extern "C" u32 b2g_ecMulABatch_dev(void* d_b, void* d_ok, const void* d_a, const
 		(const u8*)d_a, (const u8*)d_d, (u32)d_len, count);
 	b2g_note_launch();
 	return b2g_check_launch("ecp_mul_kernel");
+}
+
+extern "C" u32 b2g_ecAddMulABatch_dev(void* d_b, void* d_ok, const void* d_a, const void* d_d, size_t d_len,
+	const void* d_k, size_t count, void* stream)
+{
+	u32 e = b2g_ensure_device();
+	if (e) return e;
+	if (d_len == 0 || d_len > 32) return B2G_BAD_INPUT;
+	if (count == 0) return B2G_OK;
+	if ((uintptr_t)d_ok & 3) return B2G_BAD_INPUT;
+	cudaStream_t st = (cudaStream_t)stream;
+	if ((e = bign_ensure_gtab(st))) return e;
+	ecp_addmul_kernel<<<bign_grid(count), BIGN_THREADS, 0, st>>>((u8*)d_b, (int*)d_ok, (const u8*)d_a,
+		(const u8*)d_d, (u32)d_len, (const u8*)d_k, count, g_gtab);
+	b2g_note_launch();
+	return b2g_check_launch("ecp_addmul_kernel");
 }

@@ -51,7 +51,9 @@ __device__ __forceinline__ void mad_row_top(u32* acc, u32 a0, u32 a1, u32 a2, u3
 		: "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
 }
 
-// ---- carry chains: each chain is ONE asm statement so nothing can clobber CC.CF in between
+// ---- carry chains: each chain is ONE asm statement so nothing can clobber CC.CF in between.
+// Pure outputs are early-clobber ("=&r"): the statements write them before the last input is
+// read, so they must never share a register with an input.
 // r = a + b, returns carry (0/1)
 __device__ __forceinline__ u32 add8(u32* r, const u32* a, const u32* b)
 {
@@ -65,7 +67,7 @@ __device__ __forceinline__ u32 add8(u32* r, const u32* a, const u32* b)
 		"addc.cc.u32 %6, %15, %23;\n\t"
 		"addc.cc.u32 %7, %16, %24;\n\t"
 		"addc.u32 %8, 0, 0;"
-		: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+		: "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(c)
 		: "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
 		  "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
 	return c;
@@ -83,7 +85,7 @@ __device__ __forceinline__ u32 sub8(u32* r, const u32* a, const u32* b)
 		"subc.cc.u32 %6, %15, %23;\n\t"
 		"subc.cc.u32 %7, %16, %24;\n\t"
 		"subc.u32 %8, 0, 0;"
-		: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+		: "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(c)
 		: "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
 		  "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
 	return c;
@@ -101,7 +103,7 @@ __device__ __forceinline__ u32 add8_u32(u32* r, u32 x)
 		"addc.cc.u32 %6, %6, 0;\n\t"
 		"addc.cc.u32 %7, %7, 0;\n\t"
 		"addc.u32 %8, 0, 0;"
-		: "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(c)
+		: "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=&r"(c)
 		: "r"(x));
 	return c;
 }
@@ -118,7 +120,7 @@ __device__ __forceinline__ u32 sub8_u32(u32* r, u32 x)
 		"subc.cc.u32 %6, %6, 0;\n\t"
 		"subc.cc.u32 %7, %7, 0;\n\t"
 		"subc.u32 %8, 0, 0;"
-		: "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(c)
+		: "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=&r"(c)
 		: "r"(x));
 	return c;
 }
@@ -135,7 +137,7 @@ __device__ __forceinline__ void add7_cin(u32* r, const u32* a, const u32* b, u32
 		"addc.cc.u32 %4, %11, %18;\n\t"
 		"addc.cc.u32 %5, %12, %19;\n\t"
 		"addc.u32 %6, %13, %20;\n\t}"
-		: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6])
+		: "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6])
 		: "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]),
 		  "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(cin));
 }
@@ -288,9 +290,9 @@ __device__ __forceinline__ void fe_sqr_n(fe& r, const fe& a, int n)
 
 // r = a^(p-2) = 1/a (gfp.c:33-44 computes the same power with a sliding window).
 // p - 2 = 2^256 - 191 = (2^248 - 1) * 2^8 + 0x41: an addition chain on runs of ones.
-__device__ __noinline__ void fe_inv(fe& r, const fe& a)
+__device__ __noinline__ fe fe_inv_fn(const fe a)
 {
-	fe x2, x4, x8, x16, x32, x64, x128, t;
+	fe x2, x4, x8, x16, x32, x64, x128, t, r;
 	fe_sqr(t, a), fe_mul(x2, t, a);                 // 2^2 - 1
 	fe_sqr_n(t, x2, 2), fe_mul(x4, t, x2);          // 2^4 - 1
 	fe_sqr_n(t, x4, 4), fe_mul(x8, t, x4);          // 2^8 - 1
@@ -305,7 +307,9 @@ __device__ __noinline__ void fe_inv(fe& r, const fe& a)
 	// append 0x41 = 0100 0001b
 	fe_sqr_n(t, t, 2), fe_mul(t, t, a);             // ...01
 	fe_sqr_n(t, t, 6), fe_mul(r, t, a);             // ...01000001
+	return r;
 }
+__device__ __forceinline__ void fe_inv(fe& r, const fe& a) { r = fe_inv_fn(a); }
 
 // little-endian octets <-> limbs (unaligned-safe)
 __device__ __forceinline__ void fe_load(fe& r, const u8* p)

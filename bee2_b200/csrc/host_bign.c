@@ -321,3 +321,37 @@ done:
 	b2g_unlock();
 	return code;
 }
+
+/* b_i = d_i * a_i + k_i * G (ecAddMulA with the base point as second term, ec.c:1183-1273) */
+err_t ecAddMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d_len, const octet* k,
+	size_t count)
+{
+	err_t code;
+	b2g_slot *s0, *s1;
+	void *d_a, *d_d, *d_k, *d_b, *d_ok;
+	if (count && (!b || !ok || !a || !d || !k))
+		return ERR_BAD_INPUT;
+	if (d_len == 0 || d_len > 32)
+		return ERR_BAD_INPUT;
+	if ((code = b2g_ensure_device()))
+		return code;
+	if (!count)
+		return ERR_OK;
+	b2g_lock();
+	s0 = b2g_slot_get(0), s1 = b2g_slot_get(1);
+	if ((code = stage_in(s0, 0, a, 64 * count, &d_a)) || (code = stage_in(s0, 1, d, d_len * count, &d_d)) ||
+		(code = stage_in(s0, 2, k, 32 * count, &d_k)) || (code = b2g_slot_buf(s1, 0, 64 * count, &d_b)) ||
+		(code = b2g_slot_buf(s1, 1, 4 * count, &d_ok)))
+		goto done;
+	CU(cudaMemsetAsync(d_b, 0, 64 * count, s0->stream), "memset(ecAddMulA out)");
+	if ((code = b2g_ecAddMulABatch_dev(d_b, d_ok, d_a, d_d, d_len, d_k, count, s0->stream)))
+		goto done;
+	CU(cudaMemcpyAsync(b, d_b, 64 * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(ecAddMulA)");
+	CU(cudaMemcpyAsync(ok, d_ok, 4 * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(ecAddMulA ok)");
+	CU(cudaStreamSynchronize(s0->stream), "sync(ecAddMulA)");
+done:
+	if (code)
+		cudaStreamSynchronize(s0->stream);
+	b2g_unlock();
+	return code;
+}

@@ -185,6 +185,9 @@ err_t bignPubkeyCalcBatch(err_t* status, octet* pubkeys, const bign_params* para
 /* batch ecMulA on bign-curve256v1 (ec.c:497-525): b_i = d_i * a_i; scalars are d_len octets
    each (LE, <= 32); ok[i] = 0 iff the result is the point at infinity. */
 err_t ecMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d_len, size_t count);
+/* batch ecAddMulA with the base point (ec.c:1183-1273): b_i = d_i * a_i + k_i * G, k_i 32 octets */
+err_t ecAddMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d_len, const octet* k,
+	size_t count);
 /* device */
 err_t b2g_bignVerifyBatch_dev(void* d_status, const octet oid_der[], size_t oid_len,
 	const void* d_hashes, const void* d_sigs, const void* d_pubkeys, size_t count, void* stream);
@@ -194,6 +197,8 @@ err_t b2g_bignPubkeyCalcBatch_dev(void* d_status, void* d_pubkeys, const void* d
 	size_t count, void* stream);
 err_t b2g_ecMulABatch_dev(void* d_b, void* d_ok, const void* d_a, const void* d_d, size_t d_len,
 	size_t count, void* stream);
+err_t b2g_ecAddMulABatch_dev(void* d_b, void* d_ok, const void* d_a, const void* d_d, size_t d_len,
+	const void* d_k, size_t count, void* stream);
 
 #ifdef __cplusplus
 }

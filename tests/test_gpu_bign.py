@@ -188,6 +188,31 @@ def test_ecMulA_batch_vs_oracle():
     assert ok[0] == 0 and ok[1] == 1 and got[1].tobytes() == pts[1].tobytes()
 
 
+def test_ecAddMulA_batch_vs_oracle():
+    """d A + k G (ec.c:1183-1273) with A = a G of known a: the result must be ((d a + k) mod q) G,
+    including the collisions d A = +-k G (result 2kG resp. O) that need the complete addition."""
+    rng = np.random.default_rng(12)
+    p, n = b.bignParamsStd(), 64
+    a = [int.from_bytes(rng.integers(0, 256, 32, dtype=np.uint8).tobytes(), "little") % (Q - 1) + 1 for _ in range(n)]
+    d = [int.from_bytes(rng.integers(0, 256, 32, dtype=np.uint8).tobytes(), "little") % Q for _ in range(n)]
+    k = [int.from_bytes(rng.integers(0, 256, 32, dtype=np.uint8).tobytes(), "little") % Q for _ in range(n)]
+    a[0], d[0], k[0] = 1, 5, 5                    # d A = k G  -> doubling branch
+    a[1], d[1], k[1] = 1, 7, Q - 7                # d A = -k G -> O
+    a[2], d[2], k[2] = 3, 0, 9                    # d = 0 -> k G
+    a[3], d[3], k[3] = 3, 9, 0                    # k = 0 -> d A
+    a[4], d[4], k[4] = 2, 0, 0                    # O
+    _, A_ = b.bignPubkeyCalcBatch(p, np.stack([A(x.to_bytes(32, "little")) for x in a]))
+    dm = np.stack([A(x.to_bytes(32, "little")) for x in d])
+    km = np.stack([A(x.to_bytes(32, "little")) for x in k])
+    got, ok = b.ecAddMulABatch(A_, dm, km)
+    for i in range(n):
+        s = (d[i] * a[i] + k[i]) % Q
+        if s == 0:
+            assert ok[i] == 0, i
+        else:
+            assert ok[i] == 1 and (0, got[i].tobytes()) == o.bignPubkeyCalc(s.to_bytes(32, "little")), i
+
+
 @pytest.mark.skipif(o.ref() is None, reason="oracle/_ref/libbee2ref_64.so not on this machine")
 def test_config4_shape_vs_reference_harness():
     """A 2^13 slice of BASELINE config 4 (2^18 sigs): every status equals the unmodified
