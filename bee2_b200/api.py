@@ -17,7 +17,7 @@ __all__ = [
     "ERR_BAD_OID", "ERR_BAD_PARAMS", "ERR_BAD_PRIVKEY", "ERR_BAD_PUBKEY", "ERR_BAD_SIG",
     "ERR_B2G_NO_DEVICE", "ERR_B2G_CUDA", "Bee2Error", "BignParams", "lib", "lib_path",
     "b2g_init", "b2g_last_error", "b2g_sm_count", "b2g_launch_count", "b2g_sync", "b2g_microbench",
-    "bashF", "bashHash", "bashHashBatch", "bashFBatch", "BashHash",
+    "bashF", "bashHash", "bashHashBatch", "bashHashBatchV", "bashFBatch", "BashHash",
     "beltH", "beltKeyExpand2", "beltBlockEncr", "beltBlockDecr", "beltECBEncr", "beltECBDecr",
     "beltECBEncrBatch", "BeltECB", "BeltCTR", "beltCTR", "beltCTRKeystream", "beltHash", "beltHashBatch",
     "bignParamsStd", "bignVerify", "bignVerifyBatch", "bignSign2", "bignSign2Batch",
@@ -90,7 +90,8 @@ def _declare(L: C.CDLL) -> None:
         "bashHashStart": (None, [vp, sz]), "bashHashStepH": (None, [vp, sz, vp]),
         "bashHashStepG": (None, [vp, sz, vp]), "bashHashStepV": (ci, [vp, sz, vp]),
         "bashHash": (u32, [vp, sz, vp, sz]), "bashHashBatch": (u32, [vp, sz, vp, sz, sz, sz]),
-        "bashFBatch": (u32, [vp, sz]),
+        "bashFBatch": (u32, [vp, sz]), "bashHashBatchV": (u32, [vp, sz, vp, sz, vp, vp, sz]),
+        "b2g_bashHashBatchV_dev": (u32, [vp, sz, vp, vp, vp, sz, vp]),
         "b2g_bashHashBatch_dev": (u32, [vp, sz, vp, sz, sz, sz, vp]), "b2g_bashFBatch_dev": (u32, [vp, sz, vp]),
         "beltH": (vp, []), "beltKeyExpand": (None, [vp, vp, sz]), "beltKeyExpand2": (None, [vp, vp, sz]),
         "beltBlockEncr": (None, [vp, vp]), "beltBlockEncr2": (None, [vp, vp]),
@@ -215,6 +216,16 @@ def bashHashBatch(l: int, msgs: np.ndarray, msg_len: Optional[int] = None, strid
     k, p, n = _buf(msgs)
     out = np.zeros((count, l // 4), dtype=np.uint8)
     _chk("bashHashBatch", lib().bashHashBatch(out.ctypes.data, l, p, msg_len, stride, count))
+    return out
+
+
+def bashHashBatchV(l: int, data: np.ndarray, offsets: np.ndarray, lens: np.ndarray) -> np.ndarray:
+    """ragged batch: message i = data[offsets[i]:offsets[i]+lens[i]] -> digests [count, l/4]"""
+    off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    ln = np.ascontiguousarray(lens, dtype=np.uint64)
+    out = np.zeros((off.size, max(l // 4, 1)), dtype=np.uint8)
+    k, p, n = _buf(data)
+    _chk("bashHashBatchV", lib().bashHashBatchV(out.ctypes.data, l, p, n, off.ctypes.data, ln.ctypes.data, off.size))
     return out
 
 

@@ -22,7 +22,7 @@ void b2g_unlock(void);
 
 /* Pipelined workspace: NSLOT slots, each a stream + growable device buffers. */
 #define B2G_NSLOT 2
-#define B2G_NBUF 3
+#define B2G_NBUF 4
 typedef struct
 {
 	cudaStream_t stream;

@@ -105,6 +105,46 @@ done:
 	return code;
 }
 
+/* ragged batch: message i = data[offsets[i] .. offsets[i] + lens[i]) — many files in one buffer */
+err_t bashHashBatchV(octet* hashes, size_t l, const void* data, size_t data_len, const u64* offsets,
+	const u64* lens, size_t count)
+{
+	err_t code;
+	b2g_slot *s0, *s1;
+	void *d_data, *d_off, *d_len, *d_out;
+	size_t i, hl;
+	if (l == 0 || l % 16 != 0 || l > 256)
+		return ERR_BAD_PARAMS;
+	if (count && (!hashes || !offsets || !lens || (data_len && !data)))
+		return ERR_BAD_INPUT;
+	for (i = 0; i < count; ++i)
+		if (offsets[i] > data_len || lens[i] > data_len - offsets[i])
+			return ERR_BAD_INPUT;
+	if ((code = b2g_ensure_device()))
+		return code;
+	if (!count)
+		return ERR_OK;
+	hl = l / 4;
+	b2g_lock();
+	s0 = b2g_slot_get(0), s1 = b2g_slot_get(1);
+	if ((code = b2g_slot_buf(s0, 0, data_len, &d_data)) || (code = b2g_slot_buf(s0, 1, 8 * count, &d_off)) ||
+		(code = b2g_slot_buf(s0, 2, 8 * count, &d_len)) || (code = b2g_slot_buf(s1, 0, hl * count, &d_out)))
+		goto done;
+	if (data_len)
+		CU(cudaMemcpyAsync(d_data, data, data_len, cudaMemcpyHostToDevice, s0->stream), "H2D(bash data)");
+	CU(cudaMemcpyAsync(d_off, offsets, 8 * count, cudaMemcpyHostToDevice, s0->stream), "H2D(bash offsets)");
+	CU(cudaMemcpyAsync(d_len, lens, 8 * count, cudaMemcpyHostToDevice, s0->stream), "H2D(bash lens)");
+	if ((code = b2g_bashHashBatchV_dev(d_out, l, d_data, d_off, d_len, count, s0->stream)))
+		goto done;
+	CU(cudaMemcpyAsync(hashes, d_out, hl * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(bash digests)");
+	CU(cudaStreamSynchronize(s0->stream), "sync(bash ragged)");
+done:
+	if (code)
+		cudaStreamSynchronize(s0->stream);
+	b2g_unlock();
+	return code;
+}
+
 err_t bashHash(octet hash[], size_t l, const void* src, size_t count)
 {
 	if (l == 0 || l % 16 != 0 || l > 256)

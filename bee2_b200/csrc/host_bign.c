@@ -132,7 +132,7 @@ err_t bignVerifyBatch(err_t* status, const bign_params* params, const octet oid_
 	const octet* hashes, const octet* sigs, const octet* pubkeys, size_t count)
 {
 	err_t code;
-	b2g_slot *s0, *s1;
+	b2g_slot *s0 = b2g_slot_get(0), *s1 = b2g_slot_get(1);
 	void *d_h, *d_s, *d_p, *d_st;
 	if ((code = params_check(params)))
 		return code;
@@ -145,18 +145,30 @@ err_t bignVerifyBatch(err_t* status, const bign_params* params, const octet oid_
 	if (!count)
 		return ERR_OK;
 	b2g_lock();
-	s0 = b2g_slot_get(0), s1 = b2g_slot_get(1);
-	/* four device buffers: three from slot 0, the status array from slot 1's pool */
-	if ((code = stage_in(s0, 0, hashes, 32 * count, &d_h)) || (code = stage_in(s0, 1, sigs, 48 * count, &d_s)) ||
-		(code = stage_in(s0, 2, pubkeys, 64 * count, &d_p)) || (code = b2g_slot_buf(s1, 0, 4 * count, &d_st)))
-		goto done;
-	if ((code = b2g_bignVerifyBatch_dev(d_st, oid_der, oid_len, d_h, d_s, d_p, count, s0->stream)))
-		goto done;
-	CU(cudaMemcpyAsync(status, d_st, 4 * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(bign status)");
-	CU(cudaStreamSynchronize(s0->stream), "sync(bign verify)");
+	/* chunks of 2^16 items alternate between the two workspace slots, so the H2D copy of one
+	   chunk overlaps the kernel of the previous one */
+	{
+		const size_t chunk = (size_t)1 << 16;
+		size_t off, c;
+		for (off = 0, c = 0; off < count; off += chunk, ++c)
+		{
+			const size_t n = count - off < chunk ? count - off : chunk;
+			b2g_slot* sl = b2g_slot_get((int)c);
+			if ((code = stage_in(sl, 0, hashes + 32 * off, 32 * n, &d_h)) ||
+				(code = stage_in(sl, 1, sigs + 48 * off, 48 * n, &d_s)) ||
+				(code = stage_in(sl, 2, pubkeys + 64 * off, 64 * n, &d_p)) ||
+				(code = b2g_slot_buf(sl, 3, 4 * n, &d_st)))
+				goto done;
+			if ((code = b2g_bignVerifyBatch_dev(d_st, oid_der, oid_len, d_h, d_s, d_p, n, sl->stream)))
+				goto done;
+			CU(cudaMemcpyAsync(status + off, d_st, 4 * n, cudaMemcpyDeviceToHost, sl->stream), "D2H(bign status)");
+		}
+		CU(cudaStreamSynchronize(s0->stream), "sync(bign verify)");
+		CU(cudaStreamSynchronize(s1->stream), "sync(bign verify)");
+	}
 done:
 	if (code)
-		cudaStreamSynchronize(s0->stream);
+		cudaStreamSynchronize(s0->stream), cudaStreamSynchronize(s1->stream);
 	b2g_unlock();
 	return code;
 }

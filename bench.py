@@ -35,6 +35,9 @@ CFG = {
                      units=1 << 26, unit_bytes=16, dtype="u32"),
     "bash512": dict(metric="bash-512 GB/s hashed", unit="GB/s", workload="bash-512 batch: 2^20 messages x 4 KiB per GPU",
                     units=1 << 20, unit_bytes=4096, dtype="u64"),
+    "belt_ecb": dict(metric="belt-ECB key-agility GB/s", unit="GB/s",
+                     workload="belt-ECB key agility: 2^26 blocks under 2^26 independent 32-byte keys per GPU",
+                     units=1 << 26, unit_bytes=16, dtype="u32"),
     "bign_verify": dict(metric="bign-curve256v1 verifies/s", unit="verifies/s",
                         workload="bign-curve256v1 batch verify: 2^18 signatures per GPU (1/16 corrupted)",
                         units=1 << 18, unit_bytes=148, dtype="u32"),
@@ -43,7 +46,7 @@ CFG = {
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the bench
 # configuration, from the committed `ncu --set full` captures (profiles/r01_ncu_raw_*.csv)
-NCU_TRAFFIC = {"belt_ctr": 0.13e6 + 1.0142e9, "bash512": 4.4244e9 + 14.5e6, "bign_verify": 151.7e6 + 340.8e6}
+NCU_TRAFFIC = {"belt_ecb": None, "belt_ctr": 0.13e6 + 1.0142e9, "bash512": 4.4244e9 + 14.5e6, "bign_verify": 151.7e6 + 340.8e6}
 
 
 def hbm_peak():
@@ -78,7 +81,8 @@ class CpuArm:
 
     def __init__(self):
         self.h = C.CDLL(os.path.join(REF_DIR, "libcpuharness.so"))
-        for n in ("harness_bash", "harness_belt_ctr", "harness_bign_verify", "harness_bign_sign2", "harness_bign_pubkey"):
+        for n in ("harness_bash", "harness_belt_ctr", "harness_belt_ecb_multikey", "harness_bign_verify",
+                  "harness_bign_sign2", "harness_bign_pubkey"):
             getattr(self.h, n).restype = C.c_double
         self.threads = host_threads()
         ref64 = os.path.join(REF_DIR, "libbee2ref_64.so")
@@ -111,6 +115,10 @@ class CpuArm:
         dt = self.h.harness_belt_ctr(self.lib.encode(), self.is_port, self._p(buf), None, C.c_size_t(unit),
                                      C.c_size_t(buf.size // unit), key, iv, self.threads)
         return dt
+
+    def ecb_multikey(self, blocks, keys):
+        return self.h.harness_belt_ecb_multikey(self.lib.encode(), self.is_port, self._p(blocks), self._p(keys),
+                                                C.c_size_t(blocks.shape[0]), self.threads)
 
     def verify(self, hashes, sigs, pubs):
         st = np.zeros(hashes.shape[0], dtype=np.uint32)
@@ -145,6 +153,15 @@ class CpuArm:
             dt = self.belt_ctr(buf, bytes(range(32)), bytes(16))
             state["last"] = buf
             units, desc = nbytes, f"{nbytes >> 20} MiB keystream, {self.threads} independent beltCTR shards"
+        elif path == "belt_ecb":
+            n = (1 << 14) * self.threads if rate is None else int(min(max(rate * target_s / 16, 1 << 14), 1 << 26))
+            pair = state.get(("ecb", n))
+            if pair is None:
+                pair = state[("ecb", n)] = (rng.integers(0, 256, (n, 16), dtype=np.uint8),
+                                            rng.integers(0, 256, (n, 32), dtype=np.uint8))
+            dt = self.ecb_multikey(*pair)
+            state["last"] = pair
+            units, desc = n * 16, f"{n} (key, block) pairs via beltECBEncr(16 B, key_i)"
         elif path == "bash512":
             n = 256 * self.threads if rate is None else int(min(max(rate * target_s / 4096, 64), 1 << 20))
             msgs = state.get(("bashmsgs", n))
@@ -190,6 +207,8 @@ class CpuArm:
             return self.belt_ctr(last, bytes(range(32)), bytes(16))
         if path == "bash512":
             return self.bash(last)[0]
+        if path == "belt_ecb":
+            return self.ecb_multikey(*last)
         return self.verify(*last)[0]
 
     def baseline(self, path, target_s=4.0):
@@ -283,7 +302,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--paths", default="belt_ctr,bash512,bign_verify",
+    ap.add_argument("--paths", default="belt_ctr,bash512,bign_verify,belt_ecb",
                     help="comma list; the first one is the headline metric of the JSON line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -409,6 +428,36 @@ def main():
                 assert harr[: 1 << 20].tobytes() == out[: 1 << 20].cpu().numpy().tobytes() or rank != 0
                 del host, harr
             del out
+        elif path == "belt_ecb":
+            g = torch.Generator(device=dev).manual_seed(3 + rank)
+            keys = torch.randint(0, 256, (units, 32), dtype=torch.uint8, device=dev, generator=g)
+            blocks = torch.randint(0, 256, (units, 16), dtype=torch.uint8, device=dev, generator=g)
+            first_blocks, first_keys = blocks[:4096].cpu().numpy().copy(), keys[:4096].cpu().numpy().copy()
+            fn = lambda: b.beltECBEncrBatch_dev(blocks.data_ptr(), keys.data_ptr(), units, stream)  # noqa: E731
+            fn()
+            torch.cuda.synchronize()
+            # spot parity against the host-pointer entry point of the same library (itself parity-tested)
+            assert np.array_equal(blocks[:4096].cpu().numpy(), b.beltECBEncrBatch(first_blocks, first_keys))
+            total, launches = timed(fn, args.steps, args.warmup, flush=False)
+            r["l2"] = "keys + blocks 3 GiB per step > 126 MB L2, no flush needed"
+            algo_bytes = units * 64                    # 32 key + 16 in + 16 out per block
+            r["checksum"] = int(blocks[:: 1 << 12].to(torch.int64).sum().item())
+            if not args.no_e2e:
+                hk = torch.empty((units, 32), dtype=torch.uint8).pin_memory()
+                hb = torch.empty((units, 16), dtype=torch.uint8).pin_memory()
+                hk.copy_(keys), hb.copy_(blocks)
+                nk, nb = hk.numpy(), hb.numpy()
+                L = b.lib()
+
+                def e2e_fn():
+                    c = L.beltECBEncrBatch(nb.ctypes.data, nk.ctypes.data, units)
+                    assert c == 0, c
+                t = timed_host(e2e_fn, e2e_steps, 1)
+                r["e2e"] = {"value": world * units * 16 * e2e_steps / t / scale, "unit": cfg["unit"],
+                            "h2d_bytes_per_step": units * 48, "d2h_bytes_per_step": units * 16,
+                            "call": "beltECBEncrBatch(pinned host blocks 1 GiB + keys 2 GiB, in place)", "steps": e2e_steps}
+                del hk, hb, nk, nb
+            del keys, blocks
         elif path == "bash512":
             g = torch.Generator(device=dev).manual_seed(1 + rank)
             msgs = torch.randint(0, 256, (units, 4096), dtype=torch.uint8, device=dev, generator=g)
@@ -492,6 +541,11 @@ def main():
         r["issue_roofline"] = {"bound": "lds32 (224 conflict-free LDS.32 per block)", "achieved_Tops": blocks_s * 224 / 1e12,
                                "peak_Tops": issue.get("lds32"), "frac": blocks_s * 224 / 1e12 / issue["lds32"] if issue.get("lds32", 0) > 0 else None,
                                "alu_ops_per_block": 456, "alu_frac": blocks_s * 456 / 1e12 / issue["lop3"] if issue.get("lop3", 0) > 0 else None}
+    if "belt_ecb" in results:
+        r = results["belt_ecb"]
+        blocks_s = r["value"] * 1e9 / 16 / world
+        r["issue_roofline"] = {"bound": "lds32 (224 conflict-free LDS.32 per block)", "achieved_Tops": blocks_s * 224 / 1e12,
+                               "peak_Tops": issue.get("lds32"), "frac": blocks_s * 224 / 1e12 / issue["lds32"] if issue.get("lds32", 0) > 0 else None}
     if "bash512" in results:
         r = results["bash512"]
         f_s = r["value"] * 1e9 / 4096 * 65 / world

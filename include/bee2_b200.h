@@ -97,11 +97,18 @@ err_t bashHash(octet hash[], size_t l, const void* src, size_t count);
    (l/4 octets) at hashes + i*(l/4). Same checks as bashHash. */
 err_t bashHashBatch(octet* hashes, size_t l, const void* msgs, size_t msg_len,
 	size_t stride, size_t count);
+/* ragged batch (the many-files case of cmd/bsum/bsum.c:142-200): message i is
+   data[offsets[i] .. offsets[i] + lens[i]); digest i at hashes + i*(l/4). Sort by length for
+   best warp efficiency (a warp runs as long as its longest message). */
+err_t bashHashBatchV(octet* hashes, size_t l, const void* data, size_t data_len, const u64* offsets,
+	const u64* lens, size_t count);
 /* batch: bashF on `count` independent 192-octet states, in place */
 err_t bashFBatch(octet* blocks, size_t count);
 /* device */
 err_t b2g_bashHashBatch_dev(void* d_hashes, size_t l, const void* d_msgs, size_t msg_len,
 	size_t stride, size_t count, void* stream);
+err_t b2g_bashHashBatchV_dev(void* d_hashes, size_t l, const void* d_data, const void* d_offsets,
+	const void* d_lens, size_t count, void* stream);
 err_t b2g_bashFBatch_dev(void* d_blocks, size_t count, void* stream);
 
 /* ======================================================================= belt (STB 34.101.31) */

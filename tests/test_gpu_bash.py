@@ -64,6 +64,23 @@ def test_batch_every_level_random_lengths(l):
             assert np.array_equal(got, want), (l, msg_len, stride)
 
 
+def test_ragged_batch_bsum_style():
+    """Many messages of different lengths and alignments in one buffer (the bsum case)."""
+    rng = np.random.default_rng(21)
+    lens = np.concatenate([rng.integers(0, 700, 300), [0, 1, 63, 64, 65, 4096, 10_000]]).astype(np.uint64)
+    gaps = rng.integers(0, 9, lens.size).astype(np.uint64)
+    offsets = np.cumsum(np.concatenate([[0], (lens + gaps)[:-1]])).astype(np.uint64)
+    data = rng.integers(0, 256, int(offsets[-1] + lens[-1]) + 16, dtype=np.uint8)
+    for l in (128, 192, 256, 80):
+        got = b.bashHashBatchV(l, data, offsets, lens)
+        for i in range(lens.size):
+            m = data[int(offsets[i]):int(offsets[i] + lens[i])].tobytes()
+            assert got[i].tobytes() == o.bashHash(l, m), (l, i)
+    with pytest.raises(b.Bee2Error) as e:
+        b.bashHashBatchV(256, data, np.array([data.size], dtype=np.uint64), np.array([1], dtype=np.uint64))
+    assert e.value.code == b.ERR_BAD_INPUT
+
+
 def test_bashFBatch_random():
     rng = np.random.default_rng(1)
     st = rng.integers(0, 256, size=(300, 192), dtype=np.uint8)
