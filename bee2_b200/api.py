@@ -14,12 +14,13 @@ import numpy as np
 
 __all__ = [
     "ERR_OK", "ERR_BAD_INPUT", "ERR_OUTOFMEMORY", "ERR_NOT_IMPLEMENTED", "ERR_FILE_NOT_FOUND",
-    "ERR_BAD_OID", "ERR_BAD_PARAMS", "ERR_BAD_PRIVKEY", "ERR_BAD_PUBKEY", "ERR_BAD_SIG",
+    "ERR_BAD_OID", "ERR_BAD_PARAMS", "ERR_BAD_PRIVKEY", "ERR_BAD_PUBKEY", "ERR_BAD_SIG", "ERR_BAD_MAC",
     "ERR_B2G_NO_DEVICE", "ERR_B2G_CUDA", "Bee2Error", "BignParams", "lib", "lib_path",
     "b2g_init", "b2g_last_error", "b2g_sm_count", "b2g_launch_count", "b2g_sync", "b2g_microbench",
     "bashF", "bashHash", "bashHashBatch", "bashHashBatchV", "bashFBatch", "BashHash",
     "beltH", "beltKeyExpand2", "beltBlockEncr", "beltBlockDecr", "beltECBEncr", "beltECBDecr",
     "beltECBEncrBatch", "BeltECB", "BeltCTR", "beltCTR", "beltCTRKeystream", "beltHash", "beltHashBatch",
+    "beltDWPWrap", "beltDWPUnwrap", "beltDWPMac_dev",
     "bignParamsStd", "bignVerify", "bignVerifyBatch", "bignSign2", "bignSign2Batch",
     "bignPubkeyCalc", "bignPubkeyCalcBatch", "ecMulABatch", "ecAddMulABatch", "OID_BELT_HASH_DER",
     "bashHashBatch_dev", "bashFBatch_dev", "beltCTR_dev", "beltECB_dev", "beltECBEncrBatch_dev",
@@ -37,6 +38,7 @@ ERR_BAD_PARAMS = 502
 ERR_BAD_PRIVKEY = 504
 ERR_BAD_PUBKEY = 505
 ERR_BAD_SIG = 510
+ERR_BAD_MAC = 511
 ERR_B2G_NO_DEVICE = 9001
 ERR_B2G_CUDA = 9002
 
@@ -104,6 +106,9 @@ def _declare(L: C.CDLL) -> None:
         "beltCTR": (u32, [vp, vp, sz, vp, sz, vp]), "beltHash": (u32, [vp, vp, sz]),
         "beltCTRKeystream": (u32, [vp, sz, vp, sz, vp]), "beltECBEncrBatch": (u32, [vp, vp, sz]),
         "beltHashBatch": (u32, [vp, vp, sz, sz, sz]),
+        "beltDWPWrap": (u32, [vp, vp, vp, sz, vp, sz, vp, sz, vp]),
+        "beltDWPUnwrap": (u32, [vp, vp, sz, vp, sz, vp, vp, sz, vp]),
+        "b2g_beltDWPMac_dev": (u32, [vp, vp, sz, vp, sz, vp, vp, vp, vp]),
         "b2g_beltCTR_dev": (u32, [vp, vp, sz, vp, vp, u64, vp]), "b2g_beltECB_dev": (u32, [vp, vp, sz, vp, ci, vp]),
         "b2g_beltECBEncrBatch_dev": (u32, [vp, vp, sz, vp]), "b2g_beltHashBatch_dev": (u32, [vp, vp, sz, sz, sz, vp]),
         "bignParamsStd": (u32, [vp, C.c_char_p]), "bignVerify": (u32, [vp, vp, sz, vp, vp, vp]),
@@ -384,6 +389,35 @@ def beltCTRKeystream(count: int, key: bytes, iv: bytes, out: Optional[np.ndarray
     o = out if out is not None else _out(count)
     _chk("beltCTRKeystream", lib().beltCTRKeystream(o.ctypes.data, count, kp, kn, ivp))
     return o if out is not None else o.tobytes()
+
+
+def beltDWPWrap(src1, src2, key: bytes, iv: bytes):
+    """belt.h:984-1007 — returns (ciphertext bytes, mac[8])"""
+    k1, p1, n1 = _buf(src1)
+    k2, p2, n2 = _buf(src2)
+    kk, kp, kn = _buf(key)
+    ki, ivp, _ = _buf(iv)
+    out, mac = _out(n1), _out(8)
+    _chk("beltDWPWrap", lib().beltDWPWrap(out.ctypes.data, mac.ctypes.data, p1, n1, p2, n2, kp, kn, ivp))
+    return out.tobytes(), mac.tobytes()
+
+
+def beltDWPUnwrap(src1, src2, mac: bytes, key: bytes, iv: bytes):
+    """belt.h:1009-1030 — returns (err_t, plaintext bytes or None)"""
+    k1, p1, n1 = _buf(src1)
+    k2, p2, n2 = _buf(src2)
+    km, mp, _ = _buf(mac)
+    kk, kp, kn = _buf(key)
+    ki, ivp, _ = _buf(iv)
+    out = _out(n1)
+    code = lib().beltDWPUnwrap(out.ctypes.data, p1, n1, p2, n2, mp, kp, kn, ivp)
+    return code, (out.tobytes() if code == ERR_OK else None)
+
+
+def beltDWPMac_dev(d_mac: int, d_crit: int, n1: int, d_open: int, n2: int, key_words: np.ndarray,
+                   ctr_words: np.ndarray, d_scratch: int, stream: int = 0) -> None:
+    _chk("b2g_beltDWPMac_dev", lib().b2g_beltDWPMac_dev(d_mac, d_crit, n1, d_open, n2, key_words.ctypes.data,
+                                                        ctr_words.ctypes.data, d_scratch, stream))
 
 
 def beltHash(src: bytes) -> bytes:

@@ -1,0 +1,182 @@
+// belt_dwp.cu — the belt-DWP authentication tag (STB 34.101.31 "data wrap") for sm_100a.
+//
+// Replaces the block loop of beltDWPStepI / StepA / StepG (belt_dwp.c:73-207): a Horner
+// evaluation t <- (t ^ B_i) * r over GF(2^128), r = E_K(E_K(iv)), t_0 = beltH()[0..16), over the
+// open data, the critical data (both zero-padded to whole blocks) and the length block, followed
+// by mac = E_K(t)[0..8). Encryption itself is the belt-CTR kernel of belt.cu.
+//
+// The Horner chain is sequential in the reference; here it is a polynomial evaluation
+//     t_N = t_0 r^N  ^  sum_i B_i r^(N - i + 1)
+// cut into one contiguous chunk of K blocks per thread. Every thread runs Horner over its chunk
+// (multiplication by the fixed r through conflict-free 4-bit window tables in shared memory),
+// weights the result with r^(number of blocks after the chunk) (square-and-multiply: squarings
+// are bit spreads) and the weighted chunk values are XOR-reduced (warp shuffles + one atomicXor
+// per warp and word). A one-thread kernel encrypts the sum.
+#include "belt_dev.cuh"
+#include "gf128.cuh"
+
+#define DWP_THREADS 256
+#define DWP_MIN_CHUNK 32
+
+struct DwpArgs
+{
+	const u8* open;    // src2: open (authenticated only) data
+	u64 n2;
+	const u8* crit;    // ciphertext
+	u64 n1;
+	u64 nI, nA, N;     // blocks of open data, of critical data, total (+1 length block)
+	u64 K;             // blocks per thread
+	BeltKey key;
+	uint4 s;           // E_K(iv)
+	u32* acc;          // 4 words, zeroed: XOR of the weighted chunk values
+};
+
+// block i (0-based) of the sequence open || critical || length, zero-padded
+__device__ __forceinline__ gf128 dwp_block(const DwpArgs& a, u64 i)
+{
+	gf128 b;
+	if (i >= a.nI + a.nA)
+	{
+		const u64 l0 = a.n2 << 3, l1 = a.n1 << 3;   // belt_dwp.c:185-187: |I| || |A| in bits
+		b.w[0] = (u32)l0, b.w[1] = (u32)(l0 >> 32), b.w[2] = (u32)l1, b.w[3] = (u32)(l1 >> 32);
+		return b;
+	}
+	const bool in_open = i < a.nI;
+	const u8* base = in_open ? a.open : a.crit;
+	const u64 off = 16 * (in_open ? i : i - a.nI);
+	const u64 total = in_open ? a.n2 : a.n1;
+	const u8* p = base + off;
+	if (off + 16 <= total && ((uintptr_t)p & 15) == 0)
+	{
+		const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+		b.w[0] = v.x, b.w[1] = v.y, b.w[2] = v.z, b.w[3] = v.w;
+		return b;
+	}
+	const u32 valid = (u32)(total - off < 16 ? total - off : 16);
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+	{
+		u32 w = 0;
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+			if ((u32)(4 * k + j) < valid)
+				w |= (u32)p[4 * k + j] << (8 * j);
+		b.w[k] = w;
+	}
+	return b;
+}
+
+__global__ void __launch_bounds__(DWP_THREADS) belt_dwp_mac_kernel(const DwpArgs a)
+{
+	extern __shared__ __align__(1024) u8 sm[];
+	u8* tab = sm;                                             // GF_TAB_BYTES
+	u32* sbox = reinterpret_cast<u32*>(sm + GF_TAB_BYTES);    // 256 words
+	u32* rsh = sbox + 256;                                    // 4 words: r
+	BeltSmallT::fill(sbox);
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		// r <- E_K(s) (belt_dwp.c:52-55)
+		const BeltSmallT S(sbox);
+		u32 x0 = a.s.x, x1 = a.s.y, x2 = a.s.z, x3 = a.s.w;
+		belt_encr(S, x0, x1, x2, x3, a.key.k);
+		rsh[0] = x0, rsh[1] = x1, rsh[2] = x2, rsh[3] = x3;
+	}
+	__syncthreads();
+	gf128 r;
+#pragma unroll
+	for (int i = 0; i < 4; ++i) r.w[i] = rsh[i];
+	gf_tab_build(tab, r);
+	__syncthreads();
+
+	const u64 j = (u64)blockIdx.x * DWP_THREADS + threadIdx.x;
+	const u64 b0 = j * a.K;
+	gf128 w = {{0, 0, 0, 0}};
+	if (b0 < a.N)
+	{
+		const u64 b1 = b0 + a.K < a.N ? b0 + a.K : a.N;
+		gf128 acc = {{0, 0, 0, 0}};
+		if (j == 0)
+		{
+			// t_0 = beltH()[0..16) (belt_dwp.c:60)
+			const u32* H32 = reinterpret_cast<const u32*>(c_beltH);
+#pragma unroll
+			for (int i = 0; i < 4; ++i) acc.w[i] = H32[i];
+		}
+#pragma unroll 1
+		for (u64 i = b0; i < b1; ++i)
+			acc = gf_mul_tab(tab, gf_xor(acc, dwp_block(a, i)));
+		// weight: r^(blocks after this chunk)
+		const u64 e = a.N - b1;
+		w = e ? gf_mul(acc, gf_pow_r(tab, e)) : acc;
+	}
+	// XOR-reduce over the warp, then one atomic per word
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+	{
+		u32 v = w.w[k];
+#pragma unroll
+		for (int d = 16; d; d >>= 1) v ^= __shfl_xor_sync(0xFFFFFFFFu, v, d);
+		if ((threadIdx.x & 31) == 0 && v)
+			atomicXor(a.acc + k, v);
+	}
+}
+
+// mac <- E_K(t)[0..8) (belt_dwp.c:196-206)
+__global__ void belt_dwp_fin_kernel(u8* mac, const u32* acc, const BeltKey key)
+{
+	__shared__ u32 sbox[256];
+	BeltSmallT::fill(sbox);
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		const BeltSmallT S(sbox);
+		u32 x0 = acc[0], x1 = acc[1], x2 = acc[2], x3 = acc[3];
+		belt_encr(S, x0, x1, x2, x3, key.k);
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			mac[i] = (u8)(x0 >> (8 * i)), mac[4 + i] = (u8)(x1 >> (8 * i));
+	}
+}
+
+extern "C" u32 b2g_beltdwp_upload_tables(const u8 H[256])
+{
+	const u32 e = belt_upload_H(H);
+	if (e) return e;
+	if (cudaFuncSetAttribute(belt_dwp_mac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			GF_TAB_BYTES + 2048) != cudaSuccess)
+		return b2g_check_launch("cudaFuncSetAttribute(belt_dwp)");
+	return B2G_OK;
+}
+
+// d_mac (8 octets) <- DWP tag of (open data d_open[n2], critical data d_crit[n1]) under the
+// expanded key and ctr0 = E_K(iv); d_scratch: 16 octets of device scratch
+extern "C" u32 b2g_beltDWPMac_dev(void* d_mac, const void* d_crit, size_t n1, const void* d_open, size_t n2,
+	const u32 key[8], const u32 ctr0[4], void* d_scratch, void* stream)
+{
+	u32 e = b2g_ensure_device();
+	if (e) return e;
+	if ((uintptr_t)d_scratch & 3) return B2G_BAD_INPUT;
+	cudaStream_t st = (cudaStream_t)stream;
+	DwpArgs a;
+	a.open = (const u8*)d_open, a.n2 = n2, a.crit = (const u8*)d_crit, a.n1 = n1;
+	a.nI = ((u64)n2 + 15) / 16, a.nA = ((u64)n1 + 15) / 16, a.N = a.nI + a.nA + 1;
+	for (int i = 0; i < 8; ++i) a.key.k[i] = key[i];
+	a.s = make_uint4(ctr0[0], ctr0[1], ctr0[2], ctr0[3]);
+	a.acc = (u32*)d_scratch;
+	// one chunk per thread; at most 2 CTAs per SM worth of threads, at least DWP_MIN_CHUNK blocks each
+	const u64 tmax = (u64)b2g_sm_count() * 2 * DWP_THREADS;
+	u64 K = (a.N + tmax - 1) / tmax;
+	if (K < DWP_MIN_CHUNK) K = DWP_MIN_CHUNK;
+	a.K = K;
+	const u64 nthreads = (a.N + K - 1) / K;
+	const u32 grid = (u32)((nthreads + DWP_THREADS - 1) / DWP_THREADS);
+	if (cudaMemsetAsync(d_scratch, 0, 16, st) != cudaSuccess)
+		return b2g_check_launch("cudaMemsetAsync(dwp)");
+	belt_dwp_mac_kernel<<<grid, DWP_THREADS, GF_TAB_BYTES + 2048, st>>>(a);
+	b2g_note_launch();
+	if ((e = b2g_check_launch("belt_dwp_mac_kernel"))) return e;
+	belt_dwp_fin_kernel<<<1, 32, 0, st>>>((u8*)d_mac, (const u32*)d_scratch, a.key);
+	b2g_note_launch();
+	return b2g_check_launch("belt_dwp_fin_kernel");
+}

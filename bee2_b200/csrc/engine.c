@@ -108,6 +108,8 @@ u32 b2g_ensure_device(void)
 	if (!code)
 		code = b2g_belt_upload_tables(beltH());
 	if (!code)
+		code = b2g_beltdwp_upload_tables(beltH());
+	if (!code)
 		code = b2g_bash_upload_tables();
 	if (!code)
 		code = b2g_bign_upload_tables(beltH());

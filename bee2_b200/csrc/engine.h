@@ -36,6 +36,7 @@ u32 b2g_slot_buf(b2g_slot* s, int which, size_t bytes, void** out);
 /* kernels' device-level launchers that are not part of the public header */
 u32 b2g_belt_upload_tables(const octet H[256]);
 u32 b2g_bash_upload_tables(void);
+u32 b2g_beltdwp_upload_tables(const octet H[256]);
 u32 b2g_bign_upload_tables(const octet H[256]);
 u32 b2g_bignSign2Batch_t_dev(void* d_status, void* d_sigs, const octet oid_der[], size_t oid_len,
 	const void* d_hashes, const void* d_privkeys, size_t count, const void* t, size_t t_len, void* stream);

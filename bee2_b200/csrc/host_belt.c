@@ -400,3 +400,88 @@ err_t beltHash(octet hash[32], const void* src, size_t count)
 		return ERR_BAD_INPUT;
 	return beltHashBatch(hash, src, count, count, 1);
 }
+
+/* ---------------------------------------------------------------- belt-DWP (belt_dwp.c:250-330) */
+/* One-shot AEAD on whole buffers: the data stay on the device between the CTR pass (belt.cu) and
+   the tag pass (belt_dwp.cu). */
+static err_t dwp_run(void* dest, octet mac_out[8], const void* src1, size_t count1, const void* src2,
+	size_t count2, const octet key[], size_t len, const octet iv[16], const octet* expect_mac)
+{
+	err_t code;
+	belt_ctr_st st;
+	b2g_slot* sl;
+	void *d_crit, *d_open, *d_small;
+	octet mac[8];
+	if (!key_len_ok(len) || (count1 && (!src1 || !dest)) || (count2 && !src2) || !key || !iv)
+		return ERR_BAD_INPUT;
+	beltKeyExpand2(st.key, key, len);
+	memcpy(st.ctr, iv, 16);
+	if ((code = blocks_small(st.ctr, 1, st.key, 0)))   /* s = E_K(iv) */
+		return code;
+	b2g_lock();
+	sl = b2g_slot_get(0);
+	if ((code = b2g_slot_buf(sl, 0, (count1 + 15) & ~(size_t)15, &d_crit)) ||
+		(code = b2g_slot_buf(sl, 1, count2, &d_open)) || (code = b2g_slot_buf(sl, 2, 64, &d_small)))
+		goto done;
+	if (count1)
+		CU(cudaMemcpyAsync(d_crit, src1, count1, cudaMemcpyHostToDevice, sl->stream), "H2D(dwp data)");
+	if (count2)
+		CU(cudaMemcpyAsync(d_open, src2, count2, cudaMemcpyHostToDevice, sl->stream), "H2D(dwp open)");
+	if (!expect_mac)
+	{
+		/* wrap: encrypt, then authenticate the ciphertext (belt_dwp.c:277-282) */
+		if (count1 && (code = b2g_beltCTR_dev(d_crit, d_crit, count1, st.key, st.ctr, 0, sl->stream)))
+			goto done;
+		if ((code = b2g_beltDWPMac_dev(d_small, d_crit, count1, d_open, count2, st.key, st.ctr,
+				(octet*)d_small + 16, sl->stream)))
+			goto done;
+		CU(cudaMemcpyAsync(mac, d_small, 8, cudaMemcpyDeviceToHost, sl->stream), "D2H(dwp mac)");
+		if (count1)
+			CU(cudaMemcpyAsync(dest, d_crit, count1, cudaMemcpyDeviceToHost, sl->stream), "D2H(dwp data)");
+		CU(cudaStreamSynchronize(sl->stream), "sync(dwp)");
+		memcpy(mac_out, mac, 8);
+	}
+	else
+	{
+		/* unwrap: check the tag first; a wrong tag leaves dest untouched (belt_dwp.c:316-324) */
+		if ((code = b2g_beltDWPMac_dev(d_small, d_crit, count1, d_open, count2, st.key, st.ctr,
+				(octet*)d_small + 16, sl->stream)))
+			goto done;
+		CU(cudaMemcpyAsync(mac, d_small, 8, cudaMemcpyDeviceToHost, sl->stream), "D2H(dwp mac)");
+		CU(cudaStreamSynchronize(sl->stream), "sync(dwp)");
+		if (memcmp(mac, expect_mac, 8) != 0)
+		{
+			code = ERR_BAD_MAC;
+			goto done;
+		}
+		if (count1)
+		{
+			if ((code = b2g_beltCTR_dev(d_crit, d_crit, count1, st.key, st.ctr, 0, sl->stream)))
+				goto done;
+			CU(cudaMemcpyAsync(dest, d_crit, count1, cudaMemcpyDeviceToHost, sl->stream), "D2H(dwp data)");
+			CU(cudaStreamSynchronize(sl->stream), "sync(dwp)");
+		}
+	}
+done:
+	if (code && code != ERR_BAD_MAC)
+		cudaStreamSynchronize(sl->stream);
+	b2g_unlock();
+	return code;
+}
+
+err_t beltDWPWrap(void* dest, octet mac[8], const void* src1, size_t count1, const void* src2,
+	size_t count2, const octet key[], size_t len, const octet iv[16])
+{
+	if (!mac)
+		return ERR_BAD_INPUT;
+	return dwp_run(dest, mac, src1, count1, src2, count2, key, len, iv, 0);
+}
+
+err_t beltDWPUnwrap(void* dest, const void* src1, size_t count1, const void* src2, size_t count2,
+	const octet mac[8], const octet key[], size_t len, const octet iv[16])
+{
+	octet unused[8];
+	if (!mac)
+		return ERR_BAD_INPUT;
+	return dwp_run(dest, unused, src1, count1, src2, count2, key, len, iv, mac);
+}

@@ -52,6 +52,7 @@ typedef u32 err_t;
 #define ERR_BAD_PRIVKEY 504u
 #define ERR_BAD_PUBKEY 505u
 #define ERR_BAD_SIG 510u
+#define ERR_BAD_MAC 511u
 /* engine-specific (outside the reference's ranges) */
 #define ERR_B2G_NO_DEVICE 9001u   /* no usable CUDA device / driver */
 #define ERR_B2G_CUDA 9002u        /* a CUDA call failed; see b2g_last_error() */
@@ -138,6 +139,13 @@ err_t beltCTR(void* dest, const void* src, size_t count, const octet key[], size
 	const octet iv[16]);
 /* drop-in: belt.h (belt_hash.c:174-190) one-shot only */
 err_t beltHash(octet hash[32], const void* src, size_t count);
+/* drop-in: belt.h:984-1030 (belt_dwp.c:250-330) — authenticated encryption of (critical src1,
+   open src2): dest = CTR(src1), mac = 8-octet tag; Unwrap returns ERR_BAD_MAC and leaves dest
+   untouched when the tag differs. Whole buffers are staged on the device. */
+err_t beltDWPWrap(void* dest, octet mac[8], const void* src1, size_t count1, const void* src2,
+	size_t count2, const octet key[], size_t len, const octet iv[16]);
+err_t beltDWPUnwrap(void* dest, const void* src1, size_t count1, const void* src2, size_t count2,
+	const octet mac[8], const octet key[], size_t len, const octet iv[16]);
 /* batch: pure keystream (beltCTR of zeros) */
 err_t beltCTRKeystream(void* dest, size_t count, const octet key[], size_t len,
 	const octet iv[16]);
@@ -150,6 +158,10 @@ err_t beltHashBatch(octet* hashes, const void* msgs, size_t msg_len, size_t stri
    (keystream only) or equal to dest. key = expanded key (beltKeyExpand2). */
 err_t b2g_beltCTR_dev(void* d_dest, const void* d_src, size_t count, const u32 key[8],
 	const u32 ctr0[4], u64 first_block, void* stream);
+/* device: d_mac[8] = belt-DWP tag over (d_open[n2] open, d_crit[n1] critical = ciphertext);
+   d_scratch = 16 octets of device scratch (4-aligned) */
+err_t b2g_beltDWPMac_dev(void* d_mac, const void* d_crit, size_t n1, const void* d_open, size_t n2,
+	const u32 key[8], const u32 ctr0[4], void* d_scratch, void* stream);
 err_t b2g_beltECB_dev(void* d_dest, const void* d_src, size_t nblocks, const u32 key[8],
 	int decrypt, void* stream);
 err_t b2g_beltECBEncrBatch_dev(void* d_blocks, const void* d_keys32, size_t count, void* stream);

@@ -626,3 +626,93 @@ u32 orc_bignSign2_128(u8 sig[48], const u8* oid_der, size_t oid_len, const u8 ha
 	fe_to(sig + 16, s1);
 	return ORC_OK;
 }
+
+/* ======================================================================= belt-DWP (belt_dwp.c:45-330) */
+
+/* c = a * b in GF(2)[x]/(x^128 + x^7 + x^2 + x + 1); bit i of the 128-bit LE integer is the
+   coefficient of x^i (belt_lcl.c:119-132: ppMul + ppRedBelt, pp_red.c:129-141) */
+static void gf128_mul(u64 c[2], const u64 a[2], const u64 b[2])
+{
+	u64 r0 = 0, r1 = 0, v0 = b[0], v1 = b[1];
+	int i;
+	for (i = 0; i < 128; ++i)
+	{
+		if (a[i / 64] >> (i % 64) & 1)
+			r0 ^= v0, r1 ^= v1;
+		{
+			/* v <- v * x mod f */
+			const u64 top = v1 >> 63;
+			v1 = v1 << 1 | v0 >> 63;
+			v0 = v0 << 1 ^ (top ? 0x87 : 0);
+		}
+	}
+	c[0] = r0, c[1] = r1;
+}
+
+/* mac state after absorbing `n` octets of one data class (zero-padded to whole blocks) */
+static void dwp_absorb(u64 t[2], const u64 r[2], const u8* p, size_t n)
+{
+	while (n)
+	{
+		u8 blk[16] = {0};
+		u64 x[2];
+		const size_t take = n < 16 ? n : 16;
+		memcpy(blk, p, take), memcpy(x, blk, 16);
+		t[0] ^= x[0], t[1] ^= x[1];
+		gf128_mul(t, t, r);
+		p += take, n -= take;
+	}
+}
+
+static void dwp_mac(u8 mac[8], const u32 key[8], const u32 s[4], const u8* crit, size_t n1, const u8* open, size_t n2)
+{
+	u64 r[2], t[2], len[2];
+	u32 w[4];
+	memcpy(w, s, 16);
+	orc_beltBlockEncr2(w, key);          /* r = E_K(s), s = E_K(iv) (belt_dwp.c:52-55) */
+	memcpy(r, w, 16);
+	memcpy(t, orc_beltH(), 16);
+	dwp_absorb(t, r, open, n2);
+	dwp_absorb(t, r, crit, n1);
+	len[0] = (u64)n2 << 3, len[1] = (u64)n1 << 3;
+	t[0] ^= len[0], t[1] ^= len[1];
+	gf128_mul(t, t, r);
+	memcpy(w, t, 16);
+	orc_beltBlockEncr2(w, key);
+	memcpy(mac, w, 8);
+}
+
+/* belt_dwp.c:250-287: dest = E(src1), mac over (src2 open, dest critical) */
+u32 orc_beltDWPWrap(void* dest, u8 mac[8], const void* src1, size_t n1, const void* src2, size_t n2,
+	const u8* key, size_t len, const u8 iv[16])
+{
+	orc_belt_ctr_st st;
+	u32 s[4];
+	if (len != 16 && len != 24 && len != 32)
+		return ORC_BAD_INPUT;
+	orc_beltCTRStart(&st, key, len, iv);
+	memcpy(s, st.ctr, 16);
+	memmove(dest, src1, n1);
+	orc_beltCTRStepE(dest, n1, &st);
+	dwp_mac(mac, st.key, s, (const u8*)dest, n1, (const u8*)src2, n2);
+	return ORC_OK;
+}
+
+/* belt_dwp.c:289-330: returns 511 (ERR_BAD_MAC) without touching dest when the tag differs */
+u32 orc_beltDWPUnwrap(void* dest, const void* src1, size_t n1, const void* src2, size_t n2,
+	const u8 mac[8], const u8* key, size_t len, const u8 iv[16])
+{
+	orc_belt_ctr_st st;
+	u32 s[4];
+	u8 m[8];
+	if (len != 16 && len != 24 && len != 32)
+		return ORC_BAD_INPUT;
+	orc_beltCTRStart(&st, key, len, iv);
+	memcpy(s, st.ctr, 16);
+	dwp_mac(m, st.key, s, (const u8*)src1, n1, (const u8*)src2, n2);
+	if (memcmp(m, mac, 8) != 0)
+		return 511u;
+	memmove(dest, src1, n1);
+	orc_beltCTRStepE(dest, n1, &st);
+	return ORC_OK;
+}

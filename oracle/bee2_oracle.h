@@ -49,6 +49,11 @@ uint32_t orc_beltCTR(void* dst, const void* src, size_t n, const uint8_t* key, s
 uint32_t orc_beltECBEncr(void* dst, const void* src, size_t n, const uint8_t* key, size_t len);  /* belt_ecb.c:112-134 */
 uint32_t orc_beltECBDecr(void* dst, const void* src, size_t n, const uint8_t* key, size_t len);  /* belt_ecb.c:136-158 */
 void orc_beltHash(uint8_t hash[32], const void* src, size_t n);             /* belt_hash.c:174-190 */
+/* belt-DWP AEAD (belt_dwp.c:250-330); Unwrap returns 511 (ERR_BAD_MAC) on a wrong tag */
+uint32_t orc_beltDWPWrap(void* dest, uint8_t mac[8], const void* src1, size_t n1, const void* src2, size_t n2,
+	const uint8_t* key, size_t len, const uint8_t iv[16]);
+uint32_t orc_beltDWPUnwrap(void* dest, const void* src1, size_t n1, const void* src2, size_t n2,
+	const uint8_t mac[8], const uint8_t* key, size_t len, const uint8_t iv[16]);
 /* key-agility batch: block i under key i (config 5) */
 void orc_beltECBEncrMultiKey(uint8_t* blocks, const uint8_t* keys32, size_t count);
 

@@ -81,6 +81,12 @@ KAT = {
         {"id": "A.23-2", "in": "H[0:32]", "out": "749E4C3653AECE5E48DB4761227742EB6DBE13F4A80F7BEFF1A9CF8D10EE7786"},
         {"id": "A.23-3", "in": "H[0:48]", "out": "9D02EE446FB6A29FE5C982D4B13AF9D3E90861BC4CEF27CF306BFB0B174A154A"},
     ],
+    "beltDWP": [  # belt_test.c:473-497 (A.19-1 wrap), :523-543 (A.20-1 unwrap)
+        {"id": "A.19-1", "op": "wrap", "in": "H[0:16]", "open": "H[16:48]", "key": "H[128:160]", "iv": "H[192:208]",
+         "out": "52C9AF96FF50F64435FC43DEF56BD797", "mac": "3B2E0AEB2B91854B"},
+        {"id": "A.20-1", "op": "unwrap", "in": "H[64:80]", "open": "H[80:112]", "key": "H[160:192]", "iv": "H[208:224]",
+         "out": "DF181ED008A20F43DCBBB93650DAD34B", "mac": "6A2C2C94C4150DC0"},
+    ],
     "beltZerosum": {  # belt_test.c:69-110: XOR over i of X_i ^ Belt_0(X_i) = 0, X_i = (x_i,0,0,0)
         "x": [15014, 124106, 166335, 206478, 313245, 366839, 455597, 502723, 535141, 625112, 659461, 752253, 801048,
               897899, 943850, 1041695, 1101266, 1170856, 1217537, 1248520, 1366084, 1421171, 1448429, 1514215, 1573855,
@@ -137,6 +143,15 @@ def main():
     for klen, n in [(32, 16), (32, 17), (32, 31), (32, 32), (32, 33), (16, 100), (24, 333), (32, 1024)]:
         k, m = rb(klen), rb(n)
         out["beltECB"].append({"key": k.hex(), "in": m.hex(), "out": o.ref_beltECBEncr(m, k).hex()})
+    out["beltDWP"] = []
+    for klen, n1, n2 in [(32, 0, 0), (32, 1, 0), (32, 0, 1), (32, 15, 17), (32, 16, 16), (16, 33, 5), (24, 1000, 77),
+                         (32, 4096, 4096), (32, 5000, 3)]:
+        k, iv, a, b_ = rb(klen), rb(16), rb(n1), rb(n2)
+        import ctypes as C
+        d, m = C.create_string_buffer(max(n1, 1)), C.create_string_buffer(8)
+        assert o.ref().beltDWPWrap(d, m, a, C.c_size_t(n1), b_, C.c_size_t(n2), k, C.c_size_t(klen), iv) == 0
+        out["beltDWP"].append({"key": k.hex(), "iv": iv.hex(), "in": a.hex(), "open": b_.hex(),
+                               "out": d.raw[:n1].hex(), "mac": m.raw.hex()})
     for n in [0, 1, 31, 32, 33, 64, 75, 1000]:
         m = rb(n)
         out["beltHash"].append({"in": m.hex(), "out": o.ref_beltHash(m).hex()})

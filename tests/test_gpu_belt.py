@@ -73,6 +73,40 @@ def test_ctr_A15_A16_split_calls():
     assert e.value.code == b.ERR_BAD_INPUT
 
 
+def test_dwp_A19_A20_and_reference_fixtures():
+    for t in KAT["beltDWP"]:
+        src, op, key, iv = R(t["in"]), R(t["open"]), R(t["key"]), R(t["iv"])
+        if t["op"] == "wrap":
+            out, mac = b.beltDWPWrap(src, op, key, iv)
+            assert out.hex().upper() == t["out"] and mac.hex().upper() == t["mac"]
+        else:
+            code, out = b.beltDWPUnwrap(src, op, bytes.fromhex(t["mac"]), key, iv)
+            assert code == 0 and out.hex().upper() == t["out"]
+            bad = bytearray(bytes.fromhex(t["mac"]))
+            bad[3] ^= 1
+            assert b.beltDWPUnwrap(src, op, bad, key, iv) == (b.ERR_BAD_MAC, None)     # belt_dwp.c:318-322
+    for t in REF["beltDWP"]:
+        a = [bytes.fromhex(t[k]) for k in ("in", "open", "key", "iv")]
+        out, mac = b.beltDWPWrap(*a)
+        assert out.hex() == t["out"] and mac.hex() == t["mac"]
+        assert b.beltDWPUnwrap(out, a[1], mac, a[2], a[3]) == (0, a[0])
+
+
+def test_dwp_random_sizes_vs_oracle():
+    """Sizes that exercise one thread, many threads, many CTAs and ragged tails of both data classes."""
+    rng = np.random.default_rng(31)
+    for n1, n2 in [(0, 0), (5, 0), (0, 5), (511, 513), (16 * 40, 16 * 3), (100_001, 33), (7, 200_003), (3_000_017, 1_000_003)]:
+        key = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+        iv = rng.integers(0, 256, 16, dtype=np.uint8).tobytes()
+        a = rng.integers(0, 256, n1, dtype=np.uint8).tobytes()
+        op = rng.integers(0, 256, n2, dtype=np.uint8).tobytes()
+        want = o.beltDWPWrap(a, op, key, iv)
+        assert b.beltDWPWrap(a, op, key, iv) == want, (n1, n2)
+        assert b.beltDWPUnwrap(want[0], op, want[1], key, iv) == (0, a)
+        if n2:
+            assert b.beltDWPUnwrap(want[0], op[:-1] + bytes([op[-1] ^ 1]), want[1], key, iv)[0] == b.ERR_BAD_MAC
+
+
 def test_hash_A23():
     for t in KAT["beltHash"]:
         assert b.beltHash(R(t["in"])).hex().upper() == t["out"]
