@@ -35,6 +35,9 @@ CFG = {
                      units=1 << 26, unit_bytes=16, dtype="u32"),
     "bash512": dict(metric="bash-512 GB/s hashed", unit="GB/s", workload="bash-512 batch: 2^20 messages x 4 KiB per GPU",
                     units=1 << 20, unit_bytes=4096, dtype="u64"),
+    "belt_dwp": dict(metric="belt-DWP wrap GB/s", unit="GB/s",
+                     workload="belt-DWP authenticated encryption: 1 GiB critical + 4 KiB open data per GPU, one key",
+                     units=1 << 26, unit_bytes=16, dtype="u32"),
     "belt_ecb": dict(metric="belt-ECB key-agility GB/s", unit="GB/s",
                      workload="belt-ECB key agility: 2^26 blocks under 2^26 independent 32-byte keys per GPU",
                      units=1 << 26, unit_bytes=16, dtype="u32"),
@@ -46,7 +49,7 @@ CFG = {
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the bench
 # configuration, from the committed `ncu --set full` captures (profiles/r01_ncu_raw_*.csv)
-NCU_TRAFFIC = {"belt_ecb": None, "belt_ctr": 0.13e6 + 1.0142e9, "bash512": 4.4244e9 + 14.5e6, "bign_verify": 151.7e6 + 340.8e6}
+NCU_TRAFFIC = {"belt_dwp": None, "belt_ecb": None, "belt_ctr": 0.13e6 + 1.0142e9, "bash512": 4.4244e9 + 14.5e6, "bign_verify": 151.7e6 + 340.8e6}
 
 
 def hbm_peak():
@@ -81,7 +84,7 @@ class CpuArm:
 
     def __init__(self):
         self.h = C.CDLL(os.path.join(REF_DIR, "libcpuharness.so"))
-        for n in ("harness_bash", "harness_belt_ctr", "harness_belt_ecb_multikey", "harness_bign_verify",
+        for n in ("harness_bash", "harness_belt_ctr", "harness_belt_dwp", "harness_belt_ecb_multikey", "harness_bign_verify",
                   "harness_bign_sign2", "harness_bign_pubkey"):
             getattr(self.h, n).restype = C.c_double
         self.threads = host_threads()
@@ -115,6 +118,11 @@ class CpuArm:
         dt = self.h.harness_belt_ctr(self.lib.encode(), self.is_port, self._p(buf), None, C.c_size_t(unit),
                                      C.c_size_t(buf.size // unit), key, iv, self.threads)
         return dt
+
+    def belt_dwp(self, buf, key, iv):
+        unit = 1 << 16
+        return self.h.harness_belt_dwp(self.lib.encode(), self.is_port, self._p(buf), C.c_size_t(unit),
+                                       C.c_size_t(buf.size // unit), key, iv, self.threads)
 
     def ecb_multikey(self, blocks, keys):
         return self.h.harness_belt_ecb_multikey(self.lib.encode(), self.is_port, self._p(blocks), self._p(keys),
@@ -153,6 +161,15 @@ class CpuArm:
             dt = self.belt_ctr(buf, bytes(range(32)), bytes(16))
             state["last"] = buf
             units, desc = nbytes, f"{nbytes >> 20} MiB keystream, {self.threads} independent beltCTR shards"
+        elif path == "belt_dwp":
+            nbytes = (4 << 20) * self.threads if rate is None else int(min(max(rate * target_s, 1 << 22), 1 << 30))
+            nbytes -= nbytes % (1 << 16)
+            buf = state.get(("dwpbuf", nbytes))
+            if buf is None:
+                buf = state[("dwpbuf", nbytes)] = np.zeros(nbytes, dtype=np.uint8)
+            dt = self.belt_dwp(buf, bytes(range(32)), bytes(16))
+            state["last"] = buf
+            units, desc = nbytes, f"{nbytes >> 20} MiB, {self.threads} independent beltDWPWrap shards"
         elif path == "belt_ecb":
             n = (1 << 14) * self.threads if rate is None else int(min(max(rate * target_s / 16, 1 << 14), 1 << 26))
             pair = state.get(("ecb", n))
@@ -209,6 +226,8 @@ class CpuArm:
             return self.bash(last)[0]
         if path == "belt_ecb":
             return self.ecb_multikey(*last)
+        if path == "belt_dwp":
+            return self.belt_dwp(last, bytes(range(32)), bytes(16))
         return self.verify(*last)[0]
 
     def baseline(self, path, target_s=4.0):
@@ -302,7 +321,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--paths", default="belt_ctr,bash512,bign_verify,belt_ecb",
+    ap.add_argument("--paths", default="belt_ctr,bash512,bign_verify,belt_ecb,belt_dwp",
                     help="comma list; the first one is the headline metric of the JSON line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -428,6 +447,54 @@ def main():
                 assert harr[: 1 << 20].tobytes() == out[: 1 << 20].cpu().numpy().tobytes() or rank != 0
                 del host, harr
             del out
+        elif path == "belt_dwp":
+            secret = np.random.default_rng(11).integers(0, 256, 48, dtype=np.uint8).tobytes() if rank == 0 else None
+            kiv = shard.broadcast_bytes(secret, 48, device=dev)
+            st = b.BeltCTR(kiv[:32], kiv[32:])
+            key, ctr = st.key_words, st.ctr_words
+            nbytes = units * 16
+            g = torch.Generator(device=dev).manual_seed(4 + rank)
+            data = torch.randint(0, 256, (nbytes,), dtype=torch.uint8, device=dev, generator=g)
+            opn = torch.randint(0, 256, (4096,), dtype=torch.uint8, device=dev, generator=g)
+            small = torch.zeros(64, dtype=torch.uint8, device=dev)
+
+            def fn():
+                b.beltCTR_dev(data.data_ptr(), data.data_ptr(), nbytes, key, ctr, 0, stream)
+                b.beltDWPMac_dev(small.data_ptr(), data.data_ptr(), nbytes, opn.data_ptr(), 4096, key, ctr,
+                                 small.data_ptr() + 16, stream)
+            # parity on the spot: a 1 MiB prefix through the host entry point of the same library
+            pre, po = data[: 1 << 20].cpu().numpy().tobytes(), opn.cpu().numpy().tobytes()
+            want = b.beltDWPWrap(pre, po, kiv[:32], kiv[32:])
+            chk = data[: 1 << 20].clone()
+            b.beltCTR_dev(chk.data_ptr(), chk.data_ptr(), 1 << 20, key, ctr, 0, stream)
+            b.beltDWPMac_dev(small.data_ptr(), chk.data_ptr(), 1 << 20, opn.data_ptr(), 4096, key, ctr,
+                             small.data_ptr() + 16, stream)
+            torch.cuda.synchronize()
+            assert (chk.cpu().numpy().tobytes(), small[:8].cpu().numpy().tobytes()) == want
+            total, launches = timed(fn, args.steps, args.warmup, flush=False)
+            r["l2"] = "data 1 GiB per step > 126 MB L2, no flush needed"
+            algo_bytes = units * 48                    # CTR: 16 read + 16 written, tag: 16 read per block
+            r["checksum"] = int(small[:8].to(torch.int64).sum().item())
+            if not args.no_e2e:
+                hin = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+                hin.copy_(data)
+                hout = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+                ni, no_ = hin.numpy(), hout.numpy()
+                mac = np.zeros(8, dtype=np.uint8)
+                L = b.lib()
+                kb, ib = np.frombuffer(kiv[:32], dtype=np.uint8).copy(), np.frombuffer(kiv[32:], dtype=np.uint8).copy()
+                pon = np.frombuffer(po, dtype=np.uint8).copy()
+
+                def e2e_fn():
+                    c = L.beltDWPWrap(no_.ctypes.data, mac.ctypes.data, ni.ctypes.data, nbytes, pon.ctypes.data, 4096,
+                                      kb.ctypes.data, 32, ib.ctypes.data)
+                    assert c == 0, c
+                t = timed_host(e2e_fn, e2e_steps, 1)
+                r["e2e"] = {"value": world * nbytes * e2e_steps / t / scale, "unit": cfg["unit"],
+                            "h2d_bytes_per_step": nbytes + 4096, "d2h_bytes_per_step": nbytes + 8,
+                            "call": "beltDWPWrap(pinned host 1 GiB -> pinned host 1 GiB + mac)", "steps": e2e_steps}
+                del hin, hout, ni, no_
+            del data
         elif path == "belt_ecb":
             g = torch.Generator(device=dev).manual_seed(3 + rank)
             keys = torch.randint(0, 256, (units, 32), dtype=torch.uint8, device=dev, generator=g)
@@ -541,6 +608,13 @@ def main():
         r["issue_roofline"] = {"bound": "lds32 (224 conflict-free LDS.32 per block)", "achieved_Tops": blocks_s * 224 / 1e12,
                                "peak_Tops": issue.get("lds32"), "frac": blocks_s * 224 / 1e12 / issue["lds32"] if issue.get("lds32", 0) > 0 else None,
                                "alu_ops_per_block": 456, "alu_frac": blocks_s * 456 / 1e12 / issue["lop3"] if issue.get("lop3", 0) > 0 else None}
+    if "belt_dwp" in results:
+        r = results["belt_dwp"]
+        blocks_s = r["value"] * 1e9 / 16 / world
+        # LSU wavefronts per block: 224 (CTR LDS.32) + 32 LDS.128 x 4 (tag tables)
+        r["issue_roofline"] = {"bound": "lsu wavefronts (224 LDS.32 + 32 LDS.128 x 4 per block)",
+                               "achieved_Tops": blocks_s * 352 / 1e12, "peak_Tops": issue.get("lds32"),
+                               "frac": blocks_s * 352 / 1e12 / issue["lds32"] if issue.get("lds32", 0) > 0 else None}
     if "belt_ecb" in results:
         r = results["belt_ecb"]
         blocks_s = r["value"] * 1e9 / 16 / world

@@ -20,6 +20,7 @@
 typedef uint32_t (*bash_hash_fn)(uint8_t*, size_t, const void*, size_t);
 typedef uint32_t (*belt_ctr_fn)(void*, const void*, size_t, const uint8_t*, size_t, const uint8_t*);
 typedef uint32_t (*belt_ecb_fn)(void*, const void*, size_t, const uint8_t*, size_t);
+typedef uint32_t (*belt_dwp_fn)(void*, uint8_t*, const void*, size_t, const void*, size_t, const uint8_t*, size_t, const uint8_t*);
 typedef uint32_t (*ref_verify_fn)(const uint8_t*, const uint8_t*, const uint8_t*);
 typedef uint32_t (*ref_sign2_fn)(uint8_t*, const uint8_t*, const uint8_t*, const void*, size_t);
 typedef uint32_t (*ref_pubkey_fn)(uint8_t*, const uint8_t*);
@@ -28,7 +29,7 @@ typedef uint32_t (*orc_sign2_fn)(uint8_t*, const uint8_t*, size_t, const uint8_t
 
 static const uint8_t OID[11] = {0x06, 0x09, 0x2A, 0x70, 0x00, 0x02, 0x00, 0x22, 0x65, 0x1F, 0x51};
 
-enum { K_BASH, K_CTR, K_ECB_MK, K_VERIFY, K_SIGN2, K_PUBKEY };
+enum { K_BASH, K_CTR, K_ECB_MK, K_VERIFY, K_SIGN2, K_PUBKEY, K_DWP };
 
 typedef struct
 {
@@ -65,6 +66,17 @@ static void* worker(void* arg)
 			if (j->count && ((belt_ctr_fn)j->fn)(j->dst + j->first * j->unit_bytes,
 					j->src ? j->src + j->first * j->unit_bytes : j->dst + j->first * j->unit_bytes,
 					j->count * j->unit_bytes, j->key, 32, iv))
+				j->failed = 1;
+		}
+		break;
+	case K_DWP:
+		/* one independent beltDWPWrap per thread over its slice, 16 octets of open data */
+		{
+			uint8_t iv[16], mac[8];
+			memcpy(iv, j->iv, 16);
+			iv[0] ^= (uint8_t)j->first, iv[1] ^= (uint8_t)(j->first >> 8);
+			if (j->count && ((belt_dwp_fn)j->fn)(j->dst + j->first * j->unit_bytes, mac,
+					j->dst + j->first * j->unit_bytes, j->count * j->unit_bytes, j->iv, 16, j->key, 32, iv))
 				j->failed = 1;
 		}
 		break;
@@ -153,6 +165,17 @@ double harness_belt_ctr(const char* libpath, int is_port, uint8_t* dst, const ui
 	j.kind = K_CTR, j.is_port = is_port;
 	if (!(j.fn = sym(libpath, is_port ? "orc_beltCTR" : "beltCTR"))) return -3;
 	j.dst = dst, j.src = src, j.unit_bytes = unit_bytes, j.key = key, j.iv = iv;
+	return fan_out(j, units, threads);
+}
+
+double harness_belt_dwp(const char* libpath, int is_port, uint8_t* buf, size_t unit_bytes, size_t units,
+	const uint8_t key[32], const uint8_t iv[16], int threads)
+{
+	job_t j;
+	memset(&j, 0, sizeof j);
+	j.kind = K_DWP, j.is_port = is_port;
+	if (!(j.fn = sym(libpath, is_port ? "orc_beltDWPWrap" : "beltDWPWrap"))) return -3;
+	j.dst = buf, j.unit_bytes = unit_bytes, j.key = key, j.iv = iv;
 	return fan_out(j, units, threads);
 }
 
