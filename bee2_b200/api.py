@@ -20,7 +20,7 @@ __all__ = [
     "bashF", "bashHash", "bashHashBatch", "bashHashBatchV", "bashFBatch", "BashHash",
     "beltH", "beltKeyExpand2", "beltBlockEncr", "beltBlockDecr", "beltECBEncr", "beltECBDecr",
     "beltECBEncrBatch", "BeltECB", "BeltCTR", "beltCTR", "beltCTRKeystream", "beltHash", "beltHashBatch",
-    "beltDWPWrap", "beltDWPUnwrap", "beltDWPMac_dev",
+    "beltDWPWrap", "beltDWPUnwrap", "beltDWPMac_dev", "beltCHEWrap", "beltCHEUnwrap", "beltCHE_dev",
     "bignParamsStd", "bignVerify", "bignVerifyBatch", "bignSign2", "bignSign2Batch",
     "bignPubkeyCalc", "bignPubkeyCalcBatch", "ecMulABatch", "ecAddMulABatch", "OID_BELT_HASH_DER",
     "bashHashBatch_dev", "bashFBatch_dev", "beltCTR_dev", "beltECB_dev", "beltECBEncrBatch_dev",
@@ -108,6 +108,10 @@ def _declare(L: C.CDLL) -> None:
         "beltHashBatch": (u32, [vp, vp, sz, sz, sz]),
         "beltDWPWrap": (u32, [vp, vp, vp, sz, vp, sz, vp, sz, vp]),
         "beltDWPUnwrap": (u32, [vp, vp, sz, vp, sz, vp, vp, sz, vp]),
+        "beltCHEWrap": (u32, [vp, vp, vp, sz, vp, sz, vp, sz, vp]),
+        "beltCHEUnwrap": (u32, [vp, vp, sz, vp, sz, vp, vp, sz, vp]),
+        "b2g_beltCHE_dev": (u32, [vp, vp, sz, vp, vp, u64, vp]),
+        "b2g_beltCHEMac_dev": (u32, [vp, vp, sz, vp, sz, vp, vp, vp, vp]),
         "b2g_beltDWPMac_dev": (u32, [vp, vp, sz, vp, sz, vp, vp, vp, vp]),
         "b2g_beltCTR_dev": (u32, [vp, vp, sz, vp, vp, u64, vp]), "b2g_beltECB_dev": (u32, [vp, vp, sz, vp, ci, vp]),
         "b2g_beltECBEncrBatch_dev": (u32, [vp, vp, sz, vp]), "b2g_beltHashBatch_dev": (u32, [vp, vp, sz, sz, sz, vp]),
@@ -391,18 +395,33 @@ def beltCTRKeystream(count: int, key: bytes, iv: bytes, out: Optional[np.ndarray
     return o if out is not None else o.tobytes()
 
 
-def beltDWPWrap(src1, src2, key: bytes, iv: bytes):
+def beltCHEWrap(src1, src2, key: bytes, iv: bytes):
+    """belt-CHE wrap (belt_che.c:257-285) — returns (ciphertext bytes, mac[8])"""
+    return beltDWPWrap(src1, src2, key, iv, fn="beltCHEWrap")
+
+
+def beltCHEUnwrap(src1, src2, mac: bytes, key: bytes, iv: bytes):
+    return beltDWPUnwrap(src1, src2, mac, key, iv, fn="beltCHEUnwrap")
+
+
+def beltCHE_dev(d_dest: int, d_src: int, count: int, key_words: np.ndarray, s0_words: np.ndarray,
+                first_block: int = 0, stream: int = 0) -> None:
+    _chk("b2g_beltCHE_dev", lib().b2g_beltCHE_dev(d_dest, d_src, count, key_words.ctypes.data, s0_words.ctypes.data,
+                                                  first_block, stream))
+
+
+def beltDWPWrap(src1, src2, key: bytes, iv: bytes, fn: str = "beltDWPWrap"):
     """belt.h:984-1007 — returns (ciphertext bytes, mac[8])"""
     k1, p1, n1 = _buf(src1)
     k2, p2, n2 = _buf(src2)
     kk, kp, kn = _buf(key)
     ki, ivp, _ = _buf(iv)
     out, mac = _out(n1), _out(8)
-    _chk("beltDWPWrap", lib().beltDWPWrap(out.ctypes.data, mac.ctypes.data, p1, n1, p2, n2, kp, kn, ivp))
+    _chk(fn, getattr(lib(), fn)(out.ctypes.data, mac.ctypes.data, p1, n1, p2, n2, kp, kn, ivp))
     return out.tobytes(), mac.tobytes()
 
 
-def beltDWPUnwrap(src1, src2, mac: bytes, key: bytes, iv: bytes):
+def beltDWPUnwrap(src1, src2, mac: bytes, key: bytes, iv: bytes, fn: str = "beltDWPUnwrap"):
     """belt.h:1009-1030 — returns (err_t, plaintext bytes or None)"""
     k1, p1, n1 = _buf(src1)
     k2, p2, n2 = _buf(src2)
@@ -410,7 +429,7 @@ def beltDWPUnwrap(src1, src2, mac: bytes, key: bytes, iv: bytes):
     kk, kp, kn = _buf(key)
     ki, ivp, _ = _buf(iv)
     out = _out(n1)
-    code = lib().beltDWPUnwrap(out.ctypes.data, p1, n1, p2, n2, mp, kp, kn, ivp)
+    code = getattr(lib(), fn)(out.ctypes.data, p1, n1, p2, n2, mp, kp, kn, ivp)
     return code, (out.tobytes() if code == ERR_OK else None)
 
 

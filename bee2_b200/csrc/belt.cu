@@ -8,6 +8,7 @@
 // 128 KiB bank-replicated T-tables are built once per CTA), grid-stride over blocks
 // so that each warp stores 512 contiguous octets (4 full 128-B lines) per STG.128.
 #include "belt_dev.cuh"
+#include "gf128.cuh"
 
 #define BELT_THREADS 1024
 #define BELT_ILP 2
@@ -72,6 +73,65 @@ belt_ctr_kernel(uint4* dst, const uint4* src, u64 nblocks, u32 tail,
 				}
 			}
 		}
+	}
+}
+
+// ---------------------------------------------------------------- CHE keystream
+// belt-CHE encrypts with E_K over the LFSR counter s_j = s_(j-1) x ^ 1 (belt_che.c:75-110). Each
+// warp owns a span of 32*iters consecutive blocks; lane L takes blocks span + 32 i + L, so a
+// warp stores 512 contiguous octets per step and a lane advances its counter by x^32 (a word
+// shift) between steps. The start counter of every lane comes from the closed form in gf128.cuh.
+template <bool XOR_SRC>
+__global__ void __launch_bounds__(BELT_THREADS, 1)
+belt_che_kernel(uint4* dst, const uint4* src, u64 nblocks, u32 tail, const BeltKey key, const uint4 s0,
+	u64 first, u64 iters)
+{
+	extern __shared__ __align__(1024) u8 sm[];
+	BeltBigT::fill(sm);
+	__syncthreads();
+	const BeltBigT S(sm);
+	const u64 warp = ((u64)blockIdx.x * BELT_THREADS + threadIdx.x) >> 5;
+	const u32 lane = threadIdx.x & 31u;
+	const u64 span = warp * 32 * iters;
+	if (span >= nblocks)
+		return;
+	const u64 nfull = tail ? nblocks - 1 : nblocks;
+	gf128 s;
+	{
+		const gf128 s0g = {{s0.x, s0.y, s0.z, s0.w}};
+		s = che_counter(s0g, first + span + lane + 1);   // gamma block j uses s_(j+1), j 0-based
+	}
+#pragma unroll 1
+	for (u64 i = 0; i < iters; ++i)
+	{
+		const u64 j = span + 32 * i + lane;
+		if (span + 32 * i >= nblocks)
+			break;
+		uint4 v = make_uint4(s.w[0], s.w[1], s.w[2], s.w[3]);
+		belt_encr(S, v.x, v.y, v.z, v.w, key.k);
+		if (j < nfull)
+		{
+			if (XOR_SRC)
+			{
+				const uint4 d = ldg_stream(src + j);
+				v.x ^= d.x, v.y ^= d.y, v.z ^= d.z, v.w ^= d.w;
+			}
+			stg_stream(dst + j, v);
+		}
+		else if (j < nblocks)
+		{
+			const u32 w[4] = {v.x, v.y, v.z, v.w};
+			u8* d8 = reinterpret_cast<u8*>(dst + j);
+			const u8* s8 = reinterpret_cast<const u8*>(src + j);
+			for (u32 k = 0; k < tail; ++k)
+			{
+				u8 g = (u8)(w[k >> 2] >> (8 * (k & 3)));
+				if (XOR_SRC)
+					g ^= s8[k];
+				d8[k] = g;
+			}
+		}
+		s = che_step32(s);
 	}
 }
 
@@ -198,6 +258,7 @@ static u32 belt_grid(u64 nblocks)
 static u32 belt_optin_all(void)
 {
 	const void* ks[] = {(const void*)belt_ctr_kernel<true>, (const void*)belt_ctr_kernel<false>,
+		(const void*)belt_che_kernel<true>, (const void*)belt_che_kernel<false>,
 		(const void*)belt_ecb_kernel<false, false>, (const void*)belt_ecb_kernel<true, false>,
 		(const void*)belt_ecb_kernel<false, true>};
 	for (size_t i = 0; i < sizeof ks / sizeof ks[0]; ++i)
@@ -237,6 +298,36 @@ extern "C" u32 b2g_beltCTR_dev(void* d_dest, const void* d_src, size_t count, co
 	}
 	b2g_note_launch();
 	return b2g_check_launch("belt_ctr_kernel");
+}
+
+// belt-CHE data pass: dest = src ^ gamma, gamma block j = E_K(s_(first_block + j + 1)), s_0 = E_K(iv)
+extern "C" u32 b2g_beltCHE_dev(void* d_dest, const void* d_src, size_t count, const u32 key[8],
+	const u32 s0[4], u64 first_block, void* stream)
+{
+	u32 e = b2g_ensure_device();
+	if (e) return e;
+	if (count == 0) return B2G_OK;
+	if (((uintptr_t)d_dest & 15) || ((uintptr_t)d_src & 15)) return B2G_BAD_INPUT;
+	const u64 nblocks = ((u64)count + 15) / 16;
+	const u32 tail = (u32)(count & 15);
+	BeltKey k;
+	for (int i = 0; i < 8; ++i) k.k[i] = key[i];
+	const uint4 s = make_uint4(s0[0], s0[1], s0[2], s0[3]);
+	// one span of 32*iters blocks per warp; all warps of the persistent grid busy, spans >= 64 steps
+	const u64 warps_max = (u64)b2g_sm_count() * (BELT_THREADS / 32);
+	u64 iters = (nblocks + 32 * warps_max - 1) / (32 * warps_max);
+	if (iters < 64) iters = 64;
+	const u64 nwarps = (nblocks + 32 * iters - 1) / (32 * iters);
+	const u32 grid = (u32)((nwarps + BELT_THREADS / 32 - 1) / (BELT_THREADS / 32));
+	cudaStream_t st = (cudaStream_t)stream;
+	if (d_src)
+		belt_che_kernel<true><<<grid, BELT_THREADS, BELT_BIGT_BYTES, st>>>((uint4*)d_dest, (const uint4*)d_src,
+			nblocks, tail, k, s, first_block, iters);
+	else
+		belt_che_kernel<false><<<grid, BELT_THREADS, BELT_BIGT_BYTES, st>>>((uint4*)d_dest, (const uint4*)0,
+			nblocks, tail, k, s, first_block, iters);
+	b2g_note_launch();
+	return b2g_check_launch("belt_che_kernel");
 }
 
 extern "C" u32 b2g_beltECB_dev(void* d_dest, const void* d_src, size_t nblocks, const u32 key[8],

@@ -28,6 +28,7 @@ struct DwpArgs
 	u64 K;             // blocks per thread
 	BeltKey key;
 	uint4 s;           // E_K(iv)
+	u32 r_is_s;        // belt-CHE: r = s = E_K(iv) (belt_che.c:54-57); belt-DWP: r = E_K(s)
 	u32* acc;          // 4 words, zeroed: XOR of the weighted chunk values
 };
 
@@ -79,7 +80,8 @@ __global__ void __launch_bounds__(DWP_THREADS) belt_dwp_mac_kernel(const DwpArgs
 		// r <- E_K(s) (belt_dwp.c:52-55)
 		const BeltSmallT S(sbox);
 		u32 x0 = a.s.x, x1 = a.s.y, x2 = a.s.z, x3 = a.s.w;
-		belt_encr(S, x0, x1, x2, x3, a.key.k);
+		if (!a.r_is_s)
+			belt_encr(S, x0, x1, x2, x3, a.key.k);
 		rsh[0] = x0, rsh[1] = x1, rsh[2] = x2, rsh[3] = x3;
 	}
 	__syncthreads();
@@ -151,8 +153,24 @@ extern "C" u32 b2g_beltdwp_upload_tables(const u8 H[256])
 
 // d_mac (8 octets) <- DWP tag of (open data d_open[n2], critical data d_crit[n1]) under the
 // expanded key and ctr0 = E_K(iv); d_scratch: 16 octets of device scratch
+static u32 dwp_mac_launch(void* d_mac, const void* d_crit, size_t n1, const void* d_open, size_t n2,
+	const u32 key[8], const u32 ctr0[4], void* d_scratch, void* stream, u32 r_is_s);
+
 extern "C" u32 b2g_beltDWPMac_dev(void* d_mac, const void* d_crit, size_t n1, const void* d_open, size_t n2,
 	const u32 key[8], const u32 ctr0[4], void* d_scratch, void* stream)
+{
+	return dwp_mac_launch(d_mac, d_crit, n1, d_open, n2, key, ctr0, d_scratch, stream, 0);
+}
+
+// belt-CHE tag: same polynomial MAC with r = s0 = E_K(iv) (belt_che.c:218-239)
+extern "C" u32 b2g_beltCHEMac_dev(void* d_mac, const void* d_crit, size_t n1, const void* d_open, size_t n2,
+	const u32 key[8], const u32 s0[4], void* d_scratch, void* stream)
+{
+	return dwp_mac_launch(d_mac, d_crit, n1, d_open, n2, key, s0, d_scratch, stream, 1);
+}
+
+static u32 dwp_mac_launch(void* d_mac, const void* d_crit, size_t n1, const void* d_open, size_t n2,
+	const u32 key[8], const u32 ctr0[4], void* d_scratch, void* stream, u32 r_is_s)
 {
 	u32 e = b2g_ensure_device();
 	if (e) return e;
@@ -164,6 +182,7 @@ extern "C" u32 b2g_beltDWPMac_dev(void* d_mac, const void* d_crit, size_t n1, co
 	for (int i = 0; i < 8; ++i) a.key.k[i] = key[i];
 	a.s = make_uint4(ctr0[0], ctr0[1], ctr0[2], ctr0[3]);
 	a.acc = (u32*)d_scratch;
+	a.r_is_s = r_is_s;
 	// one chunk per thread; at most 2 CTAs per SM worth of threads, at least DWP_MIN_CHUNK blocks each
 	const u64 tmax = (u64)b2g_sm_count() * 2 * DWP_THREADS;
 	u64 K = (a.N + tmax - 1) / tmax;

@@ -28,7 +28,7 @@ __device__ __forceinline__ gf128 gf_mulx(const gf128 a)
 }
 
 // generic product, bit-serial (used once per thread, for the chunk weight)
-__device__ __noinline__ gf128 gf_mul(const gf128 a, const gf128 b)
+static __device__ __noinline__ gf128 gf_mul(const gf128 a, const gf128 b)
 {
 	gf128 r = {{0, 0, 0, 0}}, v = b;
 #pragma unroll 1
@@ -131,4 +131,50 @@ __device__ __forceinline__ gf128 gf_pow_r(const u8* tab, u64 e)
 		if (e >> i & 1) acc = gf_mul_tab(tab, acc);
 	}
 	return acc;
+}
+
+// x^e mod f: squarings (bit spreads) and multiplications by x only
+__device__ __forceinline__ gf128 gf_pow_x(u64 e)
+{
+	gf128 acc = {{1, 0, 0, 0}};
+	if (e == 0) return acc;
+	const int top = 63 - __clzll((long long)e);
+#pragma unroll 1
+	for (int i = top; i >= 0; --i)
+	{
+		acc = gf_sqr(acc);
+		if (e >> i & 1) acc = gf_mulx(acc);
+	}
+	return acc;
+}
+
+// a * x^32 mod f: a word shift; the word shifted out (< 2^32) folds back as top * (x^7 + x^2 + x + 1)
+__device__ __forceinline__ gf128 gf_mulx32(const gf128 a)
+{
+	const u32 t = a.w[3];
+	gf128 r;
+	r.w[0] = t ^ t << 1 ^ t << 2 ^ t << 7;
+	r.w[1] = a.w[0] ^ t >> 31 ^ t >> 30 ^ t >> 25;
+	r.w[2] = a.w[1];
+	r.w[3] = a.w[2];
+	return r;
+}
+
+// belt-CHE counter: s_j = s_(j-1) * x ^ 1 (belt_che.c:89, belt_lcl.c:99-108). Closed form used to
+// start any thread anywhere: s_j = s_0 x^j ^ (x^j ^ 1) (x + 1)^(-1), and (x + 1)^(-1) =
+// (f(x) + 1) / (x + 1) = x^127 + ... + x^7 + x because f(1) = 1.
+__device__ __forceinline__ gf128 che_counter(const gf128 s0, u64 j)
+{
+	const gf128 inv_xp1 = {{0xFFFFFF82u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}};
+	gf128 xj = gf_pow_x(j);
+	gf128 a = gf_mul(s0, xj);
+	xj.w[0] ^= 1u;
+	return gf_xor(a, gf_mul(xj, inv_xp1));
+}
+// s -> s_(+32): 32 steps at once, s x^32 ^ (x^31 + ... + 1)
+__device__ __forceinline__ gf128 che_step32(const gf128 s)
+{
+	gf128 r = gf_mulx32(s);
+	r.w[0] ^= 0xFFFFFFFFu;
+	return r;
 }

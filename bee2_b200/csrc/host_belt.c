@@ -405,8 +405,13 @@ err_t beltHash(octet hash[32], const void* src, size_t count)
 /* One-shot AEAD on whole buffers: the data stay on the device between the CTR pass (belt.cu) and
    the tag pass (belt_dwp.cu). */
 static err_t dwp_run(void* dest, octet mac_out[8], const void* src1, size_t count1, const void* src2,
-	size_t count2, const octet key[], size_t len, const octet iv[16], const octet* expect_mac)
+	size_t count2, const octet key[], size_t len, const octet iv[16], const octet* expect_mac, int che)
 {
+	/* che: belt-CHE (belt_che.c:257-330) — LFSR counter and r = E_K(iv); else belt-DWP */
+	err_t (*crypt)(void*, const void*, size_t, const u32*, const u32*, u64, void*) =
+		che ? b2g_beltCHE_dev : b2g_beltCTR_dev;
+	err_t (*tag)(void*, const void*, size_t, const void*, size_t, const u32*, const u32*, void*, void*) =
+		che ? b2g_beltCHEMac_dev : b2g_beltDWPMac_dev;
 	err_t code;
 	belt_ctr_st st;
 	b2g_slot* sl;
@@ -430,9 +435,9 @@ static err_t dwp_run(void* dest, octet mac_out[8], const void* src1, size_t coun
 	if (!expect_mac)
 	{
 		/* wrap: encrypt, then authenticate the ciphertext (belt_dwp.c:277-282) */
-		if (count1 && (code = b2g_beltCTR_dev(d_crit, d_crit, count1, st.key, st.ctr, 0, sl->stream)))
+		if (count1 && (code = crypt(d_crit, d_crit, count1, st.key, st.ctr, 0, sl->stream)))
 			goto done;
-		if ((code = b2g_beltDWPMac_dev(d_small, d_crit, count1, d_open, count2, st.key, st.ctr,
+		if ((code = tag(d_small, d_crit, count1, d_open, count2, st.key, st.ctr,
 				(octet*)d_small + 16, sl->stream)))
 			goto done;
 		CU(cudaMemcpyAsync(mac, d_small, 8, cudaMemcpyDeviceToHost, sl->stream), "D2H(dwp mac)");
@@ -444,7 +449,7 @@ static err_t dwp_run(void* dest, octet mac_out[8], const void* src1, size_t coun
 	else
 	{
 		/* unwrap: check the tag first; a wrong tag leaves dest untouched (belt_dwp.c:316-324) */
-		if ((code = b2g_beltDWPMac_dev(d_small, d_crit, count1, d_open, count2, st.key, st.ctr,
+		if ((code = tag(d_small, d_crit, count1, d_open, count2, st.key, st.ctr,
 				(octet*)d_small + 16, sl->stream)))
 			goto done;
 		CU(cudaMemcpyAsync(mac, d_small, 8, cudaMemcpyDeviceToHost, sl->stream), "D2H(dwp mac)");
@@ -456,7 +461,7 @@ static err_t dwp_run(void* dest, octet mac_out[8], const void* src1, size_t coun
 		}
 		if (count1)
 		{
-			if ((code = b2g_beltCTR_dev(d_crit, d_crit, count1, st.key, st.ctr, 0, sl->stream)))
+			if ((code = crypt(d_crit, d_crit, count1, st.key, st.ctr, 0, sl->stream)))
 				goto done;
 			CU(cudaMemcpyAsync(dest, d_crit, count1, cudaMemcpyDeviceToHost, sl->stream), "D2H(dwp data)");
 			CU(cudaStreamSynchronize(sl->stream), "sync(dwp)");
@@ -474,7 +479,7 @@ err_t beltDWPWrap(void* dest, octet mac[8], const void* src1, size_t count1, con
 {
 	if (!mac)
 		return ERR_BAD_INPUT;
-	return dwp_run(dest, mac, src1, count1, src2, count2, key, len, iv, 0);
+	return dwp_run(dest, mac, src1, count1, src2, count2, key, len, iv, 0, 0);
 }
 
 err_t beltDWPUnwrap(void* dest, const void* src1, size_t count1, const void* src2, size_t count2,
@@ -483,5 +488,22 @@ err_t beltDWPUnwrap(void* dest, const void* src1, size_t count1, const void* src
 	octet unused[8];
 	if (!mac)
 		return ERR_BAD_INPUT;
-	return dwp_run(dest, unused, src1, count1, src2, count2, key, len, iv, mac);
+	return dwp_run(dest, unused, src1, count1, src2, count2, key, len, iv, mac, 0);
+}
+
+err_t beltCHEWrap(void* dest, octet mac[8], const void* src1, size_t count1, const void* src2,
+	size_t count2, const octet key[], size_t len, const octet iv[16])
+{
+	if (!mac)
+		return ERR_BAD_INPUT;
+	return dwp_run(dest, mac, src1, count1, src2, count2, key, len, iv, 0, 1);
+}
+
+err_t beltCHEUnwrap(void* dest, const void* src1, size_t count1, const void* src2, size_t count2,
+	const octet mac[8], const octet key[], size_t len, const octet iv[16])
+{
+	octet unused[8];
+	if (!mac)
+		return ERR_BAD_INPUT;
+	return dwp_run(dest, unused, src1, count1, src2, count2, key, len, iv, mac, 1);
 }

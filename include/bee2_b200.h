@@ -146,6 +146,12 @@ err_t beltDWPWrap(void* dest, octet mac[8], const void* src1, size_t count1, con
 	size_t count2, const octet key[], size_t len, const octet iv[16]);
 err_t beltDWPUnwrap(void* dest, const void* src1, size_t count1, const void* src2, size_t count2,
 	const octet mac[8], const octet key[], size_t len, const octet iv[16]);
+/* drop-in: belt.h (belt_che.c:257-330) — belt-CHE: same interface as DWP; the gamma runs over
+   the LFSR counter s <- s*x ^ 1 and the tag uses r = E_K(iv) */
+err_t beltCHEWrap(void* dest, octet mac[8], const void* src1, size_t count1, const void* src2,
+	size_t count2, const octet key[], size_t len, const octet iv[16]);
+err_t beltCHEUnwrap(void* dest, const void* src1, size_t count1, const void* src2, size_t count2,
+	const octet mac[8], const octet key[], size_t len, const octet iv[16]);
 /* batch: pure keystream (beltCTR of zeros) */
 err_t beltCTRKeystream(void* dest, size_t count, const octet key[], size_t len,
 	const octet iv[16]);
@@ -162,6 +168,11 @@ err_t b2g_beltCTR_dev(void* d_dest, const void* d_src, size_t count, const u32 k
    d_scratch = 16 octets of device scratch (4-aligned) */
 err_t b2g_beltDWPMac_dev(void* d_mac, const void* d_crit, size_t n1, const void* d_open, size_t n2,
 	const u32 key[8], const u32 ctr0[4], void* d_scratch, void* stream);
+/* device: belt-CHE data pass (gamma block j = E_K(s_(first_block+j+1)), s0 = E_K(iv)) and tag */
+err_t b2g_beltCHE_dev(void* d_dest, const void* d_src, size_t count, const u32 key[8],
+	const u32 s0[4], u64 first_block, void* stream);
+err_t b2g_beltCHEMac_dev(void* d_mac, const void* d_crit, size_t n1, const void* d_open, size_t n2,
+	const u32 key[8], const u32 s0[4], void* d_scratch, void* stream);
 err_t b2g_beltECB_dev(void* d_dest, const void* d_src, size_t nblocks, const u32 key[8],
 	int decrypt, void* stream);
 err_t b2g_beltECBEncrBatch_dev(void* d_blocks, const void* d_keys32, size_t count, void* stream);

@@ -716,3 +716,76 @@ u32 orc_beltDWPUnwrap(void* dest, const void* src1, size_t n1, const void* src2,
 	orc_beltCTRStepE(dest, n1, &st);
 	return ORC_OK;
 }
+
+/* ======================================================================= belt-CHE (belt_che.c:48-330) */
+
+/* keystream of CHE: s_0 = E_K(iv); s_j = s_{j-1} * x ^ 1 (belt_lcl.c:99-108, belt_che.c:89);
+   block j (j >= 1) of the gamma is E_K(s_j) */
+static void che_crypt(u8* buf, size_t n, const u32 key[8], const u32 s0[4])
+{
+	u64 s[2];
+	memcpy(s, s0, 16);
+	while (n)
+	{
+		u32 w[4];
+		u8 g[16];
+		const size_t take = n < 16 ? n : 16;
+		size_t i;
+		const u64 top = s[1] >> 63;
+		s[1] = s[1] << 1 | s[0] >> 63;
+		s[0] = (s[0] << 1 ^ (top ? 0x87 : 0)) ^ 1;
+		memcpy(w, s, 16);
+		orc_beltBlockEncr2(w, key);
+		memcpy(g, w, 16);
+		for (i = 0; i < take; ++i) buf[i] ^= g[i];
+		buf += take, n -= take;
+	}
+}
+
+static void che_mac(u8 mac[8], const u32 key[8], const u32 r32[4], const u8* crit, size_t n1, const u8* open, size_t n2)
+{
+	u64 r[2], t[2];
+	u32 w[4];
+	memcpy(r, r32, 16);                   /* r = E_K(iv) (belt_che.c:54-57) */
+	memcpy(t, orc_beltH(), 16);
+	dwp_absorb(t, r, open, n2);
+	dwp_absorb(t, r, crit, n1);
+	t[0] ^= (u64)n2 << 3, t[1] ^= (u64)n1 << 3;
+	gf128_mul(t, t, r);
+	memcpy(w, t, 16);
+	orc_beltBlockEncr2(w, key);
+	memcpy(mac, w, 8);
+}
+
+u32 orc_beltCHEWrap(void* dest, u8 mac[8], const void* src1, size_t n1, const void* src2, size_t n2,
+	const u8* key, size_t len, const u8 iv[16])
+{
+	u32 k[8], r[4];
+	if (len != 16 && len != 24 && len != 32)
+		return ORC_BAD_INPUT;
+	orc_beltKeyExpand2(k, key, len);
+	memcpy(r, iv, 16);
+	orc_beltBlockEncr2(r, k);
+	memmove(dest, src1, n1);
+	che_crypt((u8*)dest, n1, k, r);
+	che_mac(mac, k, r, (const u8*)dest, n1, (const u8*)src2, n2);
+	return ORC_OK;
+}
+
+u32 orc_beltCHEUnwrap(void* dest, const void* src1, size_t n1, const void* src2, size_t n2,
+	const u8 mac[8], const u8* key, size_t len, const u8 iv[16])
+{
+	u32 k[8], r[4];
+	u8 m[8];
+	if (len != 16 && len != 24 && len != 32)
+		return ORC_BAD_INPUT;
+	orc_beltKeyExpand2(k, key, len);
+	memcpy(r, iv, 16);
+	orc_beltBlockEncr2(r, k);
+	che_mac(m, k, r, (const u8*)src1, n1, (const u8*)src2, n2);
+	if (memcmp(m, mac, 8) != 0)
+		return 511u;
+	memmove(dest, src1, n1);
+	che_crypt((u8*)dest, n1, k, r);
+	return ORC_OK;
+}

@@ -20,7 +20,7 @@ def port():
     if _port is None:
         L = C.CDLL(os.path.join(REF_DIR, "libbee2oracle.so"))
         L.orc_beltH.restype = C.c_void_p
-        for n in ("orc_beltDWPWrap", "orc_beltDWPUnwrap", "orc_bashHash", "orc_beltCTR", "orc_beltECBEncr", "orc_beltECBDecr", "orc_bignVerify128",
+        for n in ("orc_beltCHEWrap", "orc_beltCHEUnwrap", "orc_beltDWPWrap", "orc_beltDWPUnwrap", "orc_bashHash", "orc_beltCTR", "orc_beltECBEncr", "orc_beltECBDecr", "orc_bignVerify128",
                   "orc_bignSign2_128", "orc_bignPubkeyCalc128"):
             getattr(L, n).restype = C.c_uint32
         L.orc_ecMulA128.restype = C.c_int
@@ -37,7 +37,7 @@ def ref():
             return None
         L = C.CDLL(p)
         L.beltH.restype = C.c_void_p
-        for n in ("beltDWPWrap", "beltDWPUnwrap", "bashHash", "beltCTR", "beltECBEncr", "beltECBDecr", "beltHash", "bignVerify", "bignSign2",
+        for n in ("beltCHEWrap", "beltCHEUnwrap", "beltDWPWrap", "beltDWPUnwrap", "bashHash", "beltCTR", "beltECBEncr", "beltECBDecr", "beltHash", "bignVerify", "bignSign2",
                   "bignParamsStd", "bignPubkeyCalc"):
             getattr(L, n).restype = C.c_uint32
         _ref = L
@@ -118,16 +118,24 @@ def beltECBEncrMultiKey(blocks: np.ndarray, keys: np.ndarray) -> np.ndarray:
     return b
 
 
-def beltDWPWrap(src1: bytes, src2: bytes, key: bytes, iv: bytes):
+def beltCHEWrap(src1: bytes, src2: bytes, key: bytes, iv: bytes):
+    return beltDWPWrap(src1, src2, key, iv, fn="orc_beltCHEWrap")
+
+
+def beltCHEUnwrap(src1: bytes, src2: bytes, mac: bytes, key: bytes, iv: bytes):
+    return beltDWPUnwrap(src1, src2, mac, key, iv, fn="orc_beltCHEUnwrap")
+
+
+def beltDWPWrap(src1: bytes, src2: bytes, key: bytes, iv: bytes, fn="orc_beltDWPWrap"):
     d, m = C.create_string_buffer(max(len(src1), 1)), C.create_string_buffer(8)
-    code = port().orc_beltDWPWrap(d, m, bytes(src1), sz(len(src1)), bytes(src2), sz(len(src2)), bytes(key), sz(len(key)), bytes(iv))
+    code = getattr(port(), fn)(d, m, bytes(src1), sz(len(src1)), bytes(src2), sz(len(src2)), bytes(key), sz(len(key)), bytes(iv))
     assert code == 0
     return d.raw[: len(src1)], m.raw
 
 
-def beltDWPUnwrap(src1: bytes, src2: bytes, mac: bytes, key: bytes, iv: bytes):
+def beltDWPUnwrap(src1: bytes, src2: bytes, mac: bytes, key: bytes, iv: bytes, fn="orc_beltDWPUnwrap"):
     d = C.create_string_buffer(max(len(src1), 1))
-    code = port().orc_beltDWPUnwrap(d, bytes(src1), sz(len(src1)), bytes(src2), sz(len(src2)), bytes(mac), bytes(key),
+    code = getattr(port(), fn)(d, bytes(src1), sz(len(src1)), bytes(src2), sz(len(src2)), bytes(mac), bytes(key),
                                     sz(len(key)), bytes(iv))
     return code, (d.raw[: len(src1)] if code == 0 else None)
 

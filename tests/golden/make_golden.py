@@ -87,6 +87,12 @@ KAT = {
         {"id": "A.20-1", "op": "unwrap", "in": "H[64:80]", "open": "H[80:112]", "key": "H[160:192]", "iv": "H[208:224]",
          "out": "DF181ED008A20F43DCBBB93650DAD34B", "mac": "6A2C2C94C4150DC0"},
     ],
+    "beltCHE": [  # belt_test.c:498-522 (A.19-2 wrap), :544-564 (A.20-2 unwrap)
+        {"id": "A.19-2", "op": "wrap", "in": "H[0:15]", "open": "H[16:48]", "key": "H[128:160]", "iv": "H[192:208]",
+         "out": "BF3DAEAF5D18D2BCC30EA62D2E70A4", "mac": "548622B844123FF7"},
+        {"id": "A.20-2", "op": "unwrap", "in": "H[64:84]", "open": "H[80:112]", "key": "H[160:192]", "iv": "H[208:224]",
+         "out": "2BABF43EB37B5398A9068F31A3C758B762F44AA9", "mac": "7D9D4F59D40D197D"},
+    ],
     "beltZerosum": {  # belt_test.c:69-110: XOR over i of X_i ^ Belt_0(X_i) = 0, X_i = (x_i,0,0,0)
         "x": [15014, 124106, 166335, 206478, 313245, 366839, 455597, 502723, 535141, 625112, 659461, 752253, 801048,
               897899, 943850, 1041695, 1101266, 1170856, 1217537, 1248520, 1366084, 1421171, 1448429, 1514215, 1573855,
@@ -152,6 +158,9 @@ def main():
         assert o.ref().beltDWPWrap(d, m, a, C.c_size_t(n1), b_, C.c_size_t(n2), k, C.c_size_t(klen), iv) == 0
         out["beltDWP"].append({"key": k.hex(), "iv": iv.hex(), "in": a.hex(), "open": b_.hex(),
                                "out": d.raw[:n1].hex(), "mac": m.raw.hex()})
+        assert o.ref().beltCHEWrap(d, m, a, C.c_size_t(n1), b_, C.c_size_t(n2), k, C.c_size_t(klen), iv) == 0
+        out.setdefault("beltCHE", []).append({"key": k.hex(), "iv": iv.hex(), "in": a.hex(), "open": b_.hex(),
+                                              "out": d.raw[:n1].hex(), "mac": m.raw.hex()})
     for n in [0, 1, 31, 32, 33, 64, 75, 1000]:
         m = rb(n)
         out["beltHash"].append({"in": m.hex(), "out": o.ref_beltHash(m).hex()})

@@ -73,38 +73,61 @@ def test_ctr_A15_A16_split_calls():
     assert e.value.code == b.ERR_BAD_INPUT
 
 
-def test_dwp_A19_A20_and_reference_fixtures():
-    for t in KAT["beltDWP"]:
+@pytest.mark.parametrize("mode", ["DWP", "CHE"])
+def test_dwp_che_A19_A20_and_reference_fixtures(mode):
+    wrap, unwrap = getattr(b, f"belt{mode}Wrap"), getattr(b, f"belt{mode}Unwrap")
+    for t in KAT[f"belt{mode}"]:
         src, op, key, iv = R(t["in"]), R(t["open"]), R(t["key"]), R(t["iv"])
         if t["op"] == "wrap":
-            out, mac = b.beltDWPWrap(src, op, key, iv)
+            out, mac = wrap(src, op, key, iv)
             assert out.hex().upper() == t["out"] and mac.hex().upper() == t["mac"]
         else:
-            code, out = b.beltDWPUnwrap(src, op, bytes.fromhex(t["mac"]), key, iv)
+            code, out = unwrap(src, op, bytes.fromhex(t["mac"]), key, iv)
             assert code == 0 and out.hex().upper() == t["out"]
             bad = bytearray(bytes.fromhex(t["mac"]))
             bad[3] ^= 1
-            assert b.beltDWPUnwrap(src, op, bad, key, iv) == (b.ERR_BAD_MAC, None)     # belt_dwp.c:318-322
-    for t in REF["beltDWP"]:
+            assert unwrap(src, op, bad, key, iv) == (b.ERR_BAD_MAC, None)     # belt_dwp.c:318-322
+    for t in REF[f"belt{mode}"]:
         a = [bytes.fromhex(t[k]) for k in ("in", "open", "key", "iv")]
-        out, mac = b.beltDWPWrap(*a)
+        out, mac = wrap(*a)
         assert out.hex() == t["out"] and mac.hex() == t["mac"]
-        assert b.beltDWPUnwrap(out, a[1], mac, a[2], a[3]) == (0, a[0])
+        assert unwrap(out, a[1], mac, a[2], a[3]) == (0, a[0])
 
 
-def test_dwp_random_sizes_vs_oracle():
+@pytest.mark.parametrize("mode", ["DWP", "CHE"])
+def test_dwp_che_random_sizes_vs_oracle(mode):
     """Sizes that exercise one thread, many threads, many CTAs and ragged tails of both data classes."""
     rng = np.random.default_rng(31)
+    wrap, unwrap = getattr(b, f"belt{mode}Wrap"), getattr(b, f"belt{mode}Unwrap")
+    owrap = getattr(o, f"belt{mode}Wrap")
     for n1, n2 in [(0, 0), (5, 0), (0, 5), (511, 513), (16 * 40, 16 * 3), (100_001, 33), (7, 200_003), (3_000_017, 1_000_003)]:
         key = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
         iv = rng.integers(0, 256, 16, dtype=np.uint8).tobytes()
         a = rng.integers(0, 256, n1, dtype=np.uint8).tobytes()
         op = rng.integers(0, 256, n2, dtype=np.uint8).tobytes()
-        want = o.beltDWPWrap(a, op, key, iv)
-        assert b.beltDWPWrap(a, op, key, iv) == want, (n1, n2)
-        assert b.beltDWPUnwrap(want[0], op, want[1], key, iv) == (0, a)
+        want = owrap(a, op, key, iv)
+        assert wrap(a, op, key, iv) == want, (n1, n2)
+        assert unwrap(want[0], op, want[1], key, iv) == (0, a)
         if n2:
-            assert b.beltDWPUnwrap(want[0], op[:-1] + bytes([op[-1] ^ 1]), want[1], key, iv)[0] == b.ERR_BAD_MAC
+            assert unwrap(want[0], op[:-1] + bytes([op[-1] ^ 1]), want[1], key, iv)[0] == b.ERR_BAD_MAC
+
+
+def test_che_sharded_by_block_offset():
+    """belt-CHE gamma from any block offset equals the slice of the whole stream (multi-GPU sharding)."""
+    torch = pytest.importorskip("torch")
+    key = b.beltKeyExpand2(H[128:160])
+    s0 = np.frombuffer(b.beltBlockEncr(H[192:208], H[128:160]), dtype=np.uint32).copy()
+    n = 1 << 24
+    s = torch.cuda.current_stream().cuda_stream
+    whole = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    b.beltCHE_dev(whole.data_ptr(), 0, n, key, s0, 0, s)
+    torch.cuda.synchronize()
+    assert whole[: 1 << 16].cpu().numpy().tobytes() == o.beltCHEWrap(bytes(1 << 16), b"", H[128:160], H[192:208])[0]
+    for off_blocks, m in ((1, 4096), (12345, 1 << 20), ((n // 16) - 100, 1600)):
+        part = torch.zeros(m, dtype=torch.uint8, device="cuda")
+        b.beltCHE_dev(part.data_ptr(), 0, m, key, s0, off_blocks, s)
+        torch.cuda.synchronize()
+        assert torch.equal(part, whole[16 * off_blocks:16 * off_blocks + m])
 
 
 def test_hash_A23():

@@ -56,18 +56,20 @@ def test_belt_ctr_A15_A16():
         assert o.beltCTR(R(t["in"]), R(t["key"]), R(t["iv"])).hex().upper() == t["out"], t["id"]
 
 
-def test_belt_dwp_A19_A20():
-    for t in KAT["beltDWP"]:
+@pytest.mark.parametrize("mode", ["DWP", "CHE"])
+def test_belt_dwp_che_A19_A20(mode):
+    wrap, unwrap = getattr(o, f"belt{mode}Wrap"), getattr(o, f"belt{mode}Unwrap")
+    for t in KAT[f"belt{mode}"]:
         src, op, key, iv = R(t["in"]), R(t["open"]), R(t["key"]), R(t["iv"])
         if t["op"] == "wrap":
-            out, mac = o.beltDWPWrap(src, op, key, iv)
+            out, mac = wrap(src, op, key, iv)
             assert out.hex().upper() == t["out"] and mac.hex().upper() == t["mac"]
         else:
-            code, out = o.beltDWPUnwrap(src, op, bytes.fromhex(t["mac"]), key, iv)
+            code, out = unwrap(src, op, bytes.fromhex(t["mac"]), key, iv)
             assert code == 0 and out.hex().upper() == t["out"]
             bad = bytearray(bytes.fromhex(t["mac"]))
             bad[3] ^= 1
-            assert o.beltDWPUnwrap(src, op, bad, key, iv) == (511, None)
+            assert unwrap(src, op, bad, key, iv) == (511, None)
 
 
 def test_belt_hash_A23():
@@ -111,11 +113,12 @@ def test_reference_fixtures():
         assert o.beltECBDecr(bytes.fromhex(t["out"]), bytes.fromhex(t["key"])).hex() == t["in"]
     for t in REF["beltHash"]:
         assert o.beltHash(bytes.fromhex(t["in"])).hex() == t["out"]
-    for t in REF["beltDWP"]:
-        a = [bytes.fromhex(t[k]) for k in ("in", "open", "key", "iv")]
-        out, mac = o.beltDWPWrap(*a)
-        assert out.hex() == t["out"] and mac.hex() == t["mac"]
-        assert o.beltDWPUnwrap(out, a[1], mac, a[2], a[3]) == (0, a[0])
+    for mode in ("DWP", "CHE"):
+        for t in REF[f"belt{mode}"]:
+            a = [bytes.fromhex(t[k]) for k in ("in", "open", "key", "iv")]
+            out, mac = getattr(o, f"belt{mode}Wrap")(*a)
+            assert out.hex() == t["out"] and mac.hex() == t["mac"]
+            assert getattr(o, f"belt{mode}Unwrap")(out, a[1], mac, a[2], a[3]) == (0, a[0])
     for t in REF["bign"]:
         priv, pub, h = (bytes.fromhex(t[k]) for k in ("privkey", "pubkey", "hash"))
         tt = bytes.fromhex(t["t"]) if t["t"] else None
