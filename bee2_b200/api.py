@@ -92,6 +92,7 @@ def _declare(L: C.CDLL) -> None:
         "bashHashStart": (None, [vp, sz]), "bashHashStepH": (None, [vp, sz, vp]),
         "bashHashStepG": (None, [vp, sz, vp]), "bashHashStepV": (ci, [vp, sz, vp]),
         "bashHash": (u32, [vp, sz, vp, sz]), "bashHashBatch": (u32, [vp, sz, vp, sz, sz, sz]),
+        "bashPrg_keep": (sz, []),
         "bashFBatch": (u32, [vp, sz]), "bashHashBatchV": (u32, [vp, sz, vp, sz, vp, vp, sz]),
         "b2g_bashHashBatchV_dev": (u32, [vp, sz, vp, vp, vp, sz, vp]),
         "b2g_bashHashBatch_dev": (u32, [vp, sz, vp, sz, sz, sz, vp]), "b2g_bashFBatch_dev": (u32, [vp, sz, vp]),
@@ -578,3 +579,51 @@ def bignPubkeyCalcBatch_dev(d_status: int, d_pubkeys: int, d_privkeys: int, coun
 
 def ecMulABatch_dev(d_b: int, d_ok: int, d_a: int, d_d: int, d_len: int, count: int, stream: int = 0) -> None:
     _chk("b2g_ecMulABatch_dev", lib().b2g_ecMulABatch_dev(d_b, d_ok, d_a, d_d, d_len, count, stream))
+
+
+# ------------------------------------------------------------------ bash-prg (bash.h, bash_prg.c)
+class BashPrg:
+    """bashPrgStart/Restart/Absorb/Squeeze/Encr/Decr/Ratchet over a caller-owned state blob."""
+    _prefix = "bashPrg"
+
+    def __init__(self, l: int, d: int, ann: bytes = b"", key: bytes = b"", _lib=None, _keep=None):
+        self.L = _lib or lib()
+        self.state = np.zeros(_keep or self.L.bashPrg_keep(), dtype=np.uint8)
+        self._call("Start", self.state.ctypes.data, C.c_size_t(l), C.c_size_t(d), bytes(ann), C.c_size_t(len(ann)),
+                   bytes(key), C.c_size_t(len(key)))
+
+    def _call(self, name, *args):
+        return getattr(self.L, self._prefix + name)(*args)
+
+    def _sp(self):
+        return C.c_void_p(self.state.ctypes.data)
+
+    def restart(self, ann: bytes = b"", key: bytes = b"") -> None:
+        self._call("Restart", bytes(ann), C.c_size_t(len(ann)), bytes(key), C.c_size_t(len(key)), self._sp())
+
+    def _inout(self, name, data: bytes) -> bytes:
+        buf = np.frombuffer(bytes(data), dtype=np.uint8).copy()
+        self._call(name, C.c_void_p(buf.ctypes.data), C.c_size_t(buf.size), self._sp())
+        return buf.tobytes()
+
+    def absorb_start(self): self._call("AbsorbStart", self._sp())
+    def absorb_step(self, data: bytes): self._inout("AbsorbStep", data)
+    def absorb(self, data: bytes): self.absorb_start(); self.absorb_step(data)
+    def squeeze_start(self): self._call("SqueezeStart", self._sp())
+    def squeeze_step(self, n: int) -> bytes: return self._inout("SqueezeStep", bytes(n))
+    def squeeze(self, n: int) -> bytes: self.squeeze_start(); return self.squeeze_step(n)
+    def encr_start(self): self._call("EncrStart", self._sp())
+    def encr_step(self, data: bytes) -> bytes: return self._inout("EncrStep", data)
+    def encr(self, data: bytes) -> bytes: self.encr_start(); return self.encr_step(data)
+    def decr_start(self): self._call("DecrStart", self._sp())
+    def decr_step(self, data: bytes) -> bytes: return self._inout("DecrStep", data)
+    def decr(self, data: bytes) -> bytes: self.decr_start(); return self.decr_step(data)
+    def ratchet(self): self._call("Ratchet", self._sp())
+
+    def copy(self):
+        o = object.__new__(type(self))
+        o.L, o.state = self.L, self.state.copy()
+        return o
+
+
+__all__ += ["BashPrg"]

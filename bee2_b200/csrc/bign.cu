@@ -15,6 +15,7 @@
 //   * variable base Q: 4-bit windows, per-thread table {1..15}Q in local memory
 //     -> 4 doublings + 1 addition per nibble.
 // The reference's interleaved wNAF (ec.c:1206-1268) is irregular and would diverge.
+#include <mutex>
 #include "ecp256.cuh"
 #include "belt_dev.cuh"
 
@@ -515,10 +516,18 @@ ecp_addmul_kernel(u8* __restrict__ out, int* __restrict__ ok, const u8* __restri
 // q and yG are static constants, GTAB is built lazily; only the belt S-box needs uploading
 extern "C" u32 b2g_bign_upload_tables(const u8 H[256]) { return belt_upload_H(H); }
 
+static u32 bign_build_gtab(cudaStream_t st);
+// the device entry points may be called from several host threads: build the table once
 static u32 bign_ensure_gtab(cudaStream_t st)
 {
+	static std::mutex mu;
 	if (g_gtab)
 		return B2G_OK;
+	std::lock_guard<std::mutex> lock(mu);
+	return g_gtab ? B2G_OK : bign_build_gtab(st);
+}
+static u32 bign_build_gtab(cudaStream_t st)
+{
 	uint4* p = 0;
 	if (cudaMalloc(&p, (size_t)BIGN_GN * BIGN_GE * 64) != cudaSuccess)
 		return b2g_check_launch("cudaMalloc(gtab)");

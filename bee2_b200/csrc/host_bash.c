@@ -234,3 +234,179 @@ bool_t bashHashStepV(const octet hash[], size_t hash_len, void* state)
 	sponge_final(st);
 	return memcmp(hash, st->s1, hash_len) == 0;
 }
+
+/* ---------------------------------------------------------------- bash-prg (bash_prg.c:54-385) */
+/* same layout as the reference's bash_prg_st; every bash-f runs on the device */
+typedef struct
+{
+	size_t l;
+	size_t d;
+	octet s[192];
+	size_t buf_len;
+	size_t pos;
+	octet t[192];
+} bash_prg_st;
+
+#define PRG_NULL 0x01
+#define PRG_KEY 0x05
+#define PRG_DATA 0x09
+#define PRG_TEXT 0x0D
+#define PRG_OUT 0x11
+
+u32 b2g_bashPrgBlocks_dev(void* d_states, void* d_data, size_t stride, size_t nblocks, size_t buf_len,
+	int mode, int pre_f, size_t count, void* stream);
+
+size_t bashPrg_keep(void) { return sizeof(bash_prg_st); }
+
+/* bash-f on the state, then `nfull` whole blocks of `mode` over buf (in place) */
+static void prg_blocks(bash_prg_st* st, octet* buf, size_t nfull, int mode, const char* fn)
+{
+	err_t code;
+	b2g_slot* sl;
+	void *d_state, *d_data;
+	const size_t bytes = nfull * st->buf_len;
+	if ((code = b2g_ensure_device()))
+		b2g_die(fn, code);
+	b2g_lock();
+	sl = b2g_slot_get(0);
+	if ((code = b2g_slot_buf(sl, 0, bytes, &d_data)) || (code = b2g_slot_buf(sl, 1, 192, &d_state)))
+		goto done;
+	CU(cudaMemcpyAsync(d_state, st->s, 192, cudaMemcpyHostToDevice, sl->stream), "H2D(prg state)");
+	if (bytes && mode != 1)
+		CU(cudaMemcpyAsync(d_data, buf, bytes, cudaMemcpyHostToDevice, sl->stream), "H2D(prg data)");
+	if ((code = b2g_bashPrgBlocks_dev(d_state, d_data, bytes, nfull, st->buf_len, mode, 1, 1, sl->stream)))
+		goto done;
+	CU(cudaMemcpyAsync(st->s, d_state, 192, cudaMemcpyDeviceToHost, sl->stream), "D2H(prg state)");
+	if (bytes && mode != 0)
+		CU(cudaMemcpyAsync(buf, d_data, bytes, cudaMemcpyDeviceToHost, sl->stream), "D2H(prg data)");
+	CU(cudaStreamSynchronize(sl->stream), "sync(prg)");
+done:
+	b2g_unlock();
+	if (code)
+		b2g_die(fn, code);
+}
+
+static void prg_commit(bash_prg_st* st, octet code)   /* bash_prg.c:92-105 */
+{
+	st->s[st->pos] ^= code;
+	st->s[st->buf_len] ^= 0x80;
+	prg_blocks(st, 0, 0, 0, "bashPrgCommit");
+	st->pos = 0;
+}
+
+void bashPrgStart(void* state, size_t l, size_t d, const octet ann[], size_t ann_len, const octet key[],
+	size_t key_len)
+{
+	bash_prg_st* st = (bash_prg_st*)state;
+	st->pos = 1 + ann_len + key_len;
+	memset(st->s, 0, 192);
+	st->s[0] = (octet)(ann_len * 4 + key_len / 4);
+	if (ann_len) memcpy(st->s + 1, ann, ann_len);
+	if (key_len) memcpy(st->s + 1 + ann_len, key, key_len);
+	st->s[192 - 8] = (octet)(l / 4 + d);
+	st->buf_len = key_len ? (192 - l * (2 + d) / 16) : (192 - d * l / 4);
+	st->l = l, st->d = d;
+}
+
+void bashPrgRestart(const octet ann[], size_t ann_len, const octet key[], size_t key_len, void* state)
+{
+	bash_prg_st* st = (bash_prg_st*)state;
+	size_t i;
+	if (key_len)
+	{
+		prg_commit(st, PRG_KEY);
+		st->buf_len = 192 - st->l * (2 + st->d) / 16;
+	}
+	else
+		prg_commit(st, PRG_NULL);
+	st->pos = 1 + ann_len + key_len;
+	st->s[0] ^= (octet)(ann_len * 4 + key_len / 4);
+	for (i = 0; i < ann_len; ++i) st->s[1 + i] ^= ann[i];
+	for (i = 0; i < key_len; ++i) st->s[1 + ann_len + i] ^= key[i];
+}
+
+/* the octets that do not complete a block are merged into the host-side state (bookkeeping);
+   mode as in bash_prg_kernel */
+static void prg_bytes(bash_prg_st* st, octet* buf, size_t n, int mode)
+{
+	octet* s = st->s + st->pos;
+	size_t i;
+	for (i = 0; i < n; ++i)
+		switch (mode)
+		{
+		case 0: s[i] ^= buf[i]; break;
+		case 1: buf[i] = s[i]; break;
+		case 2: s[i] ^= buf[i], buf[i] = s[i]; break;
+		default: buf[i] ^= s[i], s[i] ^= buf[i]; break;
+		}
+}
+
+static void prg_step(bash_prg_st* st, octet* buf, size_t count, int mode, const char* fn)
+{
+	size_t nfull;
+	if (count < st->buf_len - st->pos)
+	{
+		prg_bytes(st, buf, count, mode);
+		st->pos += count;
+		return;
+	}
+	prg_bytes(st, buf, st->buf_len - st->pos, mode);
+	buf += st->buf_len - st->pos, count -= st->buf_len - st->pos;
+	st->pos = 0;
+	nfull = count / st->buf_len;
+	prg_blocks(st, buf, nfull, mode, fn);
+	buf += nfull * st->buf_len, count -= nfull * st->buf_len;
+	if (count)
+		prg_bytes(st, buf, count, mode);   /* into s[0..count): pos is still 0 here */
+	st->pos = count;
+}
+
+void bashPrgAbsorbStart(void* state) { prg_commit((bash_prg_st*)state, PRG_DATA); }
+void bashPrgAbsorbStep(const void* buf, size_t count, void* state)
+{
+	/* absorb never writes to buf */
+	prg_step((bash_prg_st*)state, (octet*)(size_t)buf, count, 0, "bashPrgAbsorbStep");
+}
+void bashPrgAbsorb(const void* buf, size_t count, void* state)
+{
+	bashPrgAbsorbStart(state);
+	bashPrgAbsorbStep(buf, count, state);
+}
+void bashPrgSqueezeStart(void* state) { prg_commit((bash_prg_st*)state, PRG_OUT); }
+void bashPrgSqueezeStep(void* buf, size_t count, void* state)
+{
+	prg_step((bash_prg_st*)state, (octet*)buf, count, 1, "bashPrgSqueezeStep");
+}
+void bashPrgSqueeze(void* buf, size_t count, void* state)
+{
+	bashPrgSqueezeStart(state);
+	bashPrgSqueezeStep(buf, count, state);
+}
+void bashPrgEncrStart(void* state) { prg_commit((bash_prg_st*)state, PRG_TEXT); }
+void bashPrgEncrStep(void* buf, size_t count, void* state)
+{
+	prg_step((bash_prg_st*)state, (octet*)buf, count, 2, "bashPrgEncrStep");
+}
+void bashPrgEncr(void* buf, size_t count, void* state)
+{
+	bashPrgEncrStart(state);
+	bashPrgEncrStep(buf, count, state);
+}
+void bashPrgDecrStart(void* state) { prg_commit((bash_prg_st*)state, PRG_TEXT); }
+void bashPrgDecrStep(void* buf, size_t count, void* state)
+{
+	prg_step((bash_prg_st*)state, (octet*)buf, count, 3, "bashPrgDecrStep");
+}
+void bashPrgDecr(void* buf, size_t count, void* state)
+{
+	bashPrgDecrStart(state);
+	bashPrgDecrStep(buf, count, state);
+}
+void bashPrgRatchet(void* state)   /* bash_prg.c:374-385 */
+{
+	bash_prg_st* st = (bash_prg_st*)state;
+	size_t i;
+	memcpy(st->t, st->s, 192);
+	prg_commit(st, PRG_NULL);
+	for (i = 0; i < 192; ++i) st->s[i] ^= st->t[i];
+}

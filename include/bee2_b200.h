@@ -94,6 +94,31 @@ void bashHashStepH(const void* buf, size_t count, void* state);
 void bashHashStepG(octet hash[], size_t hash_len, void* state);
 bool_t bashHashStepV(const octet hash[], size_t hash_len, void* state);
 err_t bashHash(octet hash[], size_t l, const void* src, size_t count);
+/* drop-in: bash.h (bash_prg.c:54-385) — the programmable sponge automaton; state layout =
+   bash_prg_st. A single automaton is sequential by construction: these calls run its
+   permutations on the device one after another (correct, latency-bound). */
+size_t bashPrg_keep(void);
+void bashPrgStart(void* state, size_t l, size_t d, const octet ann[], size_t ann_len,
+	const octet key[], size_t key_len);
+void bashPrgRestart(const octet ann[], size_t ann_len, const octet key[], size_t key_len, void* state);
+void bashPrgAbsorbStart(void* state);
+void bashPrgAbsorbStep(const void* buf, size_t count, void* state);
+void bashPrgAbsorb(const void* buf, size_t count, void* state);
+void bashPrgSqueezeStart(void* state);
+void bashPrgSqueezeStep(void* buf, size_t count, void* state);
+void bashPrgSqueeze(void* buf, size_t count, void* state);
+void bashPrgEncrStart(void* state);
+void bashPrgEncrStep(void* buf, size_t count, void* state);
+void bashPrgEncr(void* buf, size_t count, void* state);
+void bashPrgDecrStart(void* state);
+void bashPrgDecrStep(void* buf, size_t count, void* state);
+void bashPrgDecr(void* buf, size_t count, void* state);
+void bashPrgRatchet(void* state);
+/* device: `count` automata (192-octet states, 8-aligned) each run bash-f (if pre_f) and then
+   nblocks whole buf_len-octet blocks of one command over its data at d_data + i*stride, in place:
+   mode 0 absorb, 1 squeeze, 2 encr, 3 decr */
+err_t b2g_bashPrgBlocks_dev(void* d_states, void* d_data, size_t stride, size_t nblocks,
+	size_t buf_len, int mode, int pre_f, size_t count, void* stream);
 /* batch: `count` messages of msg_len octets, message i at msgs + i*stride; digest i
    (l/4 octets) at hashes + i*(l/4). Same checks as bashHash. */
 err_t bashHashBatch(octet* hashes, size_t l, const void* msgs, size_t msg_len,

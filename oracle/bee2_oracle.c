@@ -789,3 +789,81 @@ u32 orc_beltCHEUnwrap(void* dest, const void* src1, size_t n1, const void* src2,
 	che_crypt((u8*)dest, n1, k, r);
 	return ORC_OK;
 }
+
+/* ======================================================================= bash-prg (bash_prg.c:56-385) */
+/* programmable sponge automaton; own state layout (the semantics of bash_prg_st, :54-62) */
+
+static void prg_commit(orc_bash_prg_st* st, u8 code)   /* bash_prg.c:92-105 */
+{
+	st->s[st->pos] ^= code;
+	st->s[st->buf_len] ^= 0x80;
+	orc_bashF(st->s);
+	st->pos = 0;
+}
+
+void orc_bashPrgStart(orc_bash_prg_st* st, size_t l, size_t d, const u8* ann, size_t ann_len,
+	const u8* key, size_t key_len)
+{
+	memset(st->s, 0, 192);
+	st->pos = 1 + ann_len + key_len;
+	st->s[0] = (u8)(ann_len * 4 + key_len / 4);
+	if (ann_len) memcpy(st->s + 1, ann, ann_len);
+	if (key_len) memcpy(st->s + 1 + ann_len, key, key_len);
+	st->s[184] = (u8)(l / 4 + d);
+	st->buf_len = key_len ? 192 - l * (2 + d) / 16 : 192 - d * l / 4;
+	st->l = l, st->d = d;
+}
+
+void orc_bashPrgRestart(const u8* ann, size_t ann_len, const u8* key, size_t key_len, orc_bash_prg_st* st)
+{
+	size_t i;
+	if (key_len)
+		prg_commit(st, 0x05), st->buf_len = 192 - st->l * (2 + st->d) / 16;
+	else
+		prg_commit(st, 0x01);
+	st->pos = 1 + ann_len + key_len;
+	st->s[0] ^= (u8)(ann_len * 4 + key_len / 4);
+	for (i = 0; i < ann_len; ++i) st->s[1 + i] ^= ann[i];
+	for (i = 0; i < key_len; ++i) st->s[1 + ann_len + i] ^= key[i];
+}
+
+/* mode: 0 absorb (s ^= in), 1 squeeze (out = s), 2 encr (s ^= buf, buf = s), 3 decr (buf ^= s, s ^= buf) */
+static void prg_step(orc_bash_prg_st* st, u8* buf, size_t n, int mode)
+{
+	while (n)
+	{
+		size_t take = st->buf_len - st->pos, i;
+		if (take > n) take = n;
+		for (i = 0; i < take; ++i)
+		{
+			u8* s = st->s + st->pos + i;
+			switch (mode)
+			{
+			case 0: *s ^= buf[i]; break;
+			case 1: buf[i] = *s; break;
+			case 2: *s ^= buf[i], buf[i] = *s; break;
+			default: buf[i] ^= *s, *s ^= buf[i]; break;
+			}
+		}
+		st->pos += take, buf += take, n -= take;
+		if (st->pos == st->buf_len)
+			orc_bashF(st->s), st->pos = 0;
+	}
+}
+
+void orc_bashPrgAbsorbStart(orc_bash_prg_st* st) { prg_commit(st, 0x09); }
+void orc_bashPrgAbsorbStep(const void* buf, size_t n, orc_bash_prg_st* st) { prg_step(st, (u8*)(size_t)buf, n, 0); }
+void orc_bashPrgSqueezeStart(orc_bash_prg_st* st) { prg_commit(st, 0x11); }
+void orc_bashPrgSqueezeStep(void* buf, size_t n, orc_bash_prg_st* st) { prg_step(st, (u8*)buf, n, 1); }
+void orc_bashPrgEncrStart(orc_bash_prg_st* st) { prg_commit(st, 0x0D); }
+void orc_bashPrgEncrStep(void* buf, size_t n, orc_bash_prg_st* st) { prg_step(st, (u8*)buf, n, 2); }
+void orc_bashPrgDecrStart(orc_bash_prg_st* st) { prg_commit(st, 0x0D); }
+void orc_bashPrgDecrStep(void* buf, size_t n, orc_bash_prg_st* st) { prg_step(st, (u8*)buf, n, 3); }
+void orc_bashPrgRatchet(orc_bash_prg_st* st)           /* bash_prg.c:374-385 */
+{
+	u8 t[192];
+	int i;
+	memcpy(t, st->s, 192);
+	prg_commit(st, 0x01);
+	for (i = 0; i < 192; ++i) st->s[i] ^= t[i];
+}

@@ -37,6 +37,21 @@ void orc_bashHashStart(orc_bash_st* st, size_t l);                          /* b
 void orc_bashHashStepH(const void* buf, size_t n, orc_bash_st* st);         /* bash_hash.c:52-79 */
 void orc_bashHashStepG(uint8_t* hash, size_t hash_len, const orc_bash_st*); /* bash_hash.c:81-109 */
 
+/* programmable automaton bash-prg (bash_prg.c:56-385) */
+typedef struct { size_t l, d; uint8_t s[192]; size_t buf_len, pos; } orc_bash_prg_st;
+void orc_bashPrgStart(orc_bash_prg_st* st, size_t l, size_t d, const uint8_t* ann, size_t ann_len,
+	const uint8_t* key, size_t key_len);
+void orc_bashPrgRestart(const uint8_t* ann, size_t ann_len, const uint8_t* key, size_t key_len, orc_bash_prg_st* st);
+void orc_bashPrgAbsorbStart(orc_bash_prg_st* st);
+void orc_bashPrgAbsorbStep(const void* buf, size_t n, orc_bash_prg_st* st);
+void orc_bashPrgSqueezeStart(orc_bash_prg_st* st);
+void orc_bashPrgSqueezeStep(void* buf, size_t n, orc_bash_prg_st* st);
+void orc_bashPrgEncrStart(orc_bash_prg_st* st);
+void orc_bashPrgEncrStep(void* buf, size_t n, orc_bash_prg_st* st);
+void orc_bashPrgDecrStart(orc_bash_prg_st* st);
+void orc_bashPrgDecrStep(void* buf, size_t n, orc_bash_prg_st* st);
+void orc_bashPrgRatchet(orc_bash_prg_st* st);
+
 /* ---- belt (STB 34.101.31) ---- */
 const uint8_t* orc_beltH(void);                                             /* belt_block.c:43-65 */
 void orc_beltKeyExpand2(uint32_t key_[8], const uint8_t* key, size_t len);  /* belt_block.c:88-106 */

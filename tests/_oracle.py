@@ -224,3 +224,21 @@ def ref_bignPubkeyCalc(priv: bytes):
     pub = C.create_string_buffer(64)
     code = ref().bignPubkeyCalc(pub, C.byref(ref_params()), bytes(priv))
     return code, pub.raw
+
+
+def BashPrg(l, d, ann=b"", key=b""):
+    """The oracle's bash-prg automaton behind the same Python interface as bee2_b200.BashPrg."""
+    import bee2_b200.api as api
+
+    class _OrcPrg(api.BashPrg):
+        _prefix = "orc_bashPrg"
+    return _OrcPrg(l, d, ann, key, _lib=port(), _keep=8 + 8 + 192 + 8 + 8)
+
+
+def RefBashPrg(l, d, ann=b"", key=b""):
+    import bee2_b200.api as api
+    ref().bashPrg_keep.restype = C.c_size_t
+
+    class _RefPrg(api.BashPrg):
+        _prefix = "bashPrg"
+    return _RefPrg(l, d, ann, key, _lib=ref(), _keep=ref().bashPrg_keep())

@@ -81,6 +81,15 @@ def test_ragged_batch_bsum_style():
     assert e.value.code == b.ERR_BAD_INPUT
 
 
+def test_bash_prg_A4_A5_A6_and_random_programs():
+    import _prg_kats
+    _prg_kats.run(b.BashPrg, H)
+    rng = np.random.default_rng(10)
+    for _ in range(12):
+        _prg_kats.random_program(b.BashPrg, o.BashPrg, rng, H)
+    assert b.lib().bashPrg_keep() == 8 + 8 + 192 + 8 + 8 + 192        # bash_prg.c:54-62
+
+
 def test_bashFBatch_random():
     rng = np.random.default_rng(1)
     st = rng.integers(0, 256, size=(300, 192), dtype=np.uint8)

@@ -29,6 +29,16 @@ def test_bashHash_A3(t):
     assert o.bashHash(t["l"], H[: t["len"]]).hex().upper() == t["out"]
 
 
+def test_bash_prg_A4_A5_A6():
+    import _prg_kats
+    _prg_kats.run(o.BashPrg, H)
+    if o.ref() is not None:
+        _prg_kats.run(o.RefBashPrg, H)
+        rng = np.random.default_rng(9)
+        for _ in range(20):
+            _prg_kats.random_program(o.BashPrg, o.RefBashPrg, rng, H)
+
+
 def test_belt_block_A1_A4():
     for t in KAT["beltBlock"]:
         f = o.beltBlockEncr if t["op"] == "encr" else o.beltBlockDecr
