@@ -1,0 +1,245 @@
+// ecp.cuh — Jacobian point arithmetic on y^2 = x^3 - 3x + b over GF(2^(32N) - c), N = 8/12/16
+// (the three standard bign curves all have a = p - 3, bign_params.c:42-49,86-93,141-150).
+//
+// Replaces the reference's ecpDblJA3 / ecpAddJ / ecpAddAJ / ecpToAJ (ecp_j.c:241-299,
+// :397-497, :516-590, :104-133) and the variable-base part of ecMulA / ecAddMulA
+// (ec.c:497-525, :1183-1273). x = X/Z^2, y = Y/Z^3, O <=> Z = 0. The formulas never use the
+// coefficient b, exactly like the reference's.
+//
+// Every addition is COMPLETE in the reference's sense (ecp_j.c:416-427, :455-464): O + P,
+// P + O, P + P (-> doubling) and P + (-P) (-> O) are detected and handled by rare,
+// warp-divergent branches, so crafted inputs (Q = +-G, small multiples of G, ...) give the
+// same affine result as the reference.
+#pragma once
+#include "gfp.cuh"
+
+template <int N> struct pt { fe<N> X, Y, Z; };
+// a scalar of up to 32 N bits handed BY VALUE to the out-of-line multiplication routines: the
+// kernels keep no address-taken locals besides the accumulator (nvcc 12.9 was seen to overlap the
+// stack slots of two live address-taken locals of bign_verify_kernel — see DESIGN.md §4.3)
+template <int N> struct sc { u32 w[N]; };
+
+#define PT_OP GFP_HD
+
+template <int N> GFP_HD void pt_set_inf(pt<N>& R)
+{
+	fe_set_u32<N>(R.X, 1), fe_set_u32<N>(R.Y, 1), fe_set_u32<N>(R.Z, 0);
+}
+template <int N> GFP_HD void pt_set_affine(pt<N>& R, const fe<N>& x, const fe<N>& y)
+{
+	R.X = x, R.Y = y, fe_set_u32<N>(R.Z, 1);
+}
+template <int N> GFP_HD bool pt_is_inf(const pt<N>& P) { return fe_is_zero<N>(P.Z); }
+template <int N> GFP_HD void fe_neg(fe<N>& r, const fe<N>& a)
+{
+	fe<N> z;
+	fe_set_u32<N>(z, 0);
+	fe_sub<N>(r, z, a);
+}
+
+// R = 2P, a = -3 (3M + 5S). Z = 0 or Y = 0 give Z3 = 0 without special casing.
+template <int N> PT_OP void pt_dbl(pt<N>& R, const pt<N>& P)
+{
+	fe<N> delta, gamma, beta, alpha, t, u;
+	fe_sqr<N>(delta, P.Z);
+	fe_sqr<N>(gamma, P.Y);
+	fe_mul<N>(beta, P.X, gamma);
+	fe_sub<N>(t, P.X, delta), fe_add<N>(u, P.X, delta);
+	fe_mul<N>(alpha, t, u);
+	fe_dbl<N>(t, alpha), fe_add<N>(alpha, alpha, t);              // 3 (X - Z^2)(X + Z^2)
+	fe_add<N>(t, P.Y, P.Z), fe_sqr<N>(t, t);
+	fe_sub<N>(t, t, gamma), fe_sub<N>(R.Z, t, delta);             // Z3 = (Y + Z)^2 - Y^2 - Z^2
+	fe_shl<2, N>(beta, beta);                                     // 4 beta
+	fe_sqr<N>(t, alpha);
+	fe_sub<N>(t, t, beta), fe_sub<N>(R.X, t, beta);               // X3 = alpha^2 - 8 beta
+	fe_sqr<N>(gamma, gamma);
+	fe_shl<3, N>(gamma, gamma);                                   // 8 gamma^2
+	fe_sub<N>(t, beta, R.X), fe_mul<N>(t, alpha, t);
+	fe_sub<N>(R.Y, t, gamma);                                     // Y3 = alpha (4 beta - X3) - 8 gamma^2
+}
+// out-of-line copy for the rare P + P branches
+template <int N> __host__ __device__ __noinline__ void pt_dbl_slow(pt<N>* R, const pt<N>* P)
+{
+	pt<N> t = *P;
+	pt_dbl<N>(t, t);
+	*R = t;
+}
+
+// R = P + (x2, y2), the second point affine and finite (7M + 4S)
+template <int N> PT_OP void pt_madd(pt<N>& R, const pt<N>& P, const fe<N>& x2, const fe<N>& y2)
+{
+	fe<N> z1z1, u2, s2, h, hh, i, j, r, v, t;
+	fe_sqr<N>(z1z1, P.Z);
+	fe_mul<N>(u2, x2, z1z1);
+	fe_mul<N>(t, P.Z, z1z1), fe_mul<N>(s2, y2, t);
+	fe_sub<N>(h, u2, P.X);
+	fe_sub<N>(r, s2, P.Y);
+	const bool p_inf = fe_is_zero<N>(P.Z);
+	if (p_inf || fe_is_zero<N>(h))
+	{
+		if (p_inf)
+			pt_set_affine<N>(R, x2, y2);
+		else if (fe_is_zero<N>(r))
+		{
+			pt<N> q;
+			pt_set_affine<N>(q, x2, y2);
+			pt_dbl_slow<N>(&R, &q);
+		}
+		else
+			pt_set_inf<N>(R);
+		return;
+	}
+	fe_dbl<N>(r, r);
+	fe_sqr<N>(hh, h);
+	fe_shl<2, N>(i, hh);                                          // I = 4 HH
+	fe_mul<N>(j, h, i);
+	fe_mul<N>(v, P.X, i);
+	fe_add<N>(t, P.Z, h), fe_sqr<N>(t, t);
+	fe_sub<N>(t, t, z1z1), fe_sub<N>(t, t, hh);                   // Z3 = (Z1 + H)^2 - Z1Z1 - HH
+	fe<N> z3 = t;
+	fe_sqr<N>(t, r);
+	fe_sub<N>(t, t, j), fe_sub<N>(t, t, v), fe_sub<N>(t, t, v);   // X3 = r^2 - J - 2V
+	fe<N> x3 = t;
+	fe_sub<N>(t, v, x3), fe_mul<N>(t, r, t);
+	fe_mul<N>(j, P.Y, j), fe_dbl<N>(j, j);
+	fe_sub<N>(R.Y, t, j);                                         // Y3 = r (V - X3) - 2 Y1 J
+	R.X = x3, R.Z = z3;
+}
+
+// R = P + Q, both Jacobian (11M + 5S)
+template <int N> PT_OP void pt_add(pt<N>& R, const pt<N>& P, const pt<N>& Q)
+{
+	fe<N> z1z1, z2z2, u1, u2, s1, s2, h, i, j, r, v, t;
+	fe_sqr<N>(z1z1, P.Z), fe_sqr<N>(z2z2, Q.Z);
+	fe_mul<N>(u1, P.X, z2z2), fe_mul<N>(u2, Q.X, z1z1);
+	fe_mul<N>(t, Q.Z, z2z2), fe_mul<N>(s1, P.Y, t);
+	fe_mul<N>(t, P.Z, z1z1), fe_mul<N>(s2, Q.Y, t);
+	fe_sub<N>(h, u2, u1);
+	fe_sub<N>(r, s2, s1);
+	const bool p_inf = fe_is_zero<N>(P.Z), q_inf = fe_is_zero<N>(Q.Z);
+	if (p_inf || q_inf || fe_is_zero<N>(h))
+	{
+		if (p_inf)
+			R = Q;
+		else if (q_inf)
+			R = P;
+		else if (fe_is_zero<N>(r))
+			pt_dbl_slow<N>(&R, &P);
+		else
+			pt_set_inf<N>(R);
+		return;
+	}
+	fe_dbl<N>(r, r);
+	fe_dbl<N>(t, h), fe_sqr<N>(i, t);                             // I = (2H)^2
+	fe_mul<N>(j, h, i);
+	fe_mul<N>(v, u1, i);
+	fe_add<N>(t, P.Z, Q.Z), fe_sqr<N>(t, t);
+	fe_sub<N>(t, t, z1z1), fe_sub<N>(t, t, z2z2);
+	fe<N> z3;
+	fe_mul<N>(z3, t, h);                                          // Z3 = ((Z1 + Z2)^2 - Z1Z1 - Z2Z2) H
+	fe_sqr<N>(t, r);
+	fe_sub<N>(t, t, j), fe_sub<N>(t, t, v), fe_sub<N>(t, t, v);   // X3 = r^2 - J - 2V
+	fe<N> x3 = t;
+	fe_sub<N>(t, v, x3), fe_mul<N>(t, r, t);
+	fe_mul<N>(j, s1, j), fe_dbl<N>(j, j);
+	fe_sub<N>(R.Y, t, j);                                         // Y3 = r (V - X3) - 2 S1 J
+	R.X = x3, R.Z = z3;
+}
+
+// affine coordinates of a finite point, canonical residues (ecp_j.c:104-133)
+template <int N> GFP_HD void pt_to_affine(fe<N>& x, fe<N>& y, const pt<N>& P)
+{
+	fe<N> zi, zi2;
+	fe_inv<N>(zi, P.Z);
+	fe_sqr<N>(zi2, zi);
+	fe_mul<N>(x, P.X, zi2);
+	fe_mul<N>(zi2, zi2, zi), fe_mul<N>(y, P.Y, zi2);
+	fe_canon<N>(x), fe_canon<N>(y);
+}
+template <int N> GFP_HD void pt_to_affine_x(fe<N>& x, const pt<N>& P)
+{
+	fe<N> zi;
+	fe_inv<N>(zi, P.Z);
+	fe_sqr<N>(zi, zi);
+	fe_mul<N>(x, P.X, zi);
+	fe_canon<N>(x);
+}
+
+// ---------------------------------------------------------------- variable-base multiplication
+// acc = k * (x, y) for a scalar of nbits bits (little-endian limbs, bits above nbits must be 0).
+// REGULAR signed 5-bit windows so that all lanes of a warp run the same doublings and additions
+// in lock-step (the reference's width-5 wNAF, ec.c:435-484, is irregular and would diverge):
+//   k = sum d_i 32^i, d_i in [-15, 16]: d_i = (window i) + carry_i, minus 32 (carry out) if > 16;
+//   table {1..16}(x, y) in local memory (8 doublings + 7 mixed additions);
+//   5 doublings + 1 addition per window, most significant first; nbits/5 + 1 windows, the top one
+//   always has a spare bit and absorbs the last carry.
+#define PT_WIN 5
+template <int N> __host__ __device__ __noinline__ void pt_mul_var(pt<N>& acc, const sc<N> ks, int nbits,
+	const fe<N> x, const fe<N> y)
+{
+	const u32* k = ks.w;
+	constexpr int HALF = 1 << (PT_WIN - 1);
+	pt<N> T[HALF + 1];   // T[j] = j * (x, y); T[0] unused. Dynamic indexing -> local memory.
+	pt_set_affine<N>(T[1], x, y);
+#pragma unroll 1
+	for (int j = 2; j <= HALF; ++j)
+	{
+		if (j & 1)
+			pt_madd<N>(T[j], T[j - 1], x, y);
+		else
+			pt_dbl<N>(T[j], T[j >> 1]);
+	}
+	const int nw = nbits / PT_WIN + 1;
+	// carries of the recoding, least significant window first: bit i of cy = carry INTO window i
+	u32 cy[(32 * N / PT_WIN + 2 + 31) / 32];
+#pragma unroll
+	for (int i = 0; i < (int)(sizeof(cy) / 4); ++i) cy[i] = 0;
+	{
+		u32 c = 0;
+#pragma unroll 1
+		for (int i = 0; i < nw; ++i)
+		{
+			const int bit = PT_WIN * i, limb = bit >> 5, sh = bit & 31;
+			u32 w = limb < N ? k[limb] >> sh : 0u;
+			if (sh > 32 - PT_WIN && limb + 1 < N)
+				w |= k[limb + 1] << (32 - sh);
+			w = (w & (2 * HALF - 1)) + c;
+			cy[i >> 5] |= c << (i & 31);
+			c = w > HALF ? 1u : 0u;
+		}
+	}
+	bool first = true;
+#pragma unroll 1
+	for (int i = nw - 1; i >= 0; --i)
+	{
+		if (!first)
+		{
+#pragma unroll 1
+			for (int s = 0; s < PT_WIN; ++s)
+				pt_dbl<N>(acc, acc);
+		}
+		const int bit = PT_WIN * i, limb = bit >> 5, sh = bit & 31;
+		u32 w = limb < N ? k[limb] >> sh : 0u;
+		if (sh > 32 - PT_WIN && limb + 1 < N)
+			w |= k[limb + 1] << (32 - sh);
+		w = (w & (2 * HALF - 1)) + ((cy[i >> 5] >> (i & 31)) & 1u);
+		const bool neg = w > HALF;
+		const u32 d = neg ? 2 * HALF - w : w;
+		if (first)
+		{
+			// the top window only selects (no doublings of O); it is never negative
+			if (d)
+				acc = T[d];
+			else
+				pt_set_inf<N>(acc);
+			first = false;
+		}
+		else if (d)
+		{
+			pt<N> Q = T[d];
+			if (neg)
+				fe_neg<N>(Q.Y, Q.Y);
+			pt_add<N>(acc, acc, Q);
+		}
+	}
+}

@@ -12,8 +12,10 @@
 #define MB_UNROLL 32
 
 enum { MB_LOP3 = 0, MB_SHF = 1, MB_PRMT = 2, MB_IADD3 = 3, MB_IMAD = 4, MB_IMAD_WIDE = 5, MB_LDS = 6, MB_MIX_LOP3_IMADW = 7,
-	MB_MIX_LOP3_IMAD = 8, MB_MIX_LOP3_FFMA = 9, MB_IMAD_HI = 10, MB_MIX_LOP3_LDS = 11, MB_FFMA = 12 };
-#define MB_IS_MIX(k) ((k) == MB_MIX_LOP3_IMADW || (k) == MB_MIX_LOP3_IMAD || (k) == MB_MIX_LOP3_FFMA || (k) == MB_MIX_LOP3_LDS)
+	MB_MIX_LOP3_IMAD = 8, MB_MIX_LOP3_FFMA = 9, MB_IMAD_HI = 10, MB_MIX_LOP3_LDS = 11, MB_FFMA = 12, MB_DFMA = 13, MB_MIX_DFMA_IMADW = 14, MB_MIX_IMAD_IMADW = 15,
+	MB_MIX_IADDX_IMADW = 16 };
+#define MB_IS_MIX(k) ((k) == MB_MIX_LOP3_IMADW || (k) == MB_MIX_LOP3_IMAD || (k) == MB_MIX_LOP3_FFMA || (k) == MB_MIX_LOP3_LDS || \
+	(k) == MB_MIX_DFMA_IMADW || (k) == MB_MIX_IMAD_IMADW || (k) == MB_MIX_IADDX_IMADW)
 
 template <int KIND>
 __global__ void __launch_bounds__(1024) mb_kernel(u32* out, u32 iters, u32 a, u32 b, u32 sh)
@@ -22,13 +24,15 @@ __global__ void __launch_bounds__(1024) mb_kernel(u32* out, u32 iters, u32 a, u3
 	u32 x[MB_ILP], y[MB_ILP];
 	u64 w[MB_ILP];
 	float f[MB_ILP];
+	double d[MB_ILP];
+	const double da = 1.0 + 1e-9 * (a & 3), db = 1e-3 * (b & 7);
 	const float fa = __uint_as_float(0x3F800001u + (a & 1)), fb = __uint_as_float(b & 0x007FFFFFu);
 #pragma unroll
 	for (int i = 0; i < MB_ILP; ++i)
 	{
 		x[i] = (KIND == MB_LDS || KIND == MB_MIX_LOP3_LDS) ? ((threadIdx.x + i) & 63u) << 5 : threadIdx.x * 2654435761u + i * a;
 		w[i] = ((u64)x[i] << 32) | (b + i);
-		y[i] = x[i] ^ b, f[i] = (float)(threadIdx.x + i);
+		y[i] = x[i] ^ b, f[i] = (float)(threadIdx.x + i), d[i] = (double)(threadIdx.x + i);
 	}
 	for (u32 i = threadIdx.x; i < 32 * 64; i += blockDim.x)
 		sm[i] = (i * 7 + a) & (63u << 5);   // next index: keeps the lane's own bank (multiple of 32 words)
@@ -74,6 +78,23 @@ __global__ void __launch_bounds__(1024) mb_kernel(u32* out, u32 iters, u32 a, u3
 				}
 				else if (KIND == MB_FFMA)
 					asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(fa), "f"(fb));
+				else if (KIND == MB_DFMA)
+					asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(da), "d"(db));
+				else if (KIND == MB_MIX_DFMA_IMADW)
+				{
+					asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(da), "d"(db));
+					asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(sh), "r"(a));
+				}
+				else if (KIND == MB_MIX_IMAD_IMADW)
+				{
+					asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(a), "r"(b));
+					asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(sh), "r"(a));
+				}
+				else if (KIND == MB_MIX_IADDX_IMADW)
+				{
+					asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(x[i]), "+r"(y[i]) : "r"(a), "r"(b));
+					asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(sh), "r"(a));
+				}
 				else if (KIND == MB_IMAD_HI)
 					asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
 				else if (KIND == MB_MIX_LOP3_LDS)
@@ -87,7 +108,7 @@ __global__ void __launch_bounds__(1024) mb_kernel(u32* out, u32 iters, u32 a, u3
 	u32 acc = 0;
 #pragma unroll
 	for (int i = 0; i < MB_ILP; ++i)
-		acc ^= x[i] ^ y[i] ^ __float_as_uint(f[i]) ^ (u32)w[i] ^ (u32)(w[i] >> 32);
+		acc ^= x[i] ^ y[i] ^ __float_as_uint(f[i]) ^ (u32)__double2hiint(d[i]) ^ (u32)__double2loint(d[i]) ^ (u32)w[i] ^ (u32)(w[i] >> 32);
 	if (acc == 0x12345678u)
 		out[0] = acc;
 }
@@ -109,7 +130,7 @@ template <int KIND> static double mb_run(u32 iters, u32* d_out)
 	b2g_note_launch(), b2g_note_launch();
 	if (b2g_check_launch("mb_kernel") || ms <= 0)
 		return -1.0;
-	const double per_thread = (double)iters * MB_UNROLL * MB_ILP * (MB_IS_MIX(KIND) ? 2 : 1);
+	const double per_thread = (double)iters * MB_UNROLL * MB_ILP * (KIND == MB_MIX_IADDX_IMADW ? 3 : MB_IS_MIX(KIND) ? 2 : 1);
 	return per_thread * 1024.0 * grid / (ms * 1e-3);
 }
 
@@ -139,6 +160,10 @@ extern "C" double b2g_microbench(int kind, unsigned iters)
 	case MB_IMAD_HI: r = mb_run<MB_IMAD_HI>(iters, d_out); break;
 	case MB_MIX_LOP3_LDS: r = mb_run<MB_MIX_LOP3_LDS>(iters, d_out); break;
 	case MB_FFMA: r = mb_run<MB_FFMA>(iters, d_out); break;
+	case MB_DFMA: r = mb_run<MB_DFMA>(iters, d_out); break;
+	case MB_MIX_DFMA_IMADW: r = mb_run<MB_MIX_DFMA_IMADW>(iters, d_out); break;
+	case MB_MIX_IMAD_IMADW: r = mb_run<MB_MIX_IMAD_IMADW>(iters, d_out); break;
+	case MB_MIX_IADDX_IMADW: r = mb_run<MB_MIX_IADDX_IMADW>(iters, d_out); break;
 	default: break;
 	}
 	cudaFree(d_out);

@@ -1,0 +1,193 @@
+"""CPU check of the GF(p) / point LOGIC of bee2_b200/csrc/{gfp,ecp}.cuh for the three bign fields.
+
+The headers are `__host__ __device__`; on the host their PTX carry chains are replaced by the
+portable twins in gfp_asm.cuh, so the row order of the squaring, the lazy folds, the inversion
+chains, the exceptional cases of the additions and the signed-window recoding are exercised
+here against Python integers (no GPU, no oracle). The PTX forms of the same primitives are
+covered on the GPU by tests/test_gpu_bign.py.
+"""
+import os
+import random
+import shutil
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+# (p, b, q, yG) of bign-curve256v1 / 384v1 / 512v1 (bign_params.c:36-73, :78-125, :131-190); G = (0, yG), a = p - 3
+CURVES = {
+    8: (2**256 - 189,
+        0x77ce6c1515f3a8edd2c13aabe4d8fbbe4cf55069978b9253b22e7d6bd69c03f1,
+        0xffffffffffffffffffffffffffffffffd95c8ed60dfb4dfc7e5abf99263d6607,
+        0x6bf7fc3cfb16d69f5ce4c9a351d6835d78913966c408f6521e29cf1804516a93),
+    12: (2**384 - 317,
+         0x3c75dfe1959cef2033075aab655d34d2712748bb0ffbb196a6216af9e9712e3a14bde2f0f3cebd7cbca7fc236873bf64,
+         0xfffffffffffffffffffffffffffffffffffffffffffffffe6cccc40373af7bbb8046dae7a6a4ff0a3db7dc3ff30ca7b7,
+         0x5d438224a82e9e9e6330117e432dbf893a729a11dc86ffa00549e79e66b1d35584403e276b2a42f9ea5ecb31f733c451),
+    16: (2**512 - 569,
+         0x6cb45944933b8c43d88c5d6a60fd58895bc6a9eedd5d255117ce13e3daadb0882711dcb5c4245e952933008c87aca243ea8622273a49a27a09346998d6139c90,
+         0xffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffb2c0092c0198004ef26bebb02e2113f4361bcae59556df32dcffad490d068ef1,
+         0xa826ff7ae4037681b182e6f7a0d18fabb0ab41b3b361bce2d2edf81b00cccada6973dde20efa6fd2ff777395eee8226167aa83b9c94c0d04b792ae6fceefedbd),
+}
+
+
+@pytest.fixture(scope="module")
+def exe():
+    if not os.path.exists(NVCC):
+        pytest.skip("nvcc not available")
+    out = os.path.join(HERE, "_build", "host_gfp_test")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    src = os.path.join(HERE, "host_gfp_test.cu")
+    deps = [src] + [os.path.join(HERE, "..", "bee2_b200", "csrc", f) for f in ("gfp.cuh", "gfp_asm.cuh", "ecp.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.run([NVCC, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-diag-suppress", "20044",
+                        "-o", out, src], check=True)
+    return out
+
+
+def run(exe, lines):
+    r = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True)
+    out = r.stdout.strip().split("\n")
+    assert len(out) == len(lines)
+    return out
+
+
+def edge_values(n, rng):
+    p = CURVES[n][0]
+    full = 2 ** (32 * n)
+    c = full - p
+    vals = [0, 1, 2, c - 1, c, c + 1, p - 1, p, p + 1, full - 1, full - 2, full - c, 2 ** 32 - 1, 2 ** 32, full - 2 ** 32,
+            (2 ** 32 - 1) * (full // (2 ** 32 - 1) // 2), int("f" * (8 * n), 16) ^ 1, p - c, p // 2, p // 2 + 1]
+    vals += [rng.getrandbits(32 * n) for _ in range(40)]
+    # values with long runs of ones / zeros: carry and borrow ripples
+    for _ in range(20):
+        lo, hi = sorted(rng.sample(range(32 * n), 2))
+        vals.append((full - 1) ^ ((1 << hi) - (1 << lo)))
+        vals.append((1 << hi) - (1 << lo))
+    return [v % full for v in vals]
+
+
+@pytest.mark.parametrize("n", [8, 12, 16])
+def test_field_ops(exe, n):
+    rng = random.Random(1000 + n)
+    p = CURVES[n][0]
+    full = 2 ** (32 * n)
+    vals = edge_values(n, rng)
+    pairs = [(a, b) for a in vals[:24] for b in vals[:24]] + [(rng.choice(vals), rng.choice(vals)) for _ in range(400)]
+    lines, want = [], []
+    for a, b in pairs:
+        for op, f in (("mul", lambda x, y: x * y), ("add", lambda x, y: x + y), ("sub", lambda x, y: x - y)):
+            lines.append(f"{op} {n} {a:x} {b:x}")
+            want.append(("mod", f(a, b) % p))
+        lines.append(f"mulwide {n} {a:x} {b:x}")
+        want.append(("raw", a * b))
+    for a in vals:
+        lines.append(f"sqr {n} {a:x}"), want.append(("mod", a * a % p))
+        lines.append(f"sqrwide {n} {a:x}"), want.append(("raw", a * a))
+        for k in (1, 2, 3):
+            lines.append(f"shl{k} {n} {a:x}"), want.append(("mod", (a << k) % p))
+        lines.append(f"canon {n} {a:x}"), want.append(("raw", a % p if a < 2 * p else None))
+        lines.append(f"iszero {n} {a:x}"), want.append(("raw", 1 if a % p == 0 else 0))
+    for a in vals[:30]:
+        if a % p:
+            lines.append(f"inv {n} {a:x}"), want.append(("mod", pow(a, -1, p)))
+    got = run(exe, lines)
+    for line, g, (kind, w) in zip(lines, got, want):
+        v = int(g, 16)
+        if kind == "mod":
+            assert v < full and v % p == w, line      # weak residue of the right class
+        elif w is not None:
+            assert v == w, line
+
+
+# ---- affine reference arithmetic on y^2 = x^3 - 3x + b
+def ec_add(P, Q, p):
+    if P is None:
+        return Q
+    if Q is None:
+        return P
+    (x1, y1), (x2, y2) = P, Q
+    if x1 == x2:
+        if (y1 + y2) % p == 0:
+            return None
+        lam = (3 * x1 * x1 - 3) * pow(2 * y1, -1, p) % p
+    else:
+        lam = (y2 - y1) * pow(x2 - x1, -1, p) % p
+    x3 = (lam * lam - x1 - x2) % p
+    return x3, (lam * (x1 - x3) - y1) % p
+
+
+def ec_mul(k, P, p):
+    R = None
+    while k:
+        if k & 1:
+            R = ec_add(R, P, p)
+        P = ec_add(P, P, p)
+        k >>= 1
+    return R
+
+
+def to_affine(X, Y, Z, p):
+    if Z % p == 0:
+        return None
+    zi = pow(Z, -1, p)
+    return X * zi * zi % p, Y * zi * zi * zi % p
+
+
+def jac(P, p, rng):
+    """a random Jacobian representative of an affine point (None -> O with arbitrary X, Y)"""
+    if P is None:
+        return rng.randrange(1, p), rng.randrange(1, p), 0
+    z = rng.randrange(1, p)
+    return P[0] * z * z % p, P[1] * z * z * z % p, z
+
+
+@pytest.mark.parametrize("n", [8, 12, 16])
+def test_point_ops(exe, n):
+    rng = random.Random(2000 + n)
+    p, b, q, yG = CURVES[n]
+    G = (0, yG)
+    assert (yG * yG - b) % p == 0
+    pts = [None, G, ec_mul(2, G, p), ec_mul(3, G, p), ec_mul(q - 1, G, p), ec_mul(q - 2, G, p)]
+    pts += [ec_mul(rng.randrange(1, q), G, p) for _ in range(4)]
+    lines, want = [], []
+    for P in pts:
+        X, Y, Z = jac(P, p, rng)
+        lines.append(f"pdbl {n} {X:x} {Y:x} {Z:x}"), want.append(ec_add(P, P, p))
+        for Q in pts:
+            X2, Y2, Z2 = jac(Q, p, rng)
+            lines.append(f"padd {n} {X:x} {Y:x} {Z:x} {X2:x} {Y2:x} {Z2:x}"), want.append(ec_add(P, Q, p))
+            if Q is not None:
+                lines.append(f"pmadd {n} {X:x} {Y:x} {Z:x} {Q[0]:x} {Q[1]:x}"), want.append(ec_add(P, Q, p))
+    got = run(exe, lines)
+    for line, g, w in zip(lines, got, want):
+        X, Y, Z = (int(h, 16) for h in g.split())
+        assert to_affine(X, Y, Z, p) == w, line[:40]
+
+
+@pytest.mark.parametrize("n", [8, 12, 16])
+def test_scalar_mul(exe, n):
+    rng = random.Random(3000 + n)
+    p, b, q, yG = CURVES[n]
+    G = (0, yG)
+    bits = 32 * n
+    Q = ec_mul(rng.randrange(1, q), G, p)
+    cases = []
+    for nbits in (bits, bits // 2 + 1, 8, 16, 40):
+        ks = [0, 1, 2, 15, 16, 17, 31, 32, 33, (1 << nbits) - 1, (1 << nbits) - 2, 1 << (nbits - 1),
+              int("10" * (nbits // 2), 2), int("01" * (nbits // 2), 2), int("10000" * (nbits // 5 + 1), 2) % (1 << nbits),
+              int("10001" * (nbits // 5 + 1), 2) % (1 << nbits), int("01111" * (nbits // 5 + 1), 2) % (1 << nbits)]
+        ks += [rng.getrandbits(nbits) for _ in range(6)]
+        if nbits == bits:
+            ks += [q, q - 1, q + 1]
+        cases += [(nbits, k % (1 << nbits), P) for k in ks for P in ((G, Q) if nbits >= bits // 2 else (Q,))]
+    lines = [f"pmul {n} {nbits} {k:x} {P[0]:x} {P[1]:x}" for nbits, k, P in cases]
+    got = run(exe, lines)
+    for (nbits, k, P), g in zip(cases, got):
+        w = ec_mul(k, P, p)
+        if w is None:
+            assert g == "inf", (nbits, hex(k))
+        else:
+            assert g != "inf" and tuple(int(h, 16) for h in g.split()) == w, (nbits, hex(k))
