@@ -25,7 +25,7 @@ __all__ = [
     "bignPubkeyCalc", "bignPubkeyCalcBatch", "ecMulABatch", "ecAddMulABatch", "OID_BELT_HASH_DER",
     "bashHashBatch_dev", "bashFBatch_dev", "beltCTR_dev", "beltECB_dev", "beltECBEncrBatch_dev",
     "beltHashBatch_dev", "bignVerifyBatch_dev", "bignSign2Batch_dev", "bignPubkeyCalcBatch_dev",
-    "ecMulABatch_dev", "pinned_empty",
+    "ecMulABatch_dev", "bignVerifyBatchL_dev", "pinned_empty", "BIGN_CURVES",
 ]
 
 ERR_OK = 0
@@ -45,6 +45,10 @@ ERR_B2G_CUDA = 9002
 # DER of OID 1.2.112.0.2.0.34.101.31.81 (belt-hash), the hash OID used by the reference's
 # bign tests (test/crypto/bign_test.c:296-300) and by bign128 (bign128.c:151-153)
 OID_BELT_HASH_DER = bytes.fromhex("06092A7000020022651F51")
+
+
+# names of the standard parameter blocks by level l (bign_params.c:197-236)
+BIGN_CURVES = {128: "1.2.112.0.2.0.34.101.45.3.1", 192: "1.2.112.0.2.0.34.101.45.3.2", 256: "1.2.112.0.2.0.34.101.45.3.3"}
 
 
 class Bee2Error(RuntimeError):
@@ -127,6 +131,12 @@ def _declare(L: C.CDLL) -> None:
         "b2g_ecMulABatch_dev": (u32, [vp, vp, vp, vp, sz, sz, vp]),
         "ecAddMulABatch": (u32, [vp, vp, vp, vp, sz, vp, sz]),
         "b2g_ecAddMulABatch_dev": (u32, [vp, vp, vp, vp, sz, vp, sz, vp]),
+        "ecMulABatchL": (u32, [sz, vp, vp, vp, vp, sz, sz]), "ecAddMulABatchL": (u32, [sz, vp, vp, vp, vp, sz, vp, sz]),
+        "b2g_bignVerifyBatchL_dev": (u32, [sz, vp, vp, sz, vp, vp, vp, sz, vp]),
+        "b2g_bignSign2BatchL_t_dev": (u32, [sz, vp, vp, vp, sz, vp, vp, sz, vp, sz, vp]),
+        "b2g_bignPubkeyCalcBatchL_dev": (u32, [sz, vp, vp, vp, sz, vp]),
+        "b2g_ecMulABatchL_dev": (u32, [sz, vp, vp, vp, vp, sz, sz, vp]),
+        "b2g_ecAddMulABatchL_dev": (u32, [sz, vp, vp, vp, vp, sz, vp, sz, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -470,7 +480,7 @@ def bignVerify(params: BignParams, oid_der: bytes, hash_: bytes, sig: bytes, pub
 
 def bignVerifyBatch(params: BignParams, oid_der: bytes, hashes: np.ndarray, sigs: np.ndarray,
                     pubkeys: np.ndarray) -> np.ndarray:
-    count = hashes.size // 32
+    count = hashes.size // (params.l // 4)
     status = np.full(count, 0xFFFFFFFF, dtype=np.uint32)
     ko = _buf(oid_der)
     _chk("bignVerifyBatch", lib().bignVerifyBatch(status.ctypes.data, C.addressof(params), ko[1], ko[2],
@@ -480,16 +490,16 @@ def bignVerifyBatch(params: BignParams, oid_der: bytes, hashes: np.ndarray, sigs
 
 def bignSign2(params: BignParams, oid_der: bytes, hash_: bytes, privkey: bytes, t: Optional[bytes] = None) -> bytes:
     ks = [_buf(x) for x in (oid_der, hash_, privkey, t)]
-    sig = _out(48)
+    sig = _out(3 * params.l // 8)
     _chk("bignSign2", lib().bignSign2(sig.ctypes.data, C.addressof(params), ks[0][1], ks[0][2], ks[1][1], ks[2][1],
                                       ks[3][1], ks[3][2]))
     return sig.tobytes()
 
 
 def bignSign2Batch(params: BignParams, oid_der: bytes, hashes: np.ndarray, privkeys: np.ndarray):
-    count = hashes.size // 32
+    count = hashes.size // (params.l // 4)
     status = np.full(count, 0xFFFFFFFF, dtype=np.uint32)
-    sigs = np.zeros((count, 48), dtype=np.uint8)
+    sigs = np.zeros((count, 3 * params.l // 8), dtype=np.uint8)
     ko = _buf(oid_der)
     _chk("bignSign2Batch", lib().bignSign2Batch(status.ctypes.data, sigs.ctypes.data, C.addressof(params), ko[1], ko[2],
                                                 hashes.ctypes.data, privkeys.ctypes.data, count))
@@ -498,37 +508,37 @@ def bignSign2Batch(params: BignParams, oid_der: bytes, hashes: np.ndarray, privk
 
 def bignPubkeyCalc(params: BignParams, privkey: bytes) -> bytes:
     k = _buf(privkey)
-    out = _out(64)
+    out = _out(params.l // 2)
     _chk("bignPubkeyCalc", lib().bignPubkeyCalc(out.ctypes.data, C.addressof(params), k[1]))
     return out.tobytes()
 
 
 def bignPubkeyCalcBatch(params: BignParams, privkeys: np.ndarray):
-    count = privkeys.size // 32
+    count = privkeys.size // (params.l // 4)
     status = np.full(count, 0xFFFFFFFF, dtype=np.uint32)
-    pub = np.zeros((count, 64), dtype=np.uint8)
+    pub = np.zeros((count, params.l // 2), dtype=np.uint8)
     _chk("bignPubkeyCalcBatch", lib().bignPubkeyCalcBatch(status.ctypes.data, pub.ctypes.data, C.addressof(params),
                                                           privkeys.ctypes.data, count))
     return status, pub
 
 
-def ecMulABatch(points: np.ndarray, scalars: np.ndarray):
-    """points [count,64], scalars [count,d_len] -> (results [count,64], ok [count])"""
+def ecMulABatch(points: np.ndarray, scalars: np.ndarray, l: int = 128):
+    """points [count,l/2], scalars [count,d_len] -> (results [count,l/2], ok [count]) on the standard curve of level l"""
     count, d_len = scalars.shape
-    out = np.zeros((count, 64), dtype=np.uint8)
+    out = np.zeros((count, l // 2), dtype=np.uint8)
     ok = np.zeros(count, dtype=np.int32)
-    _chk("ecMulABatch", lib().ecMulABatch(out.ctypes.data, ok.ctypes.data, points.ctypes.data, scalars.ctypes.data,
-                                          d_len, count))
+    _chk("ecMulABatchL", lib().ecMulABatchL(l, out.ctypes.data, ok.ctypes.data, points.ctypes.data, scalars.ctypes.data,
+                                            d_len, count))
     return out, ok
 
 
-def ecAddMulABatch(points: np.ndarray, scalars: np.ndarray, kbase: np.ndarray):
-    """d_i * A_i + k_i * G: points [count,64], scalars [count,d_len], kbase [count,32]"""
+def ecAddMulABatch(points: np.ndarray, scalars: np.ndarray, kbase: np.ndarray, l: int = 128):
+    """d_i * A_i + k_i * G: points [count,l/2], scalars [count,d_len], kbase [count,l/4]"""
     count, d_len = scalars.shape
-    out = np.zeros((count, 64), dtype=np.uint8)
+    out = np.zeros((count, l // 2), dtype=np.uint8)
     ok = np.zeros(count, dtype=np.int32)
-    _chk("ecAddMulABatch", lib().ecAddMulABatch(out.ctypes.data, ok.ctypes.data, points.ctypes.data,
-                                                scalars.ctypes.data, d_len, kbase.ctypes.data, count))
+    _chk("ecAddMulABatchL", lib().ecAddMulABatchL(l, out.ctypes.data, ok.ctypes.data, points.ctypes.data,
+                                                  scalars.ctypes.data, d_len, kbase.ctypes.data, count))
     return out, ok
 
 
@@ -557,6 +567,13 @@ def beltECBEncrBatch_dev(d_blocks: int, d_keys32: int, count: int, stream: int =
 
 def beltHashBatch_dev(d_hashes: int, d_msgs: int, msg_len: int, stride: int, count: int, stream: int = 0) -> None:
     _chk("b2g_beltHashBatch_dev", lib().b2g_beltHashBatch_dev(d_hashes, d_msgs, msg_len, stride, count, stream))
+
+
+def bignVerifyBatchL_dev(l: int, d_status: int, oid_der: bytes, d_hashes: int, d_sigs: int, d_pubkeys: int, count: int,
+                         stream: int = 0) -> None:
+    ko = _buf(oid_der)
+    _chk("b2g_bignVerifyBatchL_dev", lib().b2g_bignVerifyBatchL_dev(l, d_status, ko[1], ko[2], d_hashes, d_sigs, d_pubkeys,
+                                                                  count, stream))
 
 
 def bignVerifyBatch_dev(d_status: int, oid_der: bytes, d_hashes: int, d_sigs: int, d_pubkeys: int, count: int,

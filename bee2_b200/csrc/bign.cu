@@ -451,19 +451,7 @@ bign_sign2_kernel(u32* __restrict__ status, u8* __restrict__ sigs, const u8* __r
 	u32 s1[N];
 	modq_reduce<N>(s1, prod, N + H2 + 1);
 	modq_sub<N>(s1, k, s1);
-	{
-		// H may be >= q here (zzSubMod takes it as is, :237-238): reduce it first so that the
-		// difference stays in range — (a - (H mod q)) mod q == (a - H) mod q
-		u32 Hq[N];
-		for (int j = 0; j < N; ++j) Hq[j] = H[j];
-		if (geq_q<N>(H))
-		{
-			u32 q[N];
-			load_q<N>(q);
-			(void)sub_n<N>(Hq, H, q);
-		}
-		modq_sub<N>(s1, s1, Hq);
-	}
+	modq_sub<N>(s1, s1, H);   // H as is, not reduced first (zzSubMod, :237-238)
 	u8* o = sigs + (NO + NO / 2) * i;
 	for (int j = 0; j < NO / 2; ++j) o[j] = (u8)(hv[j >> 2] >> (8 * (j & 3)));
 	for (int j = 0; j < NO; ++j) o[NO / 2 + j] = (u8)(s1[j >> 2] >> (8 * (j & 3)));

@@ -10,8 +10,8 @@
 
 #define CU(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { code = b2g_cuda_fail(e_, what); goto done; } } while (0)
 
-/* bign-curve256v1 = level l = 128, table B.1 of STB 34.101.45 (bign_params.c:33-73) */
-static const char curve256v1_name[] = "1.2.112.0.2.0.34.101.45.3.1";
+/* The three standard curves, tables B.1-B.3 of STB 34.101.45 (bign_params.c:33-190):
+   bign-curve256v1 / 384v1 / 512v1 = levels l = 128 / 192 / 256; p = 2^(2l) - c, a = p - 3 */
 static const octet curve256v1_b[32] = {
 	0xF1, 0x03, 0x9C, 0xD6, 0x6B, 0x7D, 0x2E, 0xB2, 0x53, 0x92, 0x8B, 0x97, 0x69, 0x50, 0xF5, 0x4C,
 	0xBE, 0xFB, 0xD8, 0xE4, 0xAB, 0x3A, 0xC1, 0xD2, 0xED, 0xA8, 0xF3, 0x15, 0x15, 0x6C, 0xCE, 0x77};
@@ -22,22 +22,75 @@ static const octet curve256v1_yG[32] = {
 	0x93, 0x6A, 0x51, 0x04, 0x18, 0xCF, 0x29, 0x1E, 0x52, 0xF6, 0x08, 0xC4, 0x66, 0x39, 0x91, 0x78,
 	0x5D, 0x83, 0xD6, 0x51, 0xA3, 0xC9, 0xE4, 0x5C, 0x9F, 0xD6, 0x16, 0xFB, 0x3C, 0xFC, 0xF7, 0x6B};
 static const octet curve256v1_seed[8] = {0x5E, 0x38, 0x01, 0x00, 0x00, 0x00, 0x00, 0x00};
+static const octet curve384v1_b[48] = {
+	0x64, 0xBF, 0x73, 0x68, 0x23, 0xFC, 0xA7, 0xBC, 0x7C, 0xBD, 0xCE, 0xF3, 0xF0, 0xE2, 0xBD, 0x14,
+	0x3A, 0x2E, 0x71, 0xE9, 0xF9, 0x6A, 0x21, 0xA6, 0x96, 0xB1, 0xFB, 0x0F, 0xBB, 0x48, 0x27, 0x71,
+	0xD2, 0x34, 0x5D, 0x65, 0xAB, 0x5A, 0x07, 0x33, 0x20, 0xEF, 0x9C, 0x95, 0xE1, 0xDF, 0x75, 0x3C};
+static const octet curve384v1_q[48] = {
+	0xB7, 0xA7, 0x0C, 0xF3, 0x3F, 0xDC, 0xB7, 0x3D, 0x0A, 0xFF, 0xA4, 0xA6, 0xE7, 0xDA, 0x46, 0x80,
+	0xBB, 0x7B, 0xAF, 0x73, 0x03, 0xC4, 0xCC, 0x6C, 0xFE, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF,
+	0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF};
+static const octet curve384v1_yG[48] = {
+	0x51, 0xC4, 0x33, 0xF7, 0x31, 0xCB, 0x5E, 0xEA, 0xF9, 0x42, 0x2A, 0x6B, 0x27, 0x3E, 0x40, 0x84,
+	0x55, 0xD3, 0xB1, 0x66, 0x9E, 0xE7, 0x49, 0x05, 0xA0, 0xFF, 0x86, 0xDC, 0x11, 0x9A, 0x72, 0x3A,
+	0x89, 0xBF, 0x2D, 0x43, 0x7E, 0x11, 0x30, 0x63, 0x9E, 0x9E, 0x2E, 0xA8, 0x24, 0x82, 0x43, 0x5D};
+static const octet curve384v1_seed[8] = {0x23, 0xAF, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00};
+static const octet curve512v1_b[64] = {
+	0x90, 0x9C, 0x13, 0xD6, 0x98, 0x69, 0x34, 0x09, 0x7A, 0xA2, 0x49, 0x3A, 0x27, 0x22, 0x86, 0xEA,
+	0x43, 0xA2, 0xAC, 0x87, 0x8C, 0x00, 0x33, 0x29, 0x95, 0x5E, 0x24, 0xC4, 0xB5, 0xDC, 0x11, 0x27,
+	0x88, 0xB0, 0xAD, 0xDA, 0xE3, 0x13, 0xCE, 0x17, 0x51, 0x25, 0x5D, 0xDD, 0xEE, 0xA9, 0xC6, 0x5B,
+	0x89, 0x58, 0xFD, 0x60, 0x6A, 0x5D, 0x8C, 0xD8, 0x43, 0x8C, 0x3B, 0x93, 0x44, 0x59, 0xB4, 0x6C};
+static const octet curve512v1_q[64] = {
+	0xF1, 0x8E, 0x06, 0x0D, 0x49, 0xAD, 0xFF, 0xDC, 0x32, 0xDF, 0x56, 0x95, 0xE5, 0xCA, 0x1B, 0x36,
+	0xF4, 0x13, 0x21, 0x2E, 0xB0, 0xEB, 0x6B, 0xF2, 0x4E, 0x00, 0x98, 0x01, 0x2C, 0x09, 0xC0, 0xB2,
+	0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF,
+	0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF};
+static const octet curve512v1_yG[64] = {
+	0xBD, 0xED, 0xEF, 0xCE, 0x6F, 0xAE, 0x92, 0xB7, 0x04, 0x0D, 0x4C, 0xC9, 0xB9, 0x83, 0xAA, 0x67,
+	0x61, 0x22, 0xE8, 0xEE, 0x95, 0x73, 0x77, 0xFF, 0xD2, 0x6F, 0xFA, 0x0E, 0xE2, 0xDD, 0x73, 0x69,
+	0xDA, 0xCA, 0xCC, 0x00, 0x1B, 0xF8, 0xED, 0xD2, 0xE2, 0xBC, 0x61, 0xB3, 0xB3, 0x41, 0xAB, 0xB0,
+	0xAB, 0x8F, 0xD1, 0xA0, 0xF7, 0xE6, 0x82, 0xB1, 0x81, 0x76, 0x03, 0xE4, 0x7A, 0xFF, 0x26, 0xA8};
+static const octet curve512v1_seed[8] = {0xAE, 0x17, 0x02, 0x00, 0x00, 0x00, 0x00, 0x00};
+
+typedef struct
+{
+	const char* name;
+	size_t l;
+	octet p0, p1;          /* the two low octets of p (all others are 0xFF) */
+	const octet *b, *q, *yG, *seed;
+} std_curve;
+static const std_curve std_curves[3] = {
+	{"1.2.112.0.2.0.34.101.45.3.1", 128, 0x43, 0xFF, curve256v1_b, curve256v1_q, curve256v1_yG, curve256v1_seed},
+	{"1.2.112.0.2.0.34.101.45.3.2", 192, 0xC3, 0xFE, curve384v1_b, curve384v1_q, curve384v1_yG, curve384v1_seed},
+	{"1.2.112.0.2.0.34.101.45.3.3", 256, 0xC7, 0xFD, curve512v1_b, curve512v1_q, curve512v1_yG, curve512v1_seed},
+};
+
+static void std_fill(bign_params* params, const std_curve* c)
+{
+	const size_t no = c->l / 4;
+	memset(params, 0, sizeof *params);
+	params->l = c->l;
+	memset(params->p, 0xFF, no), params->p[0] = c->p0, params->p[1] = c->p1;
+	memset(params->a, 0xFF, no), params->a[0] = (octet)(c->p0 - 3), params->a[1] = c->p1;
+	memcpy(params->b, c->b, no);
+	memcpy(params->q, c->q, no);
+	memcpy(params->yG, c->yG, no);
+	memcpy(params->seed, c->seed, 8);
+}
 
 err_t bignParamsStd(bign_params* params, const char* name)
 {
+	size_t i;
 	if (!params)
 		return ERR_BAD_INPUT;
 	memset(params, 0, sizeof *params);
-	if (!name || strcmp(name, curve256v1_name) != 0)
-		return ERR_FILE_NOT_FOUND;
-	params->l = 128;
-	memset(params->p, 0xFF, 32), params->p[0] = 0x43;   /* p = 2^256 - 189 */
-	memset(params->a, 0xFF, 32), params->a[0] = 0x40;   /* a = p - 3 */
-	memcpy(params->b, curve256v1_b, 32);
-	memcpy(params->q, curve256v1_q, 32);
-	memcpy(params->yG, curve256v1_yG, 32);
-	memcpy(params->seed, curve256v1_seed, 8);
-	return ERR_OK;
+	for (i = 0; name && i < 3; ++i)
+		if (strcmp(name, std_curves[i].name) == 0)
+		{
+			std_fill(params, &std_curves[i]);
+			return ERR_OK;
+		}
+	return ERR_FILE_NOT_FOUND;
 }
 
 static int is_zero(const octet* p, size_t n)
@@ -69,11 +122,18 @@ static err_t params_check(const bign_params* params)
 		return ERR_NOT_IMPLEMENTED;
 	if (params->l != 128 && params->l != 192 && params->l != 256)
 		return ERR_BAD_PARAMS;
-	/* GPU path: bign-curve256v1 only (seed is not used by sign/verify) */
-	bignParamsStd(&std, curve256v1_name);
-	if (params->l != 128 || memcmp(params->p, std.p, 64) || memcmp(params->a, std.a, 64) ||
-		memcmp(params->b, std.b, 64) || memcmp(params->q, std.q, 64) || memcmp(params->yG, std.yG, 64))
-		return ERR_NOT_IMPLEMENTED;
+	/* GPU path: the three standard curves (seed is not used by sign/verify) */
+	{
+		size_t i;
+		for (i = 0; i < 3; ++i)
+			if (params->l == std_curves[i].l)
+			{
+				std_fill(&std, &std_curves[i]);
+				if (memcmp(params->p, std.p, 64) || memcmp(params->a, std.a, 64) || memcmp(params->b, std.b, 64) ||
+					memcmp(params->q, std.q, 64) || memcmp(params->yG, std.yG, 64))
+					return ERR_NOT_IMPLEMENTED;
+			}
+	}
 	return ERR_OK;
 }
 
@@ -134,8 +194,10 @@ err_t bignVerifyBatch(err_t* status, const bign_params* params, const octet oid_
 	err_t code;
 	b2g_slot *s0 = b2g_slot_get(0), *s1 = b2g_slot_get(1);
 	void *d_h, *d_s, *d_p, *d_st;
+	size_t no;
 	if ((code = params_check(params)))
 		return code;
+	no = params->l / 4;
 	if (count && (!status || !hashes || !sigs || !pubkeys))
 		return ERR_BAD_INPUT;
 	if (!oid_der_valid(oid_der, oid_len))
@@ -154,12 +216,12 @@ err_t bignVerifyBatch(err_t* status, const bign_params* params, const octet oid_
 		{
 			const size_t n = count - off < chunk ? count - off : chunk;
 			b2g_slot* sl = b2g_slot_get((int)c);
-			if ((code = stage_in(sl, 0, hashes + 32 * off, 32 * n, &d_h)) ||
-				(code = stage_in(sl, 1, sigs + 48 * off, 48 * n, &d_s)) ||
-				(code = stage_in(sl, 2, pubkeys + 64 * off, 64 * n, &d_p)) ||
+			if ((code = stage_in(sl, 0, hashes + no * off, no * n, &d_h)) ||
+				(code = stage_in(sl, 1, sigs + (no + no / 2) * off, (no + no / 2) * n, &d_s)) ||
+				(code = stage_in(sl, 2, pubkeys + 2 * no * off, 2 * no * n, &d_p)) ||
 				(code = b2g_slot_buf(sl, 3, 4 * n, &d_st)))
 				goto done;
-			if ((code = b2g_bignVerifyBatch_dev(d_st, oid_der, oid_len, d_h, d_s, d_p, n, sl->stream)))
+			if ((code = b2g_bignVerifyBatchL_dev(params->l, d_st, oid_der, oid_len, d_h, d_s, d_p, n, sl->stream)))
 				goto done;
 			CU(cudaMemcpyAsync(status + off, d_st, 4 * n, cudaMemcpyDeviceToHost, sl->stream), "D2H(bign status)");
 		}
@@ -193,8 +255,10 @@ static err_t sign2_batch(err_t* status, octet* sigs, const bign_params* params, 
 	err_t code;
 	b2g_slot *s0, *s1;
 	void *d_h, *d_k, *d_sig, *d_st;
+	size_t no, so;
 	if ((code = params_check(params)))
 		return code;
+	no = params->l / 4, so = no + no / 2;
 	if (count && (!status || !sigs || !hashes || !privkeys))
 		return ERR_BAD_INPUT;
 	if (!oid_der_valid(oid_der, oid_len))
@@ -207,10 +271,10 @@ static err_t sign2_batch(err_t* status, octet* sigs, const bign_params* params, 
 		return ERR_OK;
 	b2g_lock();
 	s0 = b2g_slot_get(0), s1 = b2g_slot_get(1);
-	if ((code = stage_in(s0, 0, hashes, 32 * count, &d_h)) || (code = stage_in(s0, 1, privkeys, 32 * count, &d_k)) ||
-		(code = b2g_slot_buf(s0, 2, 48 * count, &d_sig)) || (code = b2g_slot_buf(s1, 0, 4 * count, &d_st)))
+	if ((code = stage_in(s0, 0, hashes, no * count, &d_h)) || (code = stage_in(s0, 1, privkeys, no * count, &d_k)) ||
+		(code = b2g_slot_buf(s0, 2, so * count, &d_sig)) || (code = b2g_slot_buf(s1, 0, 4 * count, &d_st)))
 		goto done;
-	if ((code = b2g_bignSign2Batch_t_dev(d_st, d_sig, oid_der, oid_len, d_h, d_k, count, t, t_len, s0->stream)))
+	if ((code = b2g_bignSign2BatchL_t_dev(params->l, d_st, d_sig, oid_der, oid_len, d_h, d_k, count, t, t_len, s0->stream)))
 		goto done;
 	CU(cudaMemcpyAsync(status, d_st, 4 * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(bign status)");
 	CU(cudaStreamSynchronize(s0->stream), "sync(bign sign2)");
@@ -220,14 +284,14 @@ static err_t sign2_batch(err_t* status, octet* sigs, const bign_params* params, 
 		for (i = 0; i < count; ++i)
 			all_ok &= status[i] == ERR_OK;
 		if (all_ok)
-			CU(cudaMemcpy(sigs, d_sig, 48 * count, cudaMemcpyDeviceToHost), "D2H(bign sigs)");
+			CU(cudaMemcpy(sigs, d_sig, so * count, cudaMemcpyDeviceToHost), "D2H(bign sigs)");
 		else
 			for (i = 0; i < count; ++i)
 				if (status[i] == ERR_OK)
-					CU(cudaMemcpy(sigs + 48 * i, (octet*)d_sig + 48 * i, 48, cudaMemcpyDeviceToHost), "D2H(bign sig)");
+					CU(cudaMemcpy(sigs + so * i, (octet*)d_sig + so * i, so, cudaMemcpyDeviceToHost), "D2H(bign sig)");
 	}
 	/* the private keys were staged on the device: wipe them */
-	CU(cudaMemsetAsync(d_k, 0, 32 * count, s0->stream), "memset(bign keys)");
+	CU(cudaMemsetAsync(d_k, 0, no * count, s0->stream), "memset(bign keys)");
 	CU(cudaStreamSynchronize(s0->stream), "sync(bign sign2)");
 done:
 	if (code)
@@ -261,8 +325,10 @@ err_t bignPubkeyCalcBatch(err_t* status, octet* pubkeys, const bign_params* para
 	err_t code;
 	b2g_slot *s0, *s1;
 	void *d_k, *d_p, *d_st;
+	size_t no;
 	if ((code = params_check(params)))
 		return code;
+	no = params->l / 4;
 	if (count && (!status || !pubkeys || !privkeys))
 		return ERR_BAD_INPUT;
 	if ((code = b2g_ensure_device()))
@@ -271,15 +337,15 @@ err_t bignPubkeyCalcBatch(err_t* status, octet* pubkeys, const bign_params* para
 		return ERR_OK;
 	b2g_lock();
 	s0 = b2g_slot_get(0), s1 = b2g_slot_get(1);
-	if ((code = stage_in(s0, 0, privkeys, 32 * count, &d_k)) || (code = b2g_slot_buf(s0, 1, 64 * count, &d_p)) ||
+	if ((code = stage_in(s0, 0, privkeys, no * count, &d_k)) || (code = b2g_slot_buf(s0, 1, 2 * no * count, &d_p)) ||
 		(code = b2g_slot_buf(s1, 0, 4 * count, &d_st)))
 		goto done;
-	CU(cudaMemsetAsync(d_p, 0, 64 * count, s0->stream), "memset(bign pubkeys)");
-	if ((code = b2g_bignPubkeyCalcBatch_dev(d_st, d_p, d_k, count, s0->stream)))
+	CU(cudaMemsetAsync(d_p, 0, 2 * no * count, s0->stream), "memset(bign pubkeys)");
+	if ((code = b2g_bignPubkeyCalcBatchL_dev(params->l, d_st, d_p, d_k, count, s0->stream)))
 		goto done;
 	CU(cudaMemcpyAsync(status, d_st, 4 * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(bign status)");
-	CU(cudaMemcpyAsync(pubkeys, d_p, 64 * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(bign pubkeys)");
-	CU(cudaMemsetAsync(d_k, 0, 32 * count, s0->stream), "memset(bign keys)");
+	CU(cudaMemcpyAsync(pubkeys, d_p, 2 * no * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(bign pubkeys)");
+	CU(cudaMemsetAsync(d_k, 0, no * count, s0->stream), "memset(bign keys)");
 	CU(cudaStreamSynchronize(s0->stream), "sync(bign pubkey)");
 done:
 	if (code)
@@ -291,7 +357,7 @@ done:
 err_t bignPubkeyCalc(octet pubkey[], const bign_params* params, const octet privkey[])
 {
 	err_t st = ERR_BAD_INPUT, code;
-	octet out[64];
+	octet out[128];
 	if ((code = params_check(params)))
 		return code;
 	if (!pubkey || !privkey)
@@ -299,18 +365,21 @@ err_t bignPubkeyCalc(octet pubkey[], const bign_params* params, const octet priv
 	if ((code = bignPubkeyCalcBatch(&st, out, params, privkey, 1)))
 		return code;
 	if (st == ERR_OK)
-		memcpy(pubkey, out, 64);
+		memcpy(pubkey, out, params->l / 2);
 	return st;
 }
 
-err_t ecMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d_len, size_t count)
+err_t ecMulABatchL(size_t l, octet* b, int* ok, const octet* a, const octet* d, size_t d_len, size_t count)
 {
 	err_t code;
 	b2g_slot *s0, *s1;
 	void *d_a, *d_d, *d_b, *d_ok;
+	const size_t po = l / 2;   /* octets per affine point */
+	if (l != 128 && l != 192 && l != 256)
+		return ERR_NOT_IMPLEMENTED;
 	if (count && (!b || !ok || !a || !d))
 		return ERR_BAD_INPUT;
-	if (d_len == 0 || d_len > 32)
+	if (d_len == 0 || d_len > l / 4)
 		return ERR_BAD_INPUT;
 	if ((code = b2g_ensure_device()))
 		return code;
@@ -318,13 +387,13 @@ err_t ecMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d_le
 		return ERR_OK;
 	b2g_lock();
 	s0 = b2g_slot_get(0), s1 = b2g_slot_get(1);
-	if ((code = stage_in(s0, 0, a, 64 * count, &d_a)) || (code = stage_in(s0, 1, d, d_len * count, &d_d)) ||
-		(code = b2g_slot_buf(s0, 2, 64 * count, &d_b)) || (code = b2g_slot_buf(s1, 0, 4 * count, &d_ok)))
+	if ((code = stage_in(s0, 0, a, po * count, &d_a)) || (code = stage_in(s0, 1, d, d_len * count, &d_d)) ||
+		(code = b2g_slot_buf(s0, 2, po * count, &d_b)) || (code = b2g_slot_buf(s1, 0, 4 * count, &d_ok)))
 		goto done;
-	CU(cudaMemsetAsync(d_b, 0, 64 * count, s0->stream), "memset(ecMulA out)");
-	if ((code = b2g_ecMulABatch_dev(d_b, d_ok, d_a, d_d, d_len, count, s0->stream)))
+	CU(cudaMemsetAsync(d_b, 0, po * count, s0->stream), "memset(ecMulA out)");
+	if ((code = b2g_ecMulABatchL_dev(l, d_b, d_ok, d_a, d_d, d_len, count, s0->stream)))
 		goto done;
-	CU(cudaMemcpyAsync(b, d_b, 64 * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(ecMulA)");
+	CU(cudaMemcpyAsync(b, d_b, po * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(ecMulA)");
 	CU(cudaMemcpyAsync(ok, d_ok, 4 * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(ecMulA ok)");
 	CU(cudaStreamSynchronize(s0->stream), "sync(ecMulA)");
 done:
@@ -334,16 +403,24 @@ done:
 	return code;
 }
 
+err_t ecMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d_len, size_t count)
+{
+	return ecMulABatchL(128, b, ok, a, d, d_len, count);
+}
+
 /* b_i = d_i * a_i + k_i * G (ecAddMulA with the base point as second term, ec.c:1183-1273) */
-err_t ecAddMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d_len, const octet* k,
+err_t ecAddMulABatchL(size_t l, octet* b, int* ok, const octet* a, const octet* d, size_t d_len, const octet* k,
 	size_t count)
 {
 	err_t code;
 	b2g_slot *s0, *s1;
 	void *d_a, *d_d, *d_k, *d_b, *d_ok;
+	const size_t po = l / 2;
+	if (l != 128 && l != 192 && l != 256)
+		return ERR_NOT_IMPLEMENTED;
 	if (count && (!b || !ok || !a || !d || !k))
 		return ERR_BAD_INPUT;
-	if (d_len == 0 || d_len > 32)
+	if (d_len == 0 || d_len > l / 4)
 		return ERR_BAD_INPUT;
 	if ((code = b2g_ensure_device()))
 		return code;
@@ -351,14 +428,14 @@ err_t ecAddMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d
 		return ERR_OK;
 	b2g_lock();
 	s0 = b2g_slot_get(0), s1 = b2g_slot_get(1);
-	if ((code = stage_in(s0, 0, a, 64 * count, &d_a)) || (code = stage_in(s0, 1, d, d_len * count, &d_d)) ||
-		(code = stage_in(s0, 2, k, 32 * count, &d_k)) || (code = b2g_slot_buf(s1, 0, 64 * count, &d_b)) ||
+	if ((code = stage_in(s0, 0, a, po * count, &d_a)) || (code = stage_in(s0, 1, d, d_len * count, &d_d)) ||
+		(code = stage_in(s0, 2, k, po / 2 * count, &d_k)) || (code = b2g_slot_buf(s1, 0, po * count, &d_b)) ||
 		(code = b2g_slot_buf(s1, 1, 4 * count, &d_ok)))
 		goto done;
-	CU(cudaMemsetAsync(d_b, 0, 64 * count, s0->stream), "memset(ecAddMulA out)");
-	if ((code = b2g_ecAddMulABatch_dev(d_b, d_ok, d_a, d_d, d_len, d_k, count, s0->stream)))
+	CU(cudaMemsetAsync(d_b, 0, po * count, s0->stream), "memset(ecAddMulA out)");
+	if ((code = b2g_ecAddMulABatchL_dev(l, d_b, d_ok, d_a, d_d, d_len, d_k, count, s0->stream)))
 		goto done;
-	CU(cudaMemcpyAsync(b, d_b, 64 * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(ecAddMulA)");
+	CU(cudaMemcpyAsync(b, d_b, po * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(ecAddMulA)");
 	CU(cudaMemcpyAsync(ok, d_ok, 4 * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(ecAddMulA ok)");
 	CU(cudaStreamSynchronize(s0->stream), "sync(ecAddMulA)");
 done:
@@ -366,4 +443,10 @@ done:
 		cudaStreamSynchronize(s0->stream);
 	b2g_unlock();
 	return code;
+}
+
+err_t ecAddMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d_len, const octet* k,
+	size_t count)
+{
+	return ecAddMulABatchL(128, b, ok, a, d, d_len, k, count);
 }

@@ -217,18 +217,21 @@ typedef struct
 	octet seed[8];
 } bign_params;
 
-/* drop-in: bign.h (bign_params.c:197-236); only "1.2.112.0.2.0.34.101.45.3.1"
-   (bign-curve256v1) is known to this engine, other names -> ERR_FILE_NOT_FOUND */
+/* drop-in: bign.h (bign_params.c:197-236): "1.2.112.0.2.0.34.101.45.3.1" / ".3.2" / ".3.3"
+   (bign-curve256v1 / 384v1 / 512v1, l = 128 / 192 / 256); other names -> ERR_FILE_NOT_FOUND */
 err_t bignParamsStd(bign_params* params, const char* name);
-/* drop-in: bign.h:370-402 (bign_sign.c:349-361, :247-260). Parameter blocks other than
-   bign-curve256v1 return ERR_NOT_IMPLEMENTED (after the reference's structural checks,
-   bign_params.c:244-280). */
+/* drop-in: bign.h:370-402 (bign_sign.c:349-361, :247-260). With no = l/4 octets: hash no,
+   sig no/2 + no, privkey no, pubkey 2 no. Parameter blocks other than the three standard
+   curves return ERR_NOT_IMPLEMENTED (after the reference's structural checks,
+   bign_params.c:244-280). These also serve bign128/192/256{Verify,Sign2,PubkeyCalc}
+   (bign128.c:177-185, bign192.c, bign256.c), which only fix the level and the hash OID. */
 err_t bignVerify(const bign_params* params, const octet oid_der[], size_t oid_len,
 	const octet hash[], const octet sig[], const octet pubkey[]);
 err_t bignSign2(octet sig[], const bign_params* params, const octet oid_der[], size_t oid_len,
 	const octet hash[], const octet privkey[], const void* t, size_t t_len);
 err_t bignPubkeyCalc(octet pubkey[], const bign_params* params, const octet privkey[]);
-/* batch: item i uses hashes+32i, sigs+48i, pubkeys+64i; status[i] = the err_t the
+/* batch: item i uses hashes + no i, sigs + (no + no/2) i, pubkeys + 2 no i (l = 128: 32, 48, 64
+   octets per item); status[i] = the err_t the
    reference's bignVerify would return for that item. Return value: ERR_OK when the batch
    ran (look at status[]), else the parameter/OID/device error. */
 err_t bignVerifyBatch(err_t* status, const bign_params* params, const octet oid_der[],
@@ -243,6 +246,11 @@ err_t ecMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d_le
 /* batch ecAddMulA with the base point (ec.c:1183-1273): b_i = d_i * a_i + k_i * G, k_i 32 octets */
 err_t ecAddMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d_len, const octet* k,
 	size_t count);
+/* the same on the standard curve of level l = 128 / 192 / 256: points l/2 octets, d_len <= l/4,
+   k_i l/4 octets */
+err_t ecMulABatchL(size_t l, octet* b, int* ok, const octet* a, const octet* d, size_t d_len, size_t count);
+err_t ecAddMulABatchL(size_t l, octet* b, int* ok, const octet* a, const octet* d, size_t d_len,
+	const octet* k, size_t count);
 /* device */
 err_t b2g_bignVerifyBatch_dev(void* d_status, const octet oid_der[], size_t oid_len,
 	const void* d_hashes, const void* d_sigs, const void* d_pubkeys, size_t count, void* stream);
@@ -253,6 +261,17 @@ err_t b2g_bignPubkeyCalcBatch_dev(void* d_status, void* d_pubkeys, const void* d
 err_t b2g_ecMulABatch_dev(void* d_b, void* d_ok, const void* d_a, const void* d_d, size_t d_len,
 	size_t count, void* stream);
 err_t b2g_ecAddMulABatch_dev(void* d_b, void* d_ok, const void* d_a, const void* d_d, size_t d_len,
+	const void* d_k, size_t count, void* stream);
+/* device, any level (the names above are l = 128) */
+err_t b2g_bignVerifyBatchL_dev(size_t l, void* d_status, const octet oid_der[], size_t oid_len,
+	const void* d_hashes, const void* d_sigs, const void* d_pubkeys, size_t count, void* stream);
+err_t b2g_bignSign2BatchL_t_dev(size_t l, void* d_status, void* d_sigs, const octet oid_der[], size_t oid_len,
+	const void* d_hashes, const void* d_privkeys, size_t count, const void* t, size_t t_len, void* stream);
+err_t b2g_bignPubkeyCalcBatchL_dev(size_t l, void* d_status, void* d_pubkeys, const void* d_privkeys,
+	size_t count, void* stream);
+err_t b2g_ecMulABatchL_dev(size_t l, void* d_b, void* d_ok, const void* d_a, const void* d_d, size_t d_len,
+	size_t count, void* stream);
+err_t b2g_ecAddMulABatchL_dev(size_t l, void* d_b, void* d_ok, const void* d_a, const void* d_d, size_t d_len,
 	const void* d_k, size_t count, void* stream);
 
 #ifdef __cplusplus

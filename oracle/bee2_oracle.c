@@ -325,56 +325,118 @@ void orc_beltHash(u8 hash[32], const void* src, size_t n)
 	memcpy(hash, h, 32);
 }
 
-/* wide-block encryption of exactly 32 bytes: 4 rounds, belt_wbl.c:50-82 with n = 2 */
-static void belt_wbl32(u8 buf[32], const u32 key[8])
+/* wide-block encryption of count = 32, 48 or 64 bytes: 2n rounds over n = count/16 blocks
+   (belt_wbl.c:50-82; the round counter restarts on every call, :199-207) */
+static void belt_wbl(u8* buf, size_t count, const u32 key[8])
 {
+	const size_t n = count / 16;
 	u64 round;
-	for (round = 1; round <= 4; ++round)
+	for (round = 1; round <= 2 * n; ++round)
 	{
-		u8 e[16], r1[16];
-		int i;
-		memcpy(r1, buf, 16), memcpy(e, buf, 16);
+		u8 s[16], e[16];
+		size_t i, j;
+		/* s <- r1 + ... + r_{n-1} */
+		memcpy(s, buf, 16);
+		for (j = 1; j + 1 < n; ++j)
+			for (i = 0; i < 16; ++i) s[i] ^= buf[16 * j + i];
+		/* r <- ShLo^128(r), r* <- s */
+		memmove(buf, buf + 16, count - 16);
+		memcpy(buf + count - 16, s, 16);
+		/* r*_before_shift += E(s) + <round> */
+		memcpy(e, s, 16);
 		blk_encr(e, key);
 		for (i = 0; i < 8; ++i) e[i] ^= (u8)(round >> (8 * i));
-		for (i = 0; i < 16; ++i) buf[i] = buf[16 + i] ^ e[i];
-		memcpy(buf + 16, r1, 16);
+		for (i = 0; i < 16; ++i) buf[count - 32 + i] ^= e[i];
 	}
 }
 
-/* ======================================================================= GF(p), p = 2^256 - 189 */
+/* ======================================================================= GF(p), p = 2^(64 n) - c */
+/* The three standard bign curves (bign_params.c:36-73, :78-125, :131-190): level l = 128 / 192 /
+   256, n = l/32 words of 64 bits, p = 2^(2l) - c with c = 189 / 317 / 569 (Crandall reduction
+   zz_red.c:71-105), a = p - 3, G = (0, yG). */
 
-typedef struct { u64 w[4]; } fe;
-#define PC 189u  /* p = 2^256 - 189: bign_params.c:36-41; Crandall reduction zz_red.c:71-105 */
-static const fe FP = {{0xFFFFFFFFFFFFFF43ull, ~0ull, ~0ull, ~0ull}};
-/* q: bign_params.c:61-66 (little-endian octets) */
-static const fe FQ = {{0x7E5ABF99263D6607ull, 0xD95C8ED60DFB4DFCull, ~0ull, ~0ull}};
-static const u8 B_LE[32] = { /* coefficient b, bign_params.c:50-55 */
-	0xF1, 0x03, 0x9C, 0xD6, 0x6B, 0x7D, 0x2E, 0xB2, 0x53, 0x92, 0x8B, 0x97, 0x69, 0x50, 0xF5, 0x4C,
-	0xBE, 0xFB, 0xD8, 0xE4, 0xAB, 0x3A, 0xC1, 0xD2, 0xED, 0xA8, 0xF3, 0x15, 0x15, 0x6C, 0xCE, 0x77};
-static const u8 YG_LE[32] = { /* base point G = (0, yG), bign_params.c:68-73 */
+#define FE_MAXW 8
+typedef struct { u64 w[FE_MAXW]; } fe;           /* words above n are kept 0 */
+typedef struct { int n; size_t no; fe p, q, yG; } lvl;
+
+static const u8 Q128_LE[32] = { /* q of bign-curve256v1 */
+	0x07, 0x66, 0x3D, 0x26, 0x99, 0xBF, 0x5A, 0x7E, 0xFC, 0x4D, 0xFB, 0x0D, 0xD6, 0x8E, 0x5C, 0xD9,
+	0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF};
+static const u8 YG128_LE[32] = { /* base point G = (0, yG) */
 	0x93, 0x6A, 0x51, 0x04, 0x18, 0xCF, 0x29, 0x1E, 0x52, 0xF6, 0x08, 0xC4, 0x66, 0x39, 0x91, 0x78,
 	0x5D, 0x83, 0xD6, 0x51, 0xA3, 0xC9, 0xE4, 0x5C, 0x9F, 0xD6, 0x16, 0xFB, 0x3C, 0xFC, 0xF7, 0x6B};
+static const u8 Q192_LE[48] = { /* q of bign-curve384v1 */
+	0xB7, 0xA7, 0x0C, 0xF3, 0x3F, 0xDC, 0xB7, 0x3D, 0x0A, 0xFF, 0xA4, 0xA6, 0xE7, 0xDA, 0x46, 0x80,
+	0xBB, 0x7B, 0xAF, 0x73, 0x03, 0xC4, 0xCC, 0x6C, 0xFE, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF,
+	0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF};
+static const u8 YG192_LE[48] = { /* base point G = (0, yG) */
+	0x51, 0xC4, 0x33, 0xF7, 0x31, 0xCB, 0x5E, 0xEA, 0xF9, 0x42, 0x2A, 0x6B, 0x27, 0x3E, 0x40, 0x84,
+	0x55, 0xD3, 0xB1, 0x66, 0x9E, 0xE7, 0x49, 0x05, 0xA0, 0xFF, 0x86, 0xDC, 0x11, 0x9A, 0x72, 0x3A,
+	0x89, 0xBF, 0x2D, 0x43, 0x7E, 0x11, 0x30, 0x63, 0x9E, 0x9E, 0x2E, 0xA8, 0x24, 0x82, 0x43, 0x5D};
+static const u8 Q256_LE[64] = { /* q of bign-curve512v1 */
+	0xF1, 0x8E, 0x06, 0x0D, 0x49, 0xAD, 0xFF, 0xDC, 0x32, 0xDF, 0x56, 0x95, 0xE5, 0xCA, 0x1B, 0x36,
+	0xF4, 0x13, 0x21, 0x2E, 0xB0, 0xEB, 0x6B, 0xF2, 0x4E, 0x00, 0x98, 0x01, 0x2C, 0x09, 0xC0, 0xB2,
+	0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF,
+	0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF};
+static const u8 YG256_LE[64] = { /* base point G = (0, yG) */
+	0xBD, 0xED, 0xEF, 0xCE, 0x6F, 0xAE, 0x92, 0xB7, 0x04, 0x0D, 0x4C, 0xC9, 0xB9, 0x83, 0xAA, 0x67,
+	0x61, 0x22, 0xE8, 0xEE, 0x95, 0x73, 0x77, 0xFF, 0xD2, 0x6F, 0xFA, 0x0E, 0xE2, 0xDD, 0x73, 0x69,
+	0xDA, 0xCA, 0xCC, 0x00, 0x1B, 0xF8, 0xED, 0xD2, 0xE2, 0xBC, 0x61, 0xB3, 0xB3, 0x41, 0xAB, 0xB0,
+	0xAB, 0x8F, 0xD1, 0xA0, 0xF7, 0xE6, 0x82, 0xB1, 0x81, 0x76, 0x03, 0xE4, 0x7A, 0xFF, 0x26, 0xA8};
 
-static fe fe_from(const u8 b[32]) { fe r; memcpy(r.w, b, 32); return r; }
-static void fe_to(u8 b[32], fe a) { memcpy(b, a.w, 32); }
+static fe fe_from_n(const u8* b, size_t no) { fe r; memset(&r, 0, sizeof r); memcpy(r.w, b, no); return r; }
+static const lvl* level(size_t l)
+{
+	static lvl L[3];
+	static int ready;
+	if (!ready)
+	{
+		static const size_t ls[3] = {128, 192, 256};
+		static const u64 cs[3] = {189, 317, 569};
+		static const u8* const qs[3] = {Q128_LE, Q192_LE, Q256_LE};
+		static const u8* const ys[3] = {YG128_LE, YG192_LE, YG256_LE};
+		int i, j;
+		for (i = 0; i < 3; ++i)
+		{
+			L[i].n = (int)(ls[i] / 32), L[i].no = ls[i] / 4;
+			memset(&L[i].p, 0, sizeof(fe));
+			for (j = 0; j < L[i].n; ++j) L[i].p.w[j] = ~0ull;
+			L[i].p.w[0] -= cs[i] - 1;
+			L[i].q = fe_from_n(qs[i], L[i].no), L[i].yG = fe_from_n(ys[i], L[i].no);
+		}
+		ready = 1;
+	}
+	return l == 128 ? &L[0] : l == 192 ? &L[1] : l == 256 ? &L[2] : 0;
+}
+
+static fe fe_from(const lvl* L, const u8* b) { return fe_from_n(b, L->no); }
+static void fe_to(const lvl* L, u8* b, fe a) { memcpy(b, a.w, L->no); }
 static int fe_cmp(fe a, fe b)
 {
 	int i;
-	for (i = 3; i >= 0; --i)
+	for (i = FE_MAXW - 1; i >= 0; --i)
 		if (a.w[i] != b.w[i]) return a.w[i] < b.w[i] ? -1 : 1;
 	return 0;
 }
-static int fe_is0(fe a) { return (a.w[0] | a.w[1] | a.w[2] | a.w[3]) == 0; }
-static u64 raw_add(fe* r, fe a, fe b)
+static int fe_is0(fe a)
+{
+	u64 z = 0; int i;
+	for (i = 0; i < FE_MAXW; ++i) z |= a.w[i];
+	return z == 0;
+}
+/* n-word add / sub, returning the carry / borrow out of word n-1 */
+static u64 raw_add(const lvl* L, fe* r, fe a, fe b)
 {
 	u128 c = 0; int i;
-	for (i = 0; i < 4; ++i) c += (u128)a.w[i] + b.w[i], r->w[i] = (u64)c, c >>= 64;
+	memset(r, 0, sizeof *r);
+	for (i = 0; i < L->n; ++i) c += (u128)a.w[i] + b.w[i], r->w[i] = (u64)c, c >>= 64;
 	return (u64)c;
 }
-static u64 raw_sub(fe* r, fe a, fe b)
+static u64 raw_sub(const lvl* L, fe* r, fe a, fe b)
 {
 	u64 br = 0; int i;
-	for (i = 0; i < 4; ++i)
+	memset(r, 0, sizeof *r);
+	for (i = 0; i < L->n; ++i)
 	{
 		u128 d = (u128)a.w[i] - b.w[i] - br;
 		r->w[i] = (u64)d, br = (u64)(d >> 64) & 1;
@@ -382,159 +444,167 @@ static u64 raw_sub(fe* r, fe a, fe b)
 	return br;
 }
 /* (a + b) mod m, a, b < m (zz_mod.c:42) */
-static fe addmod(fe a, fe b, fe m)
+static fe addmod(const lvl* L, fe a, fe b, fe m)
 {
 	fe r, t;
-	u64 c = raw_add(&r, a, b);
-	if (c || fe_cmp(r, m) >= 0) raw_sub(&t, r, m), r = t;
+	u64 c = raw_add(L, &r, a, b);
+	if (c || fe_cmp(r, m) >= 0) raw_sub(L, &t, r, m), r = t;
 	return r;
 }
-static fe submod(fe a, fe b, fe m)
+/* a - b mod 2^(64n), + m if it borrowed (zz_mod.c:120) */
+static fe submod(const lvl* L, fe a, fe b, fe m)
 {
 	fe r, t;
-	if (raw_sub(&r, a, b)) raw_add(&t, r, m), r = t;
+	if (raw_sub(L, &r, a, b)) raw_add(L, &t, r, m), r = t;
 	return r;
 }
-static fe fp_add(fe a, fe b) { return addmod(a, b, FP); }
-static fe fp_sub(fe a, fe b) { return submod(a, b, FP); }
+static fe fp_add(const lvl* L, fe a, fe b) { return addmod(L, a, b, L->p); }
+static fe fp_sub(const lvl* L, fe a, fe b) { return submod(L, a, b, L->p); }
 
-static void mul_wide(u64 r[8], const u64* a, const u64* b)
+/* r[0..na+nb) = a * b (zz_mul.c:82-120) */
+static void mul_wide(u64* r, const u64* a, int na, const u64* b, int nb)
 {
 	int i, j;
-	memset(r, 0, 64);
-	for (i = 0; i < 4; ++i)
+	memset(r, 0, 8 * (size_t)(na + nb));
+	for (i = 0; i < na; ++i)
 	{
 		u64 carry = 0;
-		for (j = 0; j < 4; ++j)
+		for (j = 0; j < nb; ++j)
 		{
 			u128 t = (u128)a[i] * b[j] + r[i + j] + carry;
 			r[i + j] = (u64)t, carry = (u64)(t >> 64);
 		}
-		r[i + 4] = carry;
+		r[i + nb] = carry;
 	}
 }
 
-/* x (8 words) mod (2^256 - c), c given as 4 words with c < 2^128: fold hi*c into lo until hi = 0 */
-static fe fold_mod(const u64 x[8], fe m)
+/* x (2n words) mod m, m = 2^(64n) - c: fold hi * c into lo until hi = 0, then subtract m while >= m */
+static fe fold_mod(const lvl* L, const u64* x, fe m)
 {
-	u64 c[4], cur[8], hc[8];
-	fe lo, hi, t;
+	const int n = L->n;
+	u64 cur[2 * FE_MAXW], hc[2 * FE_MAXW];
+	fe lo, hi, t, c, z;
 	int i;
-	/* c = 2^256 - m */
-	{
-		fe z = {{0, 0, 0, 0}}, cc;
-		raw_sub(&cc, z, m);
-		memcpy(c, cc.w, 32);
-	}
-	memcpy(cur, x, 64);
+	memset(&z, 0, sizeof z);
+	raw_sub(L, &c, z, m);                /* c = 2^(64n) - m */
+	memcpy(cur, x, 16 * (size_t)n);
 	for (;;)
 	{
-		u64 carry;
-		memcpy(lo.w, cur, 32), memcpy(hi.w, cur + 4, 32);
+		memset(&lo, 0, sizeof lo), memset(&hi, 0, sizeof hi);
+		memcpy(lo.w, cur, 8 * (size_t)n), memcpy(hi.w, cur + n, 8 * (size_t)n);
 		if (fe_is0(hi)) break;
-		mul_wide(hc, hi.w, c);
-		/* cur = hc + lo */
+		mul_wide(hc, hi.w, n, c.w, n);
 		{
 			u128 acc = 0;
-			for (i = 0; i < 8; ++i)
+			for (i = 0; i < 2 * n; ++i)
 			{
-				acc += (u128)hc[i] + (i < 4 ? lo.w[i] : 0);
+				acc += (u128)hc[i] + (i < n ? lo.w[i] : 0);
 				cur[i] = (u64)acc, acc >>= 64;
 			}
-			carry = (u64)acc;
-			(void)carry;
 		}
 	}
-	while (fe_cmp(lo, m) >= 0) raw_sub(&t, lo, m), lo = t;
+	while (fe_cmp(lo, m) >= 0) raw_sub(L, &t, lo, m), lo = t;
 	return lo;
 }
 
-static fe fp_mul(fe a, fe b)
+static fe fp_mul(const lvl* L, fe a, fe b)
 {
-	u64 r[8];
-	mul_wide(r, a.w, b.w);
-	return fold_mod(r, FP);
+	u64 r[2 * FE_MAXW];
+	mul_wide(r, a.w, L->n, b.w, L->n);
+	return fold_mod(L, r, L->p);
 }
-static fe fp_sqr(fe a) { return fp_mul(a, a); }
+static fe fp_sqr(const lvl* L, fe a) { return fp_mul(L, a, a); }
 /* a^(p-2), gfp.c:33-44 */
-static fe fp_inv(fe a)
+static fe fp_inv(const lvl* L, fe a)
 {
-	fe e = FP, r = {{1, 0, 0, 0}};
+	fe e = L->p, r;
 	int i;
+	memset(&r, 0, sizeof r), r.w[0] = 1;
 	e.w[0] -= 2;
-	for (i = 255; i >= 0; --i)
+	for (i = 64 * L->n - 1; i >= 0; --i)
 	{
-		r = fp_sqr(r);
-		if (e.w[i / 64] >> (i % 64) & 1) r = fp_mul(r, a);
+		r = fp_sqr(L, r);
+		if (e.w[i / 64] >> (i % 64) & 1) r = fp_mul(L, r, a);
 	}
 	return r;
 }
 
-void orc_gfpMul(u8 c[32], const u8 a[32], const u8 b[32]) { fe_to(c, fp_mul(fe_from(a), fe_from(b))); }
-void orc_gfpInv(u8 c[32], const u8 a[32]) { fe_to(c, fp_inv(fe_from(a))); }
+void orc_gfpMul(u8 c[32], const u8 a[32], const u8 b[32])
+{
+	const lvl* L = level(128);
+	fe_to(L, c, fp_mul(L, fe_from(L, a), fe_from(L, b)));
+}
+void orc_gfpInv(u8 c[32], const u8 a[32])
+{
+	const lvl* L = level(128);
+	fe_to(L, c, fp_inv(L, fe_from(L, a)));
+}
 
 /* ======================================================================= curve y^2 = x^3 - 3x + b */
 
 typedef struct { fe X, Y, Z; } pt;  /* Jacobian, O <=> Z = 0 (ecp_j.c) */
 
-static pt pt_dbl(pt P)
+static pt pt_inf(void)
 {
 	pt R;
-	fe d, g, bt, al, t, u;
-	if (fe_is0(P.Z) || fe_is0(P.Y)) { memset(&R, 0, sizeof R); R.X.w[0] = R.Y.w[0] = 1; return R; }
-	d = fp_sqr(P.Z), g = fp_sqr(P.Y), bt = fp_mul(P.X, g);
-	t = fp_sub(P.X, d), u = fp_add(P.X, d), al = fp_mul(t, u);
-	al = fp_add(fp_add(al, al), al);                      /* 3(X - Z^2)(X + Z^2), a = -3 */
-	t = fp_add(bt, bt), t = fp_add(t, t);                 /* 4 beta */
-	R.X = fp_sub(fp_sqr(al), fp_add(t, t));
-	u = fp_add(P.Y, P.Z), R.Z = fp_sub(fp_sub(fp_sqr(u), g), d);
-	g = fp_sqr(g), g = fp_add(g, g), g = fp_add(g, g), g = fp_add(g, g);  /* 8 gamma^2 */
-	R.Y = fp_sub(fp_mul(al, fp_sub(t, R.X)), g);
+	memset(&R, 0, sizeof R), R.X.w[0] = R.Y.w[0] = 1;
 	return R;
 }
 
-static pt pt_add(pt P, pt Q)
+static pt pt_dbl(const lvl* L, pt P)
+{
+	pt R;
+	fe d, g, bt, al, t, u;
+	if (fe_is0(P.Z) || fe_is0(P.Y)) return pt_inf();
+	d = fp_sqr(L, P.Z), g = fp_sqr(L, P.Y), bt = fp_mul(L, P.X, g);
+	t = fp_sub(L, P.X, d), u = fp_add(L, P.X, d), al = fp_mul(L, t, u);
+	al = fp_add(L, fp_add(L, al, al), al);                /* 3(X - Z^2)(X + Z^2), a = -3 */
+	t = fp_add(L, bt, bt), t = fp_add(L, t, t);           /* 4 beta */
+	R.X = fp_sub(L, fp_sqr(L, al), fp_add(L, t, t));
+	u = fp_add(L, P.Y, P.Z), R.Z = fp_sub(L, fp_sub(L, fp_sqr(L, u), g), d);
+	g = fp_sqr(L, g), g = fp_add(L, g, g), g = fp_add(L, g, g), g = fp_add(L, g, g);  /* 8 gamma^2 */
+	R.Y = fp_sub(L, fp_mul(L, al, fp_sub(L, t, R.X)), g);
+	return R;
+}
+
+static pt pt_add(const lvl* L, pt P, pt Q)
 {
 	pt R;
 	fe z1z1, z2z2, u1, u2, s1, s2, h, r, hh, hhh, v;
 	if (fe_is0(P.Z)) return Q;
 	if (fe_is0(Q.Z)) return P;
-	z1z1 = fp_sqr(P.Z), z2z2 = fp_sqr(Q.Z);
-	u1 = fp_mul(P.X, z2z2), u2 = fp_mul(Q.X, z1z1);
-	s1 = fp_mul(P.Y, fp_mul(Q.Z, z2z2)), s2 = fp_mul(Q.Y, fp_mul(P.Z, z1z1));
-	h = fp_sub(u2, u1), r = fp_sub(s2, s1);
+	z1z1 = fp_sqr(L, P.Z), z2z2 = fp_sqr(L, Q.Z);
+	u1 = fp_mul(L, P.X, z2z2), u2 = fp_mul(L, Q.X, z1z1);
+	s1 = fp_mul(L, P.Y, fp_mul(L, Q.Z, z2z2)), s2 = fp_mul(L, Q.Y, fp_mul(L, P.Z, z1z1));
+	h = fp_sub(L, u2, u1), r = fp_sub(L, s2, s1);
 	if (fe_is0(h))
-	{
-		if (fe_is0(r)) return pt_dbl(P);
-		memset(&R, 0, sizeof R); R.X.w[0] = R.Y.w[0] = 1; return R;
-	}
-	hh = fp_sqr(h), hhh = fp_mul(h, hh), v = fp_mul(u1, hh);
-	R.X = fp_sub(fp_sub(fp_sqr(r), hhh), fp_add(v, v));
-	R.Y = fp_sub(fp_mul(r, fp_sub(v, R.X)), fp_mul(s1, hhh));
-	R.Z = fp_mul(fp_mul(P.Z, Q.Z), h);
+		return fe_is0(r) ? pt_dbl(L, P) : pt_inf();
+	hh = fp_sqr(L, h), hhh = fp_mul(L, h, hh), v = fp_mul(L, u1, hh);
+	R.X = fp_sub(L, fp_sub(L, fp_sqr(L, r), hhh), fp_add(L, v, v));
+	R.Y = fp_sub(L, fp_mul(L, r, fp_sub(L, v, R.X)), fp_mul(L, s1, hhh));
+	R.Z = fp_mul(L, fp_mul(L, P.Z, Q.Z), h);
 	return R;
 }
 
 /* scalar given as little-endian octets of any length */
-static pt pt_mul(pt A, const u8* d, size_t d_len)
+static pt pt_mul(const lvl* L, pt A, const u8* d, size_t d_len)
 {
-	pt R;
+	pt R = pt_inf();
 	long i;
-	memset(&R, 0, sizeof R); R.X.w[0] = R.Y.w[0] = 1;
 	for (i = (long)d_len * 8 - 1; i >= 0; --i)
 	{
-		R = pt_dbl(R);
-		if (d[i / 8] >> (i % 8) & 1) R = pt_add(R, A);
+		R = pt_dbl(L, R);
+		if (d[i / 8] >> (i % 8) & 1) R = pt_add(L, R, A);
 	}
 	return R;
 }
 
-static int pt_to_affine(fe* x, fe* y, pt P)
+static int pt_to_affine(const lvl* L, fe* x, fe* y, pt P)
 {
 	fe zi, zi2;
 	if (fe_is0(P.Z)) return 0;
-	zi = fp_inv(P.Z), zi2 = fp_sqr(zi);
-	*x = fp_mul(P.X, zi2), *y = fp_mul(P.Y, fp_mul(zi2, zi));
+	zi = fp_inv(L, P.Z), zi2 = fp_sqr(L, zi);
+	*x = fp_mul(L, P.X, zi2), *y = fp_mul(L, P.Y, fp_mul(L, zi2, zi));
 	return 1;
 }
 
@@ -544,87 +614,115 @@ static pt pt_affine(fe x, fe y)
 	P.X = x, P.Y = y, memset(&P.Z, 0, sizeof P.Z), P.Z.w[0] = 1;
 	return P;
 }
-static pt pt_base(void)
+static pt pt_base(const lvl* L)
 {
-	fe zero = {{0, 0, 0, 0}};
-	return pt_affine(zero, fe_from(YG_LE));
+	fe zero;
+	memset(&zero, 0, sizeof zero);
+	return pt_affine(zero, L->yG);
 }
 
-int orc_ecMulA128(u8 b[64], const u8 a[64], const u8* d, size_t d_len)
+/* ecMulA (ec.c:497-525) on the standard curve of level l: b = d * a, 0 iff the result is O */
+int orc_ecMulA(size_t l, u8* b, const u8* a, const u8* d, size_t d_len)
 {
+	const lvl* L = level(l);
 	fe x, y;
-	(void)B_LE;
-	if (!pt_to_affine(&x, &y, pt_mul(pt_affine(fe_from(a), fe_from(a + 32)), d, d_len)))
+	if (!L) return 0;
+	if (!pt_to_affine(L, &x, &y, pt_mul(L, pt_affine(fe_from(L, a), fe_from(L, a + L->no)), d, d_len)))
 		return 0;
-	fe_to(b, x), fe_to(b + 32, y);
+	fe_to(L, b, x), fe_to(L, b + L->no, y);
 	return 1;
 }
+int orc_ecMulA128(u8 b[64], const u8 a[64], const u8* d, size_t d_len) { return orc_ecMulA(128, b, a, d, d_len); }
 
-/* bign_sign.c:268-347 with l = 128 (no = 32) */
+/* bign_sign.c:268-347; no = l/4 octets: hash no, sig no/2 + no, pubkey 2 no */
+u32 orc_bignVerify(size_t l, const u8* oid_der, size_t oid_len, const u8* hash, const u8* sig, const u8* pubkey)
+{
+	const lvl* L = level(l);
+	size_t no;
+	fe Qx, Qy, s1, Hh, t, x, y;
+	u8 s0[33], s1b[64], buf[128 + 128], hv[32];
+	pt R;
+	if (!L) return 119u;
+	no = L->no;
+	if (oid_len > 128) return ORC_BAD_INPUT;
+	Qx = fe_from(L, pubkey), Qy = fe_from(L, pubkey + no), s1 = fe_from(L, sig + no / 2), Hh = fe_from(L, hash);
+	if (fe_cmp(Qx, L->p) >= 0 || fe_cmp(Qy, L->p) >= 0) return ORC_BAD_PUBKEY;
+	if (fe_cmp(s1, L->q) >= 0) return ORC_BAD_SIG;
+	if (fe_cmp(Hh, L->q) >= 0) raw_sub(L, &t, Hh, L->q), Hh = t;
+	s1 = addmod(L, s1, Hh, L->q);
+	memcpy(s0, sig, no / 2), s0[no / 2] = 1;
+	fe_to(L, s1b, s1);
+	R = pt_add(L, pt_mul(L, pt_base(L), s1b, no), pt_mul(L, pt_affine(Qx, Qy), s0, no / 2 + 1));
+	if (!pt_to_affine(L, &x, &y, R)) return ORC_BAD_SIG;
+	memcpy(buf, oid_der, oid_len), fe_to(L, buf + oid_len, x), memcpy(buf + oid_len + no, hash, no);
+	orc_beltHash(hv, buf, oid_len + 2 * no);
+	return memcmp(hv, sig, no / 2) == 0 ? ORC_OK : ORC_BAD_SIG;
+}
 u32 orc_bignVerify128(const u8* oid_der, size_t oid_len, const u8 hash[32], const u8 sig[48], const u8 pubkey[64])
 {
-	fe Qx = fe_from(pubkey), Qy = fe_from(pubkey + 32), s1 = fe_from(sig + 16), Hh = fe_from(hash), t, x, y;
-	u8 s0[17], s1b[32], buf[256], hv[32];
-	pt R;
-	if (oid_len > 128) return ORC_BAD_INPUT;
-	if (fe_cmp(Qx, FP) >= 0 || fe_cmp(Qy, FP) >= 0) return ORC_BAD_PUBKEY;
-	if (fe_cmp(s1, FQ) >= 0) return ORC_BAD_SIG;
-	if (fe_cmp(Hh, FQ) >= 0) raw_sub(&t, Hh, FQ), Hh = t;
-	s1 = addmod(s1, Hh, FQ);
-	memcpy(s0, sig, 16), s0[16] = 1;
-	fe_to(s1b, s1);
-	R = pt_add(pt_mul(pt_base(), s1b, 32), pt_mul(pt_affine(Qx, Qy), s0, 17));
-	if (!pt_to_affine(&x, &y, R)) return ORC_BAD_SIG;
-	memcpy(buf, oid_der, oid_len), fe_to(buf + oid_len, x), memcpy(buf + oid_len + 32, hash, 32);
-	orc_beltHash(hv, buf, oid_len + 64);
-	return memcmp(hv, sig, 16) == 0 ? ORC_OK : ORC_BAD_SIG;
+	return orc_bignVerify(128, oid_der, oid_len, hash, sig, pubkey);
 }
 
-u32 orc_bignPubkeyCalc128(u8 pubkey[64], const u8 privkey[32])
+/* bign_misc.c:369-412 */
+u32 orc_bignPubkeyCalc(size_t l, u8* pubkey, const u8* privkey)
 {
-	fe d = fe_from(privkey), x, y;
-	if (fe_is0(d) || fe_cmp(d, FQ) >= 0) return ORC_BAD_PRIVKEY;
-	if (!pt_to_affine(&x, &y, pt_mul(pt_base(), privkey, 32))) return ORC_BAD_PARAMS;
-	fe_to(pubkey, x), fe_to(pubkey + 32, y);
+	const lvl* L = level(l);
+	fe d, x, y;
+	if (!L) return 119u;
+	d = fe_from(L, privkey);
+	if (fe_is0(d) || fe_cmp(d, L->q) >= 0) return ORC_BAD_PRIVKEY;
+	if (!pt_to_affine(L, &x, &y, pt_mul(L, pt_base(L), privkey, L->no))) return ORC_BAD_PARAMS;
+	fe_to(L, pubkey, x), fe_to(L, pubkey + L->no, y);
 	return ORC_OK;
 }
+u32 orc_bignPubkeyCalc128(u8 pubkey[64], const u8 privkey[32]) { return orc_bignPubkeyCalc(128, pubkey, privkey); }
 
-/* bign_sign.c:140-245 with l = 128 */
+/* bign_sign.c:140-245 */
+u32 orc_bignSign2(size_t l, u8* sig, const u8* oid_der, size_t oid_len, const u8* hash,
+	const u8* privkey, const void* t, size_t t_len)
+{
+	const lvl* L = level(l);
+	size_t no;
+	fe d, k, x, y, s0d, s1, Hh, s0w;
+	u8* buf;
+	u8 theta[32], kb[64], hv[32];
+	u32 tk[8];
+	u64 prod[2 * FE_MAXW];
+	if (!L) return 119u;
+	no = L->no;
+	d = fe_from(L, privkey);
+	if (fe_is0(d) || fe_cmp(d, L->q) >= 0) return ORC_BAD_PRIVKEY;
+	buf = (u8*)malloc(oid_len + 2 * no + t_len + 1);
+	if (!buf) return 110u;
+	/* theta = belt-hash(oid || d || t) */
+	memcpy(buf, oid_der, oid_len), memcpy(buf + oid_len, privkey, no);
+	if (t) memcpy(buf + oid_len + no, t, t_len);
+	orc_beltHash(theta, buf, oid_len + no + (t ? t_len : 0));
+	orc_beltKeyExpand2(tk, theta, 32);
+	/* k = H; k = WBL(k) until 0 < k < q */
+	memcpy(kb, hash, no);
+	do belt_wbl(kb, no, tk), k = fe_from(L, kb);
+	while (fe_is0(k) || fe_cmp(k, L->q) >= 0);
+	if (!pt_to_affine(L, &x, &y, pt_mul(L, pt_base(L), kb, no))) { free(buf); return ORC_BAD_PARAMS; }
+	/* s0 = belt-hash(oid || R.x || H)[0..no/2) */
+	memcpy(buf, oid_der, oid_len), fe_to(L, buf + oid_len, x), memcpy(buf + oid_len + no, hash, no);
+	orc_beltHash(hv, buf, oid_len + 2 * no);
+	free(buf);
+	memcpy(sig, hv, no / 2);
+	/* s1 = (k - (s0 + 2^l) d - H) mod q */
+	memset(&s0w, 0, sizeof s0w), memcpy(s0w.w, hv, no / 2), s0w.w[L->n / 2] = 1;
+	mul_wide(prod, s0w.w, L->n, d.w, L->n);
+	s0d = fold_mod(L, prod, L->q);
+	s1 = submod(L, k, s0d, L->q);
+	Hh = fe_from(L, hash);           /* not reduced first: bign_sign.c:236-237 */
+	s1 = submod(L, s1, Hh, L->q);
+	fe_to(L, sig + no / 2, s1);
+	return ORC_OK;
+}
 u32 orc_bignSign2_128(u8 sig[48], const u8* oid_der, size_t oid_len, const u8 hash[32],
 	const u8 privkey[32], const void* t, size_t t_len)
 {
-	fe d = fe_from(privkey), k, x, y, s0d, s1, Hh;
-	u8* buf;
-	u8 theta[32], kb[32], hv[32];
-	u32 tk[8];
-	u64 prod[8], s0w[4];
-	if (fe_is0(d) || fe_cmp(d, FQ) >= 0) return ORC_BAD_PRIVKEY;
-	buf = (u8*)malloc(oid_len + 64 + t_len + 1);
-	if (!buf) return 110u;
-	/* theta = belt-hash(oid || d || t) */
-	memcpy(buf, oid_der, oid_len), memcpy(buf + oid_len, privkey, 32);
-	if (t) memcpy(buf + oid_len + 32, t, t_len);
-	orc_beltHash(theta, buf, oid_len + 32 + (t ? t_len : 0));
-	orc_beltKeyExpand2(tk, theta, 32);
-	/* k = H; k = WBL(k) until 0 < k < q */
-	memcpy(kb, hash, 32);
-	do belt_wbl32(kb, tk), k = fe_from(kb);
-	while (fe_is0(k) || fe_cmp(k, FQ) >= 0);
-	if (!pt_to_affine(&x, &y, pt_mul(pt_base(), kb, 32))) { free(buf); return ORC_BAD_PARAMS; }
-	/* s0 = belt-hash(oid || R.x || H)[0..16) */
-	memcpy(buf, oid_der, oid_len), fe_to(buf + oid_len, x), memcpy(buf + oid_len + 32, hash, 32);
-	orc_beltHash(hv, buf, oid_len + 64);
-	free(buf);
-	memcpy(sig, hv, 16);
-	/* s1 = (k - (s0 + 2^128) d - H) mod q */
-	memcpy(s0w, hv, 16), s0w[2] = 1, s0w[3] = 0;
-	mul_wide(prod, s0w, d.w);
-	s0d = fold_mod(prod, FQ);
-	s1 = submod(k, s0d, FQ);
-	Hh = fe_from(hash);           /* not reduced first: bign_sign.c:236-237 */
-	s1 = submod(s1, Hh, FQ);
-	fe_to(sig + 16, s1);
-	return ORC_OK;
+	return orc_bignSign2(128, sig, oid_der, oid_len, hash, privkey, t, t_len);
 }
 
 /* ======================================================================= belt-DWP (belt_dwp.c:45-330) */

@@ -80,6 +80,14 @@ uint32_t orc_bignSign2_128(uint8_t sig[48], const uint8_t* oid_der, size_t oid_l
 uint32_t orc_bignPubkeyCalc128(uint8_t pubkey[64], const uint8_t privkey[32]); /* bign_misc.c:369-412 */
 /* d * A on the curve; returns 1, or 0 when the result is the point at infinity. ec.c:497-525 */
 int orc_ecMulA128(uint8_t b[64], const uint8_t a[64], const uint8_t* d, size_t d_len);
+/* the same on the standard curve of level l = 128 / 192 / 256 (bign-curve256v1 / 384v1 / 512v1,
+   bign_params.c:36-190); no = l/4 octets: hash no, sig no/2 + no, privkey no, pubkey 2 no */
+uint32_t orc_bignVerify(size_t l, const uint8_t* oid_der, size_t oid_len, const uint8_t* hash,
+	const uint8_t* sig, const uint8_t* pubkey);
+uint32_t orc_bignSign2(size_t l, uint8_t* sig, const uint8_t* oid_der, size_t oid_len,
+	const uint8_t* hash, const uint8_t* privkey, const void* t, size_t t_len);
+uint32_t orc_bignPubkeyCalc(size_t l, uint8_t* pubkey, const uint8_t* privkey);
+int orc_ecMulA(size_t l, uint8_t* b, const uint8_t* a, const uint8_t* d, size_t d_len);
 /* field helpers exposed for unit tests of the device field layer (zm.c:214-253, gfp.c:33-44) */
 void orc_gfpMul(uint8_t c[32], const uint8_t a[32], const uint8_t b[32]);
 void orc_gfpInv(uint8_t c[32], const uint8_t a[32]);

@@ -21,9 +21,10 @@ def port():
         L = C.CDLL(os.path.join(REF_DIR, "libbee2oracle.so"))
         L.orc_beltH.restype = C.c_void_p
         for n in ("orc_beltCHEWrap", "orc_beltCHEUnwrap", "orc_beltDWPWrap", "orc_beltDWPUnwrap", "orc_bashHash", "orc_beltCTR", "orc_beltECBEncr", "orc_beltECBDecr", "orc_bignVerify128",
-                  "orc_bignSign2_128", "orc_bignPubkeyCalc128"):
+                  "orc_bignSign2_128", "orc_bignPubkeyCalc128", "orc_bignVerify", "orc_bignSign2", "orc_bignPubkeyCalc"):
             getattr(L, n).restype = C.c_uint32
         L.orc_ecMulA128.restype = C.c_int
+        L.orc_ecMulA.restype = C.c_int
         _port = L
     return _port
 
@@ -146,25 +147,31 @@ def beltHash(src: bytes) -> bytes:
     return out.raw
 
 
-def bignVerify(hash_: bytes, sig: bytes, pub: bytes, oid: bytes = OID) -> int:
-    return port().orc_bignVerify128(oid, sz(len(oid)), bytes(hash_), bytes(sig), bytes(pub))
+# OIDs the reference's fixed-level wrappers use: belt-hash (bign128.c:151-153), bash384 (bign192.c:151-153),
+# bash512 (bign256.c:151-153)
+OIDS = {128: OID, 192: bytes.fromhex("06092A7000020022654D0C"), 256: bytes.fromhex("06092A7000020022654D0D")}
+CURVES = {128: b"1.2.112.0.2.0.34.101.45.3.1", 192: b"1.2.112.0.2.0.34.101.45.3.2", 256: b"1.2.112.0.2.0.34.101.45.3.3"}
 
 
-def bignSign2(hash_: bytes, priv: bytes, t: bytes = None, oid: bytes = OID):
-    sig = C.create_string_buffer(48)
-    code = port().orc_bignSign2_128(sig, oid, sz(len(oid)), bytes(hash_), bytes(priv), t, sz(len(t) if t else 0))
+def bignVerify(hash_: bytes, sig: bytes, pub: bytes, oid: bytes = OID, l: int = 128) -> int:
+    return port().orc_bignVerify(sz(l), oid, sz(len(oid)), bytes(hash_), bytes(sig), bytes(pub))
+
+
+def bignSign2(hash_: bytes, priv: bytes, t: bytes = None, oid: bytes = OID, l: int = 128):
+    sig = C.create_string_buffer(3 * l // 8)
+    code = port().orc_bignSign2(sz(l), sig, oid, sz(len(oid)), bytes(hash_), bytes(priv), t, sz(len(t) if t else 0))
     return code, sig.raw
 
 
-def bignPubkeyCalc(priv: bytes):
-    pub = C.create_string_buffer(64)
-    code = port().orc_bignPubkeyCalc128(pub, bytes(priv))
+def bignPubkeyCalc(priv: bytes, l: int = 128):
+    pub = C.create_string_buffer(l // 2)
+    code = port().orc_bignPubkeyCalc(sz(l), pub, bytes(priv))
     return code, pub.raw
 
 
-def ecMulA(a: bytes, d: bytes):
-    out = C.create_string_buffer(64)
-    ok = port().orc_ecMulA128(out, bytes(a), bytes(d), sz(len(d)))
+def ecMulA(a: bytes, d: bytes, l: int = 128):
+    out = C.create_string_buffer(l // 2)
+    ok = port().orc_ecMulA(sz(l), out, bytes(a), bytes(d), sz(len(d)))
     return ok, out.raw
 
 
@@ -174,15 +181,14 @@ class RefParams(C.Structure):
                 ("q", C.c_ubyte * 64), ("yG", C.c_ubyte * 64), ("seed", C.c_ubyte * 8)]
 
 
-_rp = None
+_rp = {}
 
 
-def ref_params():
-    global _rp
-    if _rp is None:
-        _rp = RefParams()
-        assert ref().bignParamsStd(C.byref(_rp), b"1.2.112.0.2.0.34.101.45.3.1") == 0
-    return _rp
+def ref_params(l: int = 128):
+    if l not in _rp:
+        _rp[l] = RefParams()
+        assert ref().bignParamsStd(C.byref(_rp[l]), CURVES[l]) == 0
+    return _rp[l]
 
 
 def ref_bashHash(l: int, src: bytes) -> bytes:
@@ -209,20 +215,20 @@ def ref_beltHash(src: bytes) -> bytes:
     return out.raw
 
 
-def ref_bignVerify(hash_: bytes, sig: bytes, pub: bytes, oid: bytes = OID) -> int:
-    return ref().bignVerify(C.byref(ref_params()), oid, sz(len(oid)), bytes(hash_), bytes(sig), bytes(pub))
+def ref_bignVerify(hash_: bytes, sig: bytes, pub: bytes, oid: bytes = OID, l: int = 128) -> int:
+    return ref().bignVerify(C.byref(ref_params(l)), oid, sz(len(oid)), bytes(hash_), bytes(sig), bytes(pub))
 
 
-def ref_bignSign2(hash_: bytes, priv: bytes, t: bytes = None, oid: bytes = OID):
-    sig = C.create_string_buffer(48)
-    code = ref().bignSign2(sig, C.byref(ref_params()), oid, sz(len(oid)), bytes(hash_), bytes(priv), t,
+def ref_bignSign2(hash_: bytes, priv: bytes, t: bytes = None, oid: bytes = OID, l: int = 128):
+    sig = C.create_string_buffer(3 * l // 8)
+    code = ref().bignSign2(sig, C.byref(ref_params(l)), oid, sz(len(oid)), bytes(hash_), bytes(priv), t,
                            sz(len(t) if t else 0))
     return code, sig.raw
 
 
-def ref_bignPubkeyCalc(priv: bytes):
-    pub = C.create_string_buffer(64)
-    code = ref().bignPubkeyCalc(pub, C.byref(ref_params()), bytes(priv))
+def ref_bignPubkeyCalc(priv: bytes, l: int = 128):
+    pub = C.create_string_buffer(l // 2)
+    code = ref().bignPubkeyCalc(pub, C.byref(ref_params(l)), bytes(priv))
     return code, pub.raw
 
 

@@ -193,6 +193,42 @@ def main():
         rec["bad"] = {"hash": bytes(bad_h).hex(), "sig": bytes(bad_sig).hex(), "pubkey": bytes(bad_pub).hex(),
                       "verify": o.ref_bignVerify(bytes(bad_h), bytes(bad_sig), bytes(bad_pub))}
         out["bign"].append(rec)
+    # levels 192 / 256 (bign-curve384v1 / 512v1) with the OIDs of bign192.c / bign256.c; an own generator so
+    # that the records above keep their values
+    rng2 = np.random.default_rng(20261018)
+    rb2 = lambda n: rng2.integers(0, 256, size=n, dtype=np.uint8).tobytes()  # noqa: E731
+    out["bignL"] = []
+    for l in (192, 256):
+        no, oid = l // 4, o.OIDS[l]
+        for i in range(10):
+            d = bytearray(rb2(no))
+            d[no - 1] &= 0x7F
+            h = rb2(no) if i != 7 else b"\xff" * no      # i = 7: H >= q
+            t = None if i % 3 else rb2(5 + i)
+            code, pub = o.ref_bignPubkeyCalc(bytes(d), l)
+            assert code == 0
+            code, sig = o.ref_bignSign2(h, bytes(d), t, oid, l)
+            assert code == 0
+            rec = {"l": l, "privkey": bytes(d).hex(), "pubkey": pub.hex(), "hash": h.hex(), "t": t.hex() if t else None,
+                   "sig": sig.hex(), "verify": o.ref_bignVerify(h, sig, pub, oid, l)}
+            assert rec["verify"] == 0
+            bad_sig, bad_pub, bad_h = bytearray(sig), bytearray(pub), bytearray(h)
+            kind = i % 6
+            if kind == 0:
+                bad_sig[i % (no // 2)] ^= 1 << (i % 8)
+            elif kind == 1:
+                bad_sig[no // 2 + i % no] ^= 1 << (i % 8)
+            elif kind == 2:
+                bad_h[i % no] ^= 0x80
+            elif kind == 3:
+                bad_pub[i % (2 * no)] ^= 1
+            elif kind == 4:
+                bad_sig[no // 2:] = b"\xff" * no        # s1 >= q
+            else:
+                bad_pub[0:no] = b"\xff" * no            # Qx >= p
+            rec["bad"] = {"hash": bytes(bad_h).hex(), "sig": bytes(bad_sig).hex(), "pubkey": bytes(bad_pub).hex(),
+                          "verify": o.ref_bignVerify(bytes(bad_h), bytes(bad_sig), bytes(bad_pub), oid, l)}
+            out["bignL"].append(rec)
     with open(os.path.join(HERE, "ref_vectors.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote ref_vectors.json")

@@ -91,6 +91,117 @@ def test_reference_fixtures():
                             bytes.fromhex(bad["pubkey"])) == bad["verify"]
 
 
+# ---------------------------------------------------------------- levels 192 / 256
+CURVE_Q = {192: 0xfffffffffffffffffffffffffffffffffffffffffffffffe6cccc40373af7bbb8046dae7a6a4ff0a3db7dc3ff30ca7b7,
+           256: 0xffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffb2c0092c0198004ef26bebb02e2113f4361bcae59556df32dcffad490d068ef1}
+
+
+@pytest.mark.parametrize("l", [192, 256])
+def test_levels_params_and_fixtures(l):
+    """bign-curve384v1 / 512v1 against outputs of the unmodified reference (tests/golden/ref_vectors.json
+    "bignL"): key calculation, deterministic signatures, verification verdicts incl. corrupted inputs."""
+    p = b.bignParamsStd(b.BIGN_CURVES[l])
+    no, oid = l // 4, o.OIDS[l]
+    assert p.l == l and bytes(p.q)[:no] == CURVE_Q[l].to_bytes(no, "little") and bytes(p.q)[no:] == bytes(64 - no)
+    if o.ref() is not None:
+        rp = o.ref_params(l)
+        for f in ("p", "a", "b", "q", "yG", "seed"):
+            assert bytes(getattr(p, f)) == bytes(getattr(rp, f)), f
+    other = b.bignParamsStd(b.BIGN_CURVES[l])
+    other.b[0] ^= 2
+    assert b.bignVerify(other, oid, bytes(no), bytes(no + no // 2), bytes(2 * no)) == b.ERR_NOT_IMPLEMENTED
+    for t in [t for t in REF["bignL"] if t["l"] == l]:
+        priv, pub, h, sig = (bytes.fromhex(t[k]) for k in ("privkey", "pubkey", "hash", "sig"))
+        tt = bytes.fromhex(t["t"]) if t["t"] else None
+        assert b.bignPubkeyCalc(p, priv) == pub
+        assert b.bignSign2(p, oid, h, priv, tt) == sig
+        assert b.bignVerify(p, oid, h, sig, pub) == t["verify"]
+        bad = t["bad"]
+        assert b.bignVerify(p, oid, bytes.fromhex(bad["hash"]), bytes.fromhex(bad["sig"]),
+                            bytes.fromhex(bad["pubkey"])) == bad["verify"]
+    with pytest.raises(b.Bee2Error) as e:
+        b.bignSign2(p, oid, bytes(no), CURVE_Q[l].to_bytes(no, "little"))       # d = q
+    assert e.value.code == b.ERR_BAD_PRIVKEY
+
+
+@pytest.mark.parametrize("l", [192, 256])
+def test_levels_batch_random_vs_oracle(l):
+    rng = np.random.default_rng(100 + l)
+    p, n = b.bignParamsStd(b.BIGN_CURVES[l]), 200
+    no, oid, q = l // 4, o.OIDS[l], CURVE_Q[l]
+    priv = rng.integers(0, 256, (n, no), dtype=np.uint8)
+    priv[:, no - 1] &= 0x7F
+    for i, d in enumerate([1, 2, q - 1, q - 2, 1 << l, (1 << l) + 1]):          # exceptional keys: Q = +-G, ...
+        priv[i] = A(d.to_bytes(no, "little"))
+    hashes = rng.integers(0, 256, (n, no), dtype=np.uint8)
+    hashes[::5, no // 2:] = 0xFF                                               # H >= q path
+    st, pubs = b.bignPubkeyCalcBatch(p, priv)
+    assert (st == 0).all()
+    st, sigs = b.bignSign2Batch(p, oid, hashes, priv)
+    assert (st == 0).all()
+    for i in list(range(6)) + list(range(6, n, 25)):
+        assert o.bignPubkeyCalc(priv[i].tobytes(), l) == (0, pubs[i].tobytes())
+        assert o.bignSign2(hashes[i].tobytes(), priv[i].tobytes(), None, oid, l) == (0, sigs[i].tobytes())
+    assert (b.bignVerifyBatch(p, oid, hashes, sigs, pubs) == 0).all()
+    for i in range(n):
+        kind = int(rng.integers(0, 18))
+        if kind == 0:
+            sigs[i, int(rng.integers(0, no // 2))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:
+            sigs[i, no // 2 + int(rng.integers(0, no))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 2:
+            hashes[i, int(rng.integers(0, no))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 3:
+            pubs[i, int(rng.integers(0, 2 * no))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 4:
+            sigs[i, no // 2:] = 0xFF
+        elif kind == 5:
+            pubs[i, (0 if i & 1 else no):][:no] = 0xFF
+    got = b.bignVerifyBatch(p, oid, hashes, sigs, pubs)
+    want = np.array([o.bignVerify(hashes[i].tobytes(), sigs[i].tobytes(), pubs[i].tobytes(), oid, l) for i in range(n)],
+                    dtype=np.uint32)
+    assert np.array_equal(got, want)
+    assert {0, 505, 510} <= set(int(x) for x in got)
+
+
+@pytest.mark.parametrize("l", [192, 256])
+def test_levels_ecMulA_vs_oracle(l):
+    rng = np.random.default_rng(200 + l)
+    p, n = b.bignParamsStd(b.BIGN_CURVES[l]), 24
+    no, q = l // 4, CURVE_Q[l]
+    priv = rng.integers(0, 256, (n, no), dtype=np.uint8)
+    priv[:, no - 1] &= 0x7F
+    _, pts = b.bignPubkeyCalcBatch(p, priv)
+    for d_len in (no, no // 2 + 1, 3):
+        sc = rng.integers(0, 256, (n, d_len), dtype=np.uint8)
+        sc[0] = 0
+        sc[1] = 0
+        sc[1, 0] = 1
+        got, ok = b.ecMulABatch(pts, sc, l)
+        for i in range(n):
+            want_ok, want = o.ecMulA(pts[i].tobytes(), sc[i].tobytes(), l)
+            assert ok[i] == want_ok
+            if want_ok:
+                assert got[i].tobytes() == want
+        assert ok[0] == 0 and got[1].tobytes() == pts[1].tobytes()
+    sc = np.stack([A(q.to_bytes(no, "little")), A((q + 1).to_bytes(no, "little"))])
+    got, ok = b.ecMulABatch(pts[:2].copy(), sc, l)
+    assert ok[0] == 0 and ok[1] == 1 and got[1].tobytes() == pts[1].tobytes()
+    # d A + k G with A = a G: the result is ((d a + k) mod q) G, incl. d A = +-k G
+    a = [1, 1] + [int.from_bytes(priv[i].tobytes(), "little") for i in range(2, 8)]
+    d = [5, 7] + [int(rng.integers(1, 1 << 62)) for _ in range(6)]
+    k = [5, q - 7] + [int.from_bytes(rng.integers(0, 256, no, dtype=np.uint8).tobytes(), "little") % q for _ in range(6)]
+    _, apts = b.bignPubkeyCalcBatch(p, np.stack([A(x.to_bytes(no, "little")) for x in a]))
+    got, ok = b.ecAddMulABatch(apts, np.stack([A(x.to_bytes(no, "little")) for x in d]),
+                               np.stack([A(x.to_bytes(no, "little")) for x in k]), l)
+    for i in range(8):
+        e = (d[i] * a[i] + k[i]) % q
+        if e == 0:
+            assert ok[i] == 0
+        else:
+            assert ok[i] == 1 and (0, got[i].tobytes()) == o.bignPubkeyCalc(e.to_bytes(no, "little"), l)
+
+
 def _corrupt(rng, hashes, sigs, pubs):
     """~1/3 of the items get one of the SURVEY §8d corruptions."""
     n = hashes.shape[0]

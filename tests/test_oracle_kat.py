@@ -139,6 +139,21 @@ def test_reference_fixtures():
         assert o.bignVerify(bytes.fromhex(bad["hash"]), bytes.fromhex(bad["sig"]), bytes.fromhex(bad["pubkey"])) == bad["verify"]
 
 
+def test_reference_fixtures_levels_192_256():
+    """bign-curve384v1 / 512v1: the reference's own tests are self-consistency only (bign192_test.c,
+    bign256_test.c), so the restatement is pinned on outputs of the unmodified reference."""
+    for t in REF["bignL"]:
+        l, oid = t["l"], o.OIDS[t["l"]]
+        priv, pub, h = (bytes.fromhex(t[k]) for k in ("privkey", "pubkey", "hash"))
+        tt = bytes.fromhex(t["t"]) if t["t"] else None
+        assert o.bignPubkeyCalc(priv, l) == (0, pub)
+        assert o.bignSign2(h, priv, tt, oid, l) == (0, bytes.fromhex(t["sig"]))
+        assert o.bignVerify(h, bytes.fromhex(t["sig"]), pub, oid, l) == t["verify"] == 0
+        bad = t["bad"]
+        assert o.bignVerify(bytes.fromhex(bad["hash"]), bytes.fromhex(bad["sig"]), bytes.fromhex(bad["pubkey"]),
+                            oid, l) == bad["verify"]
+
+
 @pytest.mark.skipif(o.ref() is None, reason="oracle/_ref/libbee2ref_64.so not built here")
 def test_live_differential_against_reference():
     rng = np.random.default_rng(5)
@@ -164,3 +179,17 @@ def test_live_differential_against_reference():
         s2 = bytearray(sig)
         s2[i] ^= 4
         assert o.bignVerify(h, s2, pub) == o.ref_bignVerify(h, bytes(s2), pub) == 510
+    for l in (192, 256):
+        no, oid = l // 4, o.OIDS[l]
+        for i in range(3):
+            d = bytearray(rb(no))
+            d[no - 1] &= 0x7F
+            h = rb(no)
+            code, sig = o.bignSign2(h, bytes(d), None, oid, l)
+            assert (code, sig) == o.ref_bignSign2(h, bytes(d), None, oid, l)
+            code, pub = o.bignPubkeyCalc(bytes(d), l)
+            assert (code, pub) == o.ref_bignPubkeyCalc(bytes(d), l)
+            assert o.bignVerify(h, sig, pub, oid, l) == o.ref_bignVerify(h, sig, pub, oid, l) == 0
+            s2 = bytearray(sig)
+            s2[no // 2 + i] ^= 4
+            assert o.bignVerify(h, s2, pub, oid, l) == o.ref_bignVerify(h, bytes(s2), pub, oid, l) == 510
