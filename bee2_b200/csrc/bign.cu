@@ -233,6 +233,85 @@ template <int N> __device__ __forceinline__ void hash_oid_ab(const BeltSmallT& S
 	for (int i = 0; i < 8; ++i) out[i] = dg.w[i];
 }
 
+// ---------------------------------------------------------------- block-wide inversion
+// Montgomery's simultaneous inversion as a product tree in shared memory: every thread of the CTA
+// hands in one z != 0 (1 if it has nothing to invert) and gets 1/z back, for ONE field inversion
+// per CTA (thread 0, ~270 squarings) plus 2 log2(BIGN_THREADS) products per thread — instead of
+// one inversion per thread, which was 12 % of a verification and half of a signature.
+// Node i has children 2i and 2i+1, leaves at BIGN_THREADS + tid, root at 1. The tree is stored
+// word-major (word j of node i at sm[j * 2 BIGN_THREADS + i]) so that lanes hit distinct banks.
+// Must be reached by ALL threads of the CTA (it synchronises).
+#define BIGN_TREE_WORDS(N) (2 * BIGN_THREADS * (N))
+template <int N> __device__ __forceinline__ void tree_put(u32* sm, int i, const fe<N>& a)
+{
+#pragma unroll
+	for (int j = 0; j < N; ++j) sm[j * (2 * BIGN_THREADS) + i] = a.v[j];
+}
+template <int N> __device__ __forceinline__ void tree_get(fe<N>& a, const u32* sm, int i)
+{
+#pragma unroll
+	for (int j = 0; j < N; ++j) a.v[j] = sm[j * (2 * BIGN_THREADS) + i];
+}
+template <int N> __device__ __noinline__ fe<N> block_inv(const fe<N> z, u32* sm)
+{
+	const int tid = threadIdx.x;
+	fe<N> a, b;
+	tree_put<N>(sm, BIGN_THREADS + tid, z);
+	__syncthreads();
+	// up: products of the children
+#pragma unroll 1
+	for (int s = BIGN_THREADS / 2; s >= 1; s >>= 1)
+	{
+		if (tid < s)
+		{
+			tree_get<N>(a, sm, 2 * (s + tid)), tree_get<N>(b, sm, 2 * (s + tid) + 1);
+			fe_mul<N>(a, a, b);
+			tree_put<N>(sm, s + tid, a);
+		}
+		__syncthreads();
+	}
+	if (tid == 0)
+	{
+		tree_get<N>(a, sm, 1);
+		fe_inv<N>(a, a);
+		tree_put<N>(sm, 1, a);
+	}
+	__syncthreads();
+	// down: 1/child = 1/parent * sibling
+#pragma unroll 1
+	for (int s = 2; s <= BIGN_THREADS; s <<= 1)
+	{
+		const bool on = tid < s;
+		if (on)
+		{
+			tree_get<N>(a, sm, (s + tid) >> 1), tree_get<N>(b, sm, (s + tid) ^ 1);
+			fe_mul<N>(a, a, b);
+		}
+		__syncthreads();
+		if (on)
+			tree_put<N>(sm, s + tid, a);
+		__syncthreads();
+	}
+	tree_get<N>(a, sm, BIGN_THREADS + tid);
+	return a;
+}
+// affine x (and y) of a point from the inverse of its Z (ecp_j.c:104-133), canonical residues
+template <int N> __device__ __forceinline__ void pt_affine_x_zi(fe<N>& x, const pt<N>& P, const fe<N>& zi)
+{
+	fe<N> zi2;
+	fe_sqr<N>(zi2, zi);
+	fe_mul<N>(x, P.X, zi2);
+	fe_canon<N>(x);
+}
+template <int N> __device__ __forceinline__ void pt_affine_xy_zi(fe<N>& x, fe<N>& y, const pt<N>& P, const fe<N>& zi)
+{
+	fe<N> zi2;
+	fe_sqr<N>(zi2, zi);
+	fe_mul<N>(x, P.X, zi2);
+	fe_mul<N>(zi2, zi2, zi), fe_mul<N>(y, P.Y, zi2);
+	fe_canon<N>(x), fe_canon<N>(y);
+}
+
 // ---------------------------------------------------------------- kernels
 // Table of fixed-base multiples: entry (i, j) = j * 2^(BIGN_GW i) * G, affine.
 template <int N> __global__ void __launch_bounds__(BIGN_THREADS) bign_gtab_kernel(uint4* gtab)
@@ -279,80 +358,92 @@ bign_verify_kernel(u32* __restrict__ status, const u8* __restrict__ hashes, cons
 {
 	constexpr int NO = 4 * N, H2 = N / 2;
 	__shared__ u32 tab[256];
+	__shared__ u32 tree[BIGN_TREE_WORDS(N)];
 	BeltSmallT::fill(tab);
 	__syncthreads();
 	const BeltSmallT S(tab);
 	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= count)
-		return;
+	// every thread stays until the block-wide inversion; `live` = still computing, `st` = verdict so far
+	bool live = i < count;
+	u32 st = B2G_OK;
 	fe<N> qx, qy;
-	u32 s0[H2], s1[N], H[N], Hq[N];
-	fe_load<N>(qx, pubkeys + 2 * NO * i), fe_load<N>(qy, pubkeys + 2 * NO * i + NO);
-	load_uN<N>(s1, sigs + (NO + NO / 2) * i + NO / 2);
-	load_uN<N>(H, hashes + NO * i);
-	{
-		const u8* p = sigs + (NO + NO / 2) * i;
-#pragma unroll
-		for (int k = 0; k < H2; ++k)
-			s0[k] = (u32)p[4 * k] | (u32)p[4 * k + 1] << 8 | (u32)p[4 * k + 2] << 16 | (u32)p[4 * k + 3] << 24;
-	}
-	// Q.x, Q.y < p else BAD_PUBKEY (qrFrom, :306-311); no on-curve check in the reference
-	{
-		fe<N> cx = qx, cy = qy;
-		fe_canon<N>(cx), fe_canon<N>(cy);
-		bool same = true;
-#pragma unroll
-		for (int k = 0; k < N; ++k) same &= cx.v[k] == qx.v[k] && cy.v[k] == qy.v[k];
-		if (!same)
-		{
-			status[i] = B2G_BAD_PUBKEY;
-			return;
-		}
-	}
-	// s1 < q else BAD_SIG (:313-318)
-	if (geq_q<N>(s1))
-	{
-		status[i] = B2G_BAD_SIG;
-		return;
-	}
-	// H >= q -> H - q, once (:320-326); s1 <- (s1 + H) mod q
-#pragma unroll
-	for (int k = 0; k < N; ++k) Hq[k] = H[k];
-	if (geq_q<N>(H))
-	{
-		u32 q[N];
-		load_q<N>(q);
-		(void)sub_n<N>(Hq, H, q);
-	}
-	modq_add<N>(s1, s1, Hq);
-	// R <- (s0 + 2^l) Q + s1 G   (:329-336)
+	u32 s0[H2], s1[N], H[N];
 	pt<N> R;
+	if (live)
 	{
-		sc<N> k5;
+		u32 Hq[N];
+		fe_load<N>(qx, pubkeys + 2 * NO * i), fe_load<N>(qy, pubkeys + 2 * NO * i + NO);
+		load_uN<N>(s1, sigs + (NO + NO / 2) * i + NO / 2);
+		load_uN<N>(H, hashes + NO * i);
+		{
+			const u8* p = sigs + (NO + NO / 2) * i;
 #pragma unroll
-		for (int k = 0; k < N; ++k) k5.w[k] = k < H2 ? s0[k] : (k == H2 ? 1u : 0u);
-		pt_mul_var<N>(R, k5, 16 * N + 1, qx, qy);
+			for (int k = 0; k < H2; ++k)
+				s0[k] = (u32)p[4 * k] | (u32)p[4 * k + 1] << 8 | (u32)p[4 * k + 2] << 16 | (u32)p[4 * k + 3] << 24;
+		}
+		// Q.x, Q.y < p else BAD_PUBKEY (qrFrom, :306-311); no on-curve check in the reference
+		{
+			fe<N> cx = qx, cy = qy;
+			fe_canon<N>(cx), fe_canon<N>(cy);
+			bool same = true;
+#pragma unroll
+			for (int k = 0; k < N; ++k) same &= cx.v[k] == qx.v[k] && cy.v[k] == qy.v[k];
+			if (!same)
+				st = B2G_BAD_PUBKEY, live = false;
+		}
+		// s1 < q else BAD_SIG (:313-318)
+		if (live && geq_q<N>(s1))
+			st = B2G_BAD_SIG, live = false;
+		// H >= q -> H - q, once (:320-326); s1 <- (s1 + H) mod q
+#pragma unroll
+		for (int k = 0; k < N; ++k) Hq[k] = H[k];
+		if (geq_q<N>(H))
+		{
+			u32 q[N];
+			load_q<N>(q);
+			(void)sub_n<N>(Hq, H, q);
+		}
+		if (live)
+			modq_add<N>(s1, s1, Hq);
 	}
+	if (live)
 	{
-		sc<N> ks;
+		// R <- (s0 + 2^l) Q + s1 G   (:329-336)
+		{
+			sc<N> k5;
 #pragma unroll
-		for (int k = 0; k < N; ++k) ks.w[k] = s1[k];
-		pt_add_mul_base<N>(R, ks, gtab);
+			for (int k = 0; k < N; ++k) k5.w[k] = k < H2 ? s0[k] : (k == H2 ? 1u : 0u);
+			pt_mul_var<N>(R, k5, 16 * N + 1, qx, qy);
+		}
+		{
+			sc<N> ks;
+#pragma unroll
+			for (int k = 0; k < N; ++k) ks.w[k] = s1[k];
+			pt_add_mul_base<N>(R, ks, gtab);
+		}
+		if (pt_is_inf<N>(R))
+			st = B2G_BAD_SIG, live = false;
 	}
-	if (pt_is_inf<N>(R))
+	fe<N> z;
+	if (live)
+		z = R.Z;
+	else
+		fe_set_u32<N>(z, 1);
+	const fe<N> zi = block_inv<N>(z, tree);
+	if (live)
 	{
-		status[i] = B2G_BAD_SIG;
-		return;
-	}
-	fe<N> rx;
-	pt_to_affine_x<N>(rx, R);
-	// s0 == belt-hash(oid || R.x || H) mod 2^l ? (:339-343)
-	u32 hv[8];
-	hash_oid_ab<N>(S, hv, oid, rx.v, H, (const u8*)0, 0);
-	bool ok = true;
+		fe<N> rx;
+		pt_affine_x_zi<N>(rx, R, zi);
+		// s0 == belt-hash(oid || R.x || H) mod 2^l ? (:339-343)
+		u32 hv[8];
+		hash_oid_ab<N>(S, hv, oid, rx.v, H, (const u8*)0, 0);
+		bool ok = true;
 #pragma unroll
-	for (int k = 0; k < H2; ++k) ok &= hv[k] == s0[k];
-	status[i] = ok ? B2G_OK : B2G_BAD_SIG;
+		for (int k = 0; k < H2; ++k) ok &= hv[k] == s0[k];
+		st = ok ? B2G_OK : B2G_BAD_SIG;
+	}
+	if (i < count)
+		status[i] = st;
 }
 
 // belt-WBL encryption of NB = 2, 3, 4 blocks: 2 NB rounds (belt_wbl.c:50-82, round reset :203).
@@ -389,73 +480,85 @@ bign_sign2_kernel(u32* __restrict__ status, u8* __restrict__ sigs, const u8* __r
 {
 	constexpr int NO = 4 * N, H2 = N / 2;
 	__shared__ u32 tab[256];
+	__shared__ u32 tree[BIGN_TREE_WORDS(N)];
 	BeltSmallT::fill(tab);
 	__syncthreads();
 	const BeltSmallT S(tab);
 	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= count)
-		return;
-	u32 d[N], H[N], k[N], theta[8];
-	load_uN<N>(d, privkeys + NO * i);
-	load_uN<N>(H, hashes + NO * i);
-	// 0 < d < q else BAD_PRIVKEY (:189-194)
-	if (uN_is_zero<N>(d) || geq_q<N>(d))
-	{
-		status[i] = B2G_BAD_PRIVKEY;
-		return;
-	}
-	// theta <- belt-hash(oid || d || t); k <- H; k <- WBL_theta(k) until 0 < k < q (:198-218)
-	hash_oid_ab<N>(S, theta, oid, d, (const u32*)0, targ.t, targ.len);
-#pragma unroll
-	for (int j = 0; j < N; ++j) k[j] = H[j];
-	do
-		wbl<N / 4>(S, k, theta);
-	while (uN_is_zero<N>(k) || geq_q<N>(k));
-	// R <- k G (:219-224)
+	bool live = i < count;
+	u32 st = B2G_OK;
+	u32 d[N], H[N], k[N];
 	pt<N> R;
-	pt_set_inf<N>(R);
+	if (live)
 	{
-		sc<N> ks;
+		load_uN<N>(d, privkeys + NO * i);
+		load_uN<N>(H, hashes + NO * i);
+		// 0 < d < q else BAD_PRIVKEY (:189-194)
+		if (uN_is_zero<N>(d) || geq_q<N>(d))
+			st = B2G_BAD_PRIVKEY, live = false;
+	}
+	if (live)
+	{
+		// theta <- belt-hash(oid || d || t); k <- H; k <- WBL_theta(k) until 0 < k < q (:198-218)
+		u32 theta[8];
+		hash_oid_ab<N>(S, theta, oid, d, (const u32*)0, targ.t, targ.len);
 #pragma unroll
-		for (int j = 0; j < N; ++j) ks.w[j] = k[j];
-		pt_add_mul_base<N>(R, ks, gtab);
-	}
-	if (pt_is_inf<N>(R))
-	{
-		status[i] = B2G_BAD_PARAMS;
-		return;
-	}
-	fe<N> rx;
-	pt_to_affine_x<N>(rx, R);
-	// s0 <- belt-hash(oid || R.x || H) mod 2^l (:226-229)
-	u32 hv[8];
-	hash_oid_ab<N>(S, hv, oid, rx.v, H, (const u8*)0, 0);
-	// s1 <- (k - (s0 + 2^l) d - H) mod q (:231-238)
-	u32 prod[N + H2 + 1];
-	{
-		u32 s0w[H2 + 1];
-		for (int j = 0; j < H2; ++j) s0w[j] = hv[j];
-		s0w[H2] = 1u;
-		for (int j = 0; j < N + H2 + 1; ++j) prod[j] = 0;
-		for (int a = 0; a < H2 + 1; ++a)
+		for (int j = 0; j < N; ++j) k[j] = H[j];
+		do
+			wbl<N / 4>(S, k, theta);
+		while (uN_is_zero<N>(k) || geq_q<N>(k));
+		// R <- k G (:219-224)
+		pt_set_inf<N>(R);
 		{
-			u64 carry = 0;
-			for (int b = 0; b < N; ++b)
-			{
-				const u64 t = (u64)s0w[a] * d[b] + prod[a + b] + carry;
-				prod[a + b] = (u32)t, carry = t >> 32;
-			}
-			prod[a + N] = (u32)carry;
+			sc<N> ks;
+#pragma unroll
+			for (int j = 0; j < N; ++j) ks.w[j] = k[j];
+			pt_add_mul_base<N>(R, ks, gtab);
 		}
+		if (pt_is_inf<N>(R))
+			st = B2G_BAD_PARAMS, live = false;
 	}
-	u32 s1[N];
-	modq_reduce<N>(s1, prod, N + H2 + 1);
-	modq_sub<N>(s1, k, s1);
-	modq_sub<N>(s1, s1, H);   // H as is, not reduced first (zzSubMod, :237-238)
-	u8* o = sigs + (NO + NO / 2) * i;
-	for (int j = 0; j < NO / 2; ++j) o[j] = (u8)(hv[j >> 2] >> (8 * (j & 3)));
-	for (int j = 0; j < NO; ++j) o[NO / 2 + j] = (u8)(s1[j >> 2] >> (8 * (j & 3)));
-	status[i] = B2G_OK;
+	fe<N> z;
+	if (live)
+		z = R.Z;
+	else
+		fe_set_u32<N>(z, 1);
+	const fe<N> zi = block_inv<N>(z, tree);
+	if (live)
+	{
+		fe<N> rx;
+		pt_affine_x_zi<N>(rx, R, zi);
+		// s0 <- belt-hash(oid || R.x || H) mod 2^l (:226-229)
+		u32 hv[8];
+		hash_oid_ab<N>(S, hv, oid, rx.v, H, (const u8*)0, 0);
+		// s1 <- (k - (s0 + 2^l) d - H) mod q (:231-238)
+		u32 prod[N + H2 + 1];
+		{
+			u32 s0w[H2 + 1];
+			for (int j = 0; j < H2; ++j) s0w[j] = hv[j];
+			s0w[H2] = 1u;
+			for (int j = 0; j < N + H2 + 1; ++j) prod[j] = 0;
+			for (int a = 0; a < H2 + 1; ++a)
+			{
+				u64 carry = 0;
+				for (int b = 0; b < N; ++b)
+				{
+					const u64 t = (u64)s0w[a] * d[b] + prod[a + b] + carry;
+					prod[a + b] = (u32)t, carry = t >> 32;
+				}
+				prod[a + N] = (u32)carry;
+			}
+		}
+		u32 s1[N];
+		modq_reduce<N>(s1, prod, N + H2 + 1);
+		modq_sub<N>(s1, k, s1);
+		modq_sub<N>(s1, s1, H);   // H as is, not reduced first (zzSubMod, :237-238)
+		u8* o = sigs + (NO + NO / 2) * i;
+		for (int j = 0; j < NO / 2; ++j) o[j] = (u8)(hv[j >> 2] >> (8 * (j & 3)));
+		for (int j = 0; j < NO; ++j) o[NO / 2 + j] = (u8)(s1[j >> 2] >> (8 * (j & 3)));
+	}
+	if (i < count)
+		status[i] = st;
 }
 
 // bignPubkeyCalc per item (bign_misc.c:369-412): Q = d G, 0 < d < q
@@ -464,86 +567,85 @@ bign_pubkey_kernel(u32* __restrict__ status, u8* __restrict__ pubkeys, const u8*
 	u64 count, const uint4* __restrict__ gtab)
 {
 	constexpr int NO = 4 * N;
+	__shared__ u32 tree[BIGN_TREE_WORDS(N)];
 	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= count)
-		return;
-	u32 d[N];
-	load_uN<N>(d, privkeys + NO * i);
-	if (uN_is_zero<N>(d) || geq_q<N>(d))
-	{
-		status[i] = B2G_BAD_PRIVKEY;
-		return;
-	}
+	bool live = i < count;
+	u32 st = B2G_OK;
 	pt<N> R;
-	pt_set_inf<N>(R);
+	if (live)
 	{
-		sc<N> ks;
+		u32 d[N];
+		load_uN<N>(d, privkeys + NO * i);
+		if (uN_is_zero<N>(d) || geq_q<N>(d))
+			st = B2G_BAD_PRIVKEY, live = false;
+		else
+		{
+			pt_set_inf<N>(R);
+			sc<N> ks;
 #pragma unroll
-		for (int j = 0; j < N; ++j) ks.w[j] = d[j];
-		pt_add_mul_base<N>(R, ks, gtab);
+			for (int j = 0; j < N; ++j) ks.w[j] = d[j];
+			pt_add_mul_base<N>(R, ks, gtab);
+			if (pt_is_inf<N>(R))
+				st = B2G_BAD_PARAMS, live = false;
+		}
 	}
-	if (pt_is_inf<N>(R))
+	fe<N> z;
+	if (live)
+		z = R.Z;
+	else
+		fe_set_u32<N>(z, 1);
+	const fe<N> zi = block_inv<N>(z, tree);
+	if (live)
 	{
-		status[i] = B2G_BAD_PARAMS;
-		return;
+		fe<N> x, y;
+		pt_affine_xy_zi<N>(x, y, R, zi);
+		fe_store<N>(pubkeys + 2 * NO * i, x), fe_store<N>(pubkeys + 2 * NO * i + NO, y);
 	}
-	fe<N> x, y;
-	pt_to_affine<N>(x, y, R);
-	fe_store<N>(pubkeys + 2 * NO * i, x), fe_store<N>(pubkeys + 2 * NO * i + NO, y);
-	status[i] = B2G_OK;
+	if (i < count)
+		status[i] = st;
 }
 
-// ecMulA per item (ec.c:497-525): b = d * a, affine in/out; ok = 0 iff the result is O
+// ecMulA per item (ec.c:497-525): b = d * a, affine in/out; ok = 0 iff the result is O.
+// ecAddMulA with the base point (ec.c:1183-1273) when kbase != 0: b = d * a + k * G.
 template <int N> __global__ void __launch_bounds__(BIGN_THREADS, BIGN_BLOCKS(N))
 ecp_mul_kernel(u8* __restrict__ out, int* __restrict__ ok, const u8* __restrict__ pts,
-	const u8* __restrict__ scalars, u32 d_len, u64 count)
-{
-	constexpr int NO = 4 * N;
-	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= count)
-		return;
-	fe<N> x, y;
-	fe_load<N>(x, pts + 2 * NO * i), fe_load<N>(y, pts + 2 * NO * i + NO);
-	sc<N> k;
-	load_scalar<N>(k, scalars + (u64)d_len * i, d_len);
-	pt<N> R;
-	pt_mul_var<N>(R, k, (int)(8 * d_len), x, y);
-	if (pt_is_inf<N>(R))
-	{
-		ok[i] = 0;
-		return;
-	}
-	pt_to_affine<N>(x, y, R);
-	fe_store<N>(out + 2 * NO * i, x), fe_store<N>(out + 2 * NO * i + NO, y);
-	ok[i] = 1;
-}
-
-// ecAddMulA with the base point (ec.c:1183-1273): b = d * a + k * G; ok = 0 iff the result is O
-template <int N> __global__ void __launch_bounds__(BIGN_THREADS, BIGN_BLOCKS(N))
-ecp_addmul_kernel(u8* __restrict__ out, int* __restrict__ ok, const u8* __restrict__ pts,
 	const u8* __restrict__ scalars, u32 d_len, const u8* __restrict__ kbase, u64 count,
 	const uint4* __restrict__ gtab)
 {
 	constexpr int NO = 4 * N;
+	__shared__ u32 tree[BIGN_TREE_WORDS(N)];
 	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= count)
-		return;
-	fe<N> x, y;
-	fe_load<N>(x, pts + 2 * NO * i), fe_load<N>(y, pts + 2 * NO * i + NO);
-	sc<N> k, kg;
-	load_scalar<N>(k, scalars + (u64)d_len * i, d_len);
-	load_uN<N>(kg.w, kbase + NO * i);
+	bool live = i < count;
 	pt<N> R;
-	pt_mul_var<N>(R, k, (int)(8 * d_len), x, y);
-	pt_add_mul_base<N>(R, kg, gtab);
-	if (pt_is_inf<N>(R))
+	if (live)
 	{
-		ok[i] = 0;
-		return;
+		fe<N> x, y;
+		fe_load<N>(x, pts + 2 * NO * i), fe_load<N>(y, pts + 2 * NO * i + NO);
+		sc<N> k;
+		load_scalar<N>(k, scalars + (u64)d_len * i, d_len);
+		pt_mul_var<N>(R, k, (int)(8 * d_len), x, y);
+		if (kbase)
+		{
+			sc<N> kg;
+			load_uN<N>(kg.w, kbase + NO * i);
+			pt_add_mul_base<N>(R, kg, gtab);
+		}
+		live = !pt_is_inf<N>(R);
 	}
-	pt_to_affine<N>(x, y, R);
-	fe_store<N>(out + 2 * NO * i, x), fe_store<N>(out + 2 * NO * i + NO, y);
-	ok[i] = 1;
+	fe<N> z;
+	if (live)
+		z = R.Z;
+	else
+		fe_set_u32<N>(z, 1);
+	const fe<N> zi = block_inv<N>(z, tree);
+	if (live)
+	{
+		fe<N> x, y;
+		pt_affine_xy_zi<N>(x, y, R, zi);
+		fe_store<N>(out + 2 * NO * i, x), fe_store<N>(out + 2 * NO * i + NO, y);
+	}
+	if (i < count)
+		ok[i] = live ? 1 : 0;
 }
 
 // ---------------------------------------------------------------- launchers (C ABI)
@@ -716,7 +818,7 @@ template <int N> static u32 mul_launch(void* d_b, void* d_ok, const void* d_a, c
 	size_t count, cudaStream_t st)
 {
 	ecp_mul_kernel<N><<<bign_grid(count), BIGN_THREADS, 0, st>>>((u8*)d_b, (int*)d_ok,
-		(const u8*)d_a, (const u8*)d_d, (u32)d_len, count);
+		(const u8*)d_a, (const u8*)d_d, (u32)d_len, (const u8*)0, count, (const uint4*)0);
 	b2g_note_launch();
 	return b2g_check_launch("ecp_mul_kernel");
 }
@@ -747,10 +849,11 @@ template <int N> static u32 addmul_launch(void* d_b, void* d_ok, const void* d_a
 	const uint4* gtab;
 	u32 e = bign_ensure_gtab<N>(st, &gtab);
 	if (e) return e;
-	ecp_addmul_kernel<N><<<bign_grid(count), BIGN_THREADS, 0, st>>>((u8*)d_b, (int*)d_ok, (const u8*)d_a,
+	if (!d_k) return B2G_BAD_INPUT;
+	ecp_mul_kernel<N><<<bign_grid(count), BIGN_THREADS, 0, st>>>((u8*)d_b, (int*)d_ok, (const u8*)d_a,
 		(const u8*)d_d, (u32)d_len, (const u8*)d_k, count, gtab);
 	b2g_note_launch();
-	return b2g_check_launch("ecp_addmul_kernel");
+	return b2g_check_launch("ecp_mul_kernel(+G)");
 }
 
 extern "C" u32 b2g_ecAddMulABatchL_dev(size_t l, void* d_b, void* d_ok, const void* d_a, const void* d_d, size_t d_len,

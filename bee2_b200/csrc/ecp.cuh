@@ -38,25 +38,35 @@ template <int N> GFP_HD void fe_neg(fe<N>& r, const fe<N>& a)
 }
 
 // R = 2P, a = -3 (3M + 5S). Z = 0 or Y = 0 give Z3 = 0 without special casing.
-template <int N> PT_OP void pt_dbl(pt<N>& R, const pt<N>& P)
+// INL: products inlined (hot loop of pt_mul_var: no call, no argument moves, independent products
+// interleave) instead of calls to the shared copies.
+template <int N, bool INL> PT_OP void pt_dbl_t(pt<N>& R, const pt<N>& P)
 {
+#define PM(r, a, b) (INL ? fe_mul_i<N>(r, a, b) : fe_mul<N>(r, a, b))
+#define PS(r, a) (INL ? fe_sqr_i<N>(r, a) : fe_sqr<N>(r, a))
 	fe<N> delta, gamma, beta, alpha, t, u;
-	fe_sqr<N>(delta, P.Z);
-	fe_sqr<N>(gamma, P.Y);
-	fe_mul<N>(beta, P.X, gamma);
+	PS(delta, P.Z);
+	PS(gamma, P.Y);
+	PM(beta, P.X, gamma);
 	fe_sub<N>(t, P.X, delta), fe_add<N>(u, P.X, delta);
-	fe_mul<N>(alpha, t, u);
+	PM(alpha, t, u);
 	fe_dbl<N>(t, alpha), fe_add<N>(alpha, alpha, t);              // 3 (X - Z^2)(X + Z^2)
-	fe_add<N>(t, P.Y, P.Z), fe_sqr<N>(t, t);
+	fe_add<N>(t, P.Y, P.Z), PS(t, t);
 	fe_sub<N>(t, t, gamma), fe_sub<N>(R.Z, t, delta);             // Z3 = (Y + Z)^2 - Y^2 - Z^2
 	fe_shl<2, N>(beta, beta);                                     // 4 beta
-	fe_sqr<N>(t, alpha);
+	PS(t, alpha);
 	fe_sub<N>(t, t, beta), fe_sub<N>(R.X, t, beta);               // X3 = alpha^2 - 8 beta
-	fe_sqr<N>(gamma, gamma);
+	PS(gamma, gamma);
 	fe_shl<3, N>(gamma, gamma);                                   // 8 gamma^2
-	fe_sub<N>(t, beta, R.X), fe_mul<N>(t, alpha, t);
+	fe_sub<N>(t, beta, R.X), PM(t, alpha, t);
 	fe_sub<N>(R.Y, t, gamma);                                     // Y3 = alpha (4 beta - X3) - 8 gamma^2
+#undef PM
+#undef PS
 }
+template <int N> PT_OP void pt_dbl(pt<N>& R, const pt<N>& P) { pt_dbl_t<N, false>(R, P); }
+#ifndef PT_DBL_INLINE
+#define PT_DBL_INLINE 0
+#endif
 // out-of-line copy for the rare P + P branches
 template <int N> __host__ __device__ __noinline__ void pt_dbl_slow(pt<N>* R, const pt<N>* P)
 {
@@ -216,7 +226,7 @@ template <int N> __host__ __device__ __noinline__ void pt_mul_var(pt<N>& acc, co
 		{
 #pragma unroll 1
 			for (int s = 0; s < PT_WIN; ++s)
-				pt_dbl<N>(acc, acc);
+				pt_dbl_t<N, PT_DBL_INLINE != 0>(acc, acc);
 		}
 		const int bit = PT_WIN * i, limb = bit >> 5, sh = bit & 31;
 		u32 w = limb < N ? k[limb] >> sh : 0u;

@@ -13,7 +13,7 @@
 
 enum { MB_LOP3 = 0, MB_SHF = 1, MB_PRMT = 2, MB_IADD3 = 3, MB_IMAD = 4, MB_IMAD_WIDE = 5, MB_LDS = 6, MB_MIX_LOP3_IMADW = 7,
 	MB_MIX_LOP3_IMAD = 8, MB_MIX_LOP3_FFMA = 9, MB_IMAD_HI = 10, MB_MIX_LOP3_LDS = 11, MB_FFMA = 12, MB_DFMA = 13, MB_MIX_DFMA_IMADW = 14, MB_MIX_IMAD_IMADW = 15,
-	MB_MIX_IADDX_IMADW = 16 };
+	MB_MIX_IADDX_IMADW = 16, MB_MADC_ROW = 17, MB_ADDC_ROW = 18, MB_MADWIDE_ROW = 19, MB_MIX_MADC_ADDC = 20, MB_MIX_MADC_2ADDC = 21, MB_MIX_MADWIDE_ADDC = 22 };
 #define MB_IS_MIX(k) ((k) == MB_MIX_LOP3_IMADW || (k) == MB_MIX_LOP3_IMAD || (k) == MB_MIX_LOP3_FFMA || (k) == MB_MIX_LOP3_LDS || \
 	(k) == MB_MIX_DFMA_IMADW || (k) == MB_MIX_IMAD_IMADW || (k) == MB_MIX_IADDX_IMADW)
 
@@ -21,8 +21,9 @@ template <int KIND>
 __global__ void __launch_bounds__(1024) mb_kernel(u32* out, u32 iters, u32 a, u32 b, u32 sh)
 {
 	__shared__ u32 sm[32 * 64];
-	u32 x[MB_ILP], y[MB_ILP];
-	u64 w[MB_ILP];
+	u32 x[MB_ILP], y[MB_ILP], z[MB_ILP], v[MB_ILP];
+	u64 w[MB_ILP], w2[MB_ILP];
+	u32 p0[MB_ILP], p1[MB_ILP], p2[MB_ILP], p3[MB_ILP];
 	float f[MB_ILP];
 	double d[MB_ILP];
 	const double da = 1.0 + 1e-9 * (a & 3), db = 1e-3 * (b & 7);
@@ -33,6 +34,8 @@ __global__ void __launch_bounds__(1024) mb_kernel(u32* out, u32 iters, u32 a, u3
 		x[i] = (KIND == MB_LDS || KIND == MB_MIX_LOP3_LDS) ? ((threadIdx.x + i) & 63u) << 5 : threadIdx.x * 2654435761u + i * a;
 		w[i] = ((u64)x[i] << 32) | (b + i);
 		y[i] = x[i] ^ b, f[i] = (float)(threadIdx.x + i), d[i] = (double)(threadIdx.x + i);
+		z[i] = x[i] + a, v[i] = y[i] + b, w2[i] = w[i] ^ a;
+		p0[i] = x[i] * 3u, p1[i] = y[i] * 5u, p2[i] = x[i] * 7u, p3[i] = y[i] * 9u;
 	}
 	for (u32 i = threadIdx.x; i < 32 * 64; i += blockDim.x)
 		sm[i] = (i * 7 + a) & (63u << 5);   // next index: keeps the lane's own bank (multiple of 32 words)
@@ -95,6 +98,78 @@ __global__ void __launch_bounds__(1024) mb_kernel(u32* out, u32 iters, u32 a, u3
 					asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(x[i]), "+r"(y[i]) : "r"(a), "r"(b));
 					asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(sh), "r"(a));
 				}
+				else if (KIND == MB_MADC_ROW)
+				{
+					// the carry-chained row of gfp_asm.cuh mad_row<4>: 8 wide multiply-adds linked through CC.CF
+					asm volatile("mad.lo.cc.u32 %0, %4, %8, %0;\n\tmadc.hi.cc.u32 %1, %4, %8, %1;\n\t"
+						"madc.lo.cc.u32 %2, %5, %8, %2;\n\tmadc.hi.cc.u32 %3, %5, %8, %3;\n\t"
+						"madc.lo.cc.u32 %0, %6, %8, %0;\n\tmadc.hi.cc.u32 %1, %6, %8, %1;\n\t"
+						"madc.lo.cc.u32 %2, %7, %8, %2;\n\tmadc.hi.cc.u32 %3, %7, %8, %3;\n\t"
+						"madc.lo.cc.u32 %0, %4, %7, %0;\n\tmadc.hi.cc.u32 %1, %4, %7, %1;\n\t"
+						"madc.lo.cc.u32 %2, %5, %6, %2;\n\tmadc.hi.cc.u32 %3, %5, %6, %3;\n\t"
+						"madc.lo.cc.u32 %0, %6, %5, %0;\n\tmadc.hi.cc.u32 %1, %6, %5, %1;\n\t"
+						"madc.lo.cc.u32 %2, %7, %4, %2;\n\tmadc.hi.u32 %3, %7, %4, %3;"
+						: "+r"(x[i]), "+r"(y[i]), "+r"(z[i]), "+r"(v[i]) : "r"(a), "r"(b), "r"(sh), "r"(a ^ b), "r"(b + i));
+				}
+				else if (KIND == MB_MADWIDE_ROW)
+				{
+					// the same 8 products as independent plain wide multiply-adds (no carry links)
+					asm volatile("mad.wide.u32 %0, %2, %6, %0;\n\tmad.wide.u32 %1, %3, %6, %1;\n\t"
+						"mad.wide.u32 %0, %4, %6, %0;\n\tmad.wide.u32 %1, %5, %6, %1;\n\t"
+						"mad.wide.u32 %0, %2, %5, %0;\n\tmad.wide.u32 %1, %3, %4, %1;\n\t"
+						"mad.wide.u32 %0, %4, %3, %0;\n\tmad.wide.u32 %1, %5, %2, %1;"
+						: "+l"(w[i]), "+l"(w2[i]) : "r"(a), "r"(b), "r"(sh), "r"(a ^ b), "r"(b + i));
+				}
+				else if (KIND == MB_ADDC_ROW)
+				{
+					asm volatile("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %5;\n\taddc.cc.u32 %2, %2, %4;\n\taddc.cc.u32 %3, %3, %5;\n\t"
+						"addc.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.cc.u32 %2, %2, %5;\n\taddc.u32 %3, %3, %4;"
+						: "+r"(x[i]), "+r"(y[i]), "+r"(z[i]), "+r"(v[i]) : "r"(a), "r"(b));
+				}
+				else if (KIND == MB_MIX_MADC_ADDC)
+				{
+					asm volatile("mad.lo.cc.u32 %0, %4, %8, %0;\n\tmadc.hi.cc.u32 %1, %4, %8, %1;\n\t"
+						"madc.lo.cc.u32 %2, %5, %8, %2;\n\tmadc.hi.cc.u32 %3, %5, %8, %3;\n\t"
+						"madc.lo.cc.u32 %0, %6, %8, %0;\n\tmadc.hi.cc.u32 %1, %6, %8, %1;\n\t"
+						"madc.lo.cc.u32 %2, %7, %8, %2;\n\tmadc.hi.cc.u32 %3, %7, %8, %3;\n\t"
+						"madc.lo.cc.u32 %0, %4, %7, %0;\n\tmadc.hi.cc.u32 %1, %4, %7, %1;\n\t"
+						"madc.lo.cc.u32 %2, %5, %6, %2;\n\tmadc.hi.cc.u32 %3, %5, %6, %3;\n\t"
+						"madc.lo.cc.u32 %0, %6, %5, %0;\n\tmadc.hi.cc.u32 %1, %6, %5, %1;\n\t"
+						"madc.lo.cc.u32 %2, %7, %4, %2;\n\tmadc.hi.u32 %3, %7, %4, %3;"
+						: "+r"(x[i]), "+r"(y[i]), "+r"(z[i]), "+r"(v[i]) : "r"(a), "r"(b), "r"(sh), "r"(a ^ b), "r"(b + i));
+					asm volatile("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %5;\n\taddc.cc.u32 %2, %2, %4;\n\taddc.cc.u32 %3, %3, %5;\n\t"
+						"addc.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.cc.u32 %2, %2, %5;\n\taddc.u32 %3, %3, %4;"
+						: "+r"(p0[i]), "+r"(p1[i]), "+r"(p2[i]), "+r"(p3[i]) : "r"(a), "r"(b));
+				}
+				else if (KIND == MB_MIX_MADC_2ADDC)
+				{
+					asm volatile("mad.lo.cc.u32 %0, %4, %8, %0;\n\tmadc.hi.cc.u32 %1, %4, %8, %1;\n\t"
+						"madc.lo.cc.u32 %2, %5, %8, %2;\n\tmadc.hi.cc.u32 %3, %5, %8, %3;\n\t"
+						"madc.lo.cc.u32 %0, %6, %8, %0;\n\tmadc.hi.cc.u32 %1, %6, %8, %1;\n\t"
+						"madc.lo.cc.u32 %2, %7, %8, %2;\n\tmadc.hi.cc.u32 %3, %7, %8, %3;\n\t"
+						"madc.lo.cc.u32 %0, %4, %7, %0;\n\tmadc.hi.cc.u32 %1, %4, %7, %1;\n\t"
+						"madc.lo.cc.u32 %2, %5, %6, %2;\n\tmadc.hi.cc.u32 %3, %5, %6, %3;\n\t"
+						"madc.lo.cc.u32 %0, %6, %5, %0;\n\tmadc.hi.cc.u32 %1, %6, %5, %1;\n\t"
+						"madc.lo.cc.u32 %2, %7, %4, %2;\n\tmadc.hi.u32 %3, %7, %4, %3;"
+						: "+r"(x[i]), "+r"(y[i]), "+r"(z[i]), "+r"(v[i]) : "r"(a), "r"(b), "r"(sh), "r"(a ^ b), "r"(b + i));
+					asm volatile("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %5;\n\taddc.cc.u32 %2, %2, %4;\n\taddc.cc.u32 %3, %3, %5;\n\t"
+						"addc.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.cc.u32 %2, %2, %5;\n\taddc.u32 %3, %3, %4;"
+						: "+r"(p0[i]), "+r"(p1[i]), "+r"(p2[i]), "+r"(p3[i]) : "r"(a), "r"(b));
+					asm volatile("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %5;\n\taddc.cc.u32 %2, %2, %4;\n\taddc.cc.u32 %3, %3, %5;\n\t"
+						"addc.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.cc.u32 %2, %2, %5;\n\taddc.u32 %3, %3, %4;"
+						: "+r"(p2[i]), "+r"(p3[i]), "+r"(p0[i]), "+r"(p1[i]) : "r"(a), "r"(b));
+				}
+				else if (KIND == MB_MIX_MADWIDE_ADDC)
+				{
+					asm volatile("mad.wide.u32 %0, %2, %6, %0;\n\tmad.wide.u32 %1, %3, %6, %1;\n\t"
+						"mad.wide.u32 %0, %4, %6, %0;\n\tmad.wide.u32 %1, %5, %6, %1;\n\t"
+						"mad.wide.u32 %0, %2, %5, %0;\n\tmad.wide.u32 %1, %3, %4, %1;\n\t"
+						"mad.wide.u32 %0, %4, %3, %0;\n\tmad.wide.u32 %1, %5, %2, %1;"
+						: "+l"(w[i]), "+l"(w2[i]) : "r"(a), "r"(b), "r"(sh), "r"(a ^ b), "r"(b + i));
+					asm volatile("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %5;\n\taddc.cc.u32 %2, %2, %4;\n\taddc.cc.u32 %3, %3, %5;\n\t"
+						"addc.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.cc.u32 %2, %2, %5;\n\taddc.u32 %3, %3, %4;"
+						: "+r"(p0[i]), "+r"(p1[i]), "+r"(p2[i]), "+r"(p3[i]) : "r"(a), "r"(b));
+				}
 				else if (KIND == MB_IMAD_HI)
 					asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
 				else if (KIND == MB_MIX_LOP3_LDS)
@@ -108,7 +183,7 @@ __global__ void __launch_bounds__(1024) mb_kernel(u32* out, u32 iters, u32 a, u3
 	u32 acc = 0;
 #pragma unroll
 	for (int i = 0; i < MB_ILP; ++i)
-		acc ^= x[i] ^ y[i] ^ __float_as_uint(f[i]) ^ (u32)__double2hiint(d[i]) ^ (u32)__double2loint(d[i]) ^ (u32)w[i] ^ (u32)(w[i] >> 32);
+		acc ^= p0[i] ^ p1[i] ^ p2[i] ^ p3[i] ^ x[i] ^ y[i] ^ z[i] ^ v[i] ^ (u32)w2[i] ^ (u32)(w2[i] >> 32) ^ __float_as_uint(f[i]) ^ (u32)__double2hiint(d[i]) ^ (u32)__double2loint(d[i]) ^ (u32)w[i] ^ (u32)(w[i] >> 32);
 	if (acc == 0x12345678u)
 		out[0] = acc;
 }
@@ -130,7 +205,7 @@ template <int KIND> static double mb_run(u32 iters, u32* d_out)
 	b2g_note_launch(), b2g_note_launch();
 	if (b2g_check_launch("mb_kernel") || ms <= 0)
 		return -1.0;
-	const double per_thread = (double)iters * MB_UNROLL * MB_ILP * (KIND == MB_MIX_IADDX_IMADW ? 3 : MB_IS_MIX(KIND) ? 2 : 1);
+	const double per_thread = (double)iters * MB_UNROLL * MB_ILP * (KIND == MB_MIX_IADDX_IMADW ? 3 : (KIND == MB_MADC_ROW || KIND == MB_ADDC_ROW || KIND == MB_MADWIDE_ROW) ? 8 : (KIND == MB_MIX_MADC_ADDC || KIND == MB_MIX_MADWIDE_ADDC) ? 16 : KIND == MB_MIX_MADC_2ADDC ? 24 : MB_IS_MIX(KIND) ? 2 : 1);
 	return per_thread * 1024.0 * grid / (ms * 1e-3);
 }
 
@@ -161,6 +236,12 @@ extern "C" double b2g_microbench(int kind, unsigned iters)
 	case MB_MIX_LOP3_LDS: r = mb_run<MB_MIX_LOP3_LDS>(iters, d_out); break;
 	case MB_FFMA: r = mb_run<MB_FFMA>(iters, d_out); break;
 	case MB_DFMA: r = mb_run<MB_DFMA>(iters, d_out); break;
+	case MB_MADC_ROW: r = mb_run<MB_MADC_ROW>(iters / 4, d_out); break;
+	case MB_ADDC_ROW: r = mb_run<MB_ADDC_ROW>(iters / 4, d_out); break;
+	case MB_MADWIDE_ROW: r = mb_run<MB_MADWIDE_ROW>(iters / 4, d_out); break;
+	case MB_MIX_MADC_ADDC: r = mb_run<MB_MIX_MADC_ADDC>(iters / 8, d_out); break;
+	case MB_MIX_MADC_2ADDC: r = mb_run<MB_MIX_MADC_2ADDC>(iters / 8, d_out); break;
+	case MB_MIX_MADWIDE_ADDC: r = mb_run<MB_MIX_MADWIDE_ADDC>(iters / 8, d_out); break;
 	case MB_MIX_DFMA_IMADW: r = mb_run<MB_MIX_DFMA_IMADW>(iters, d_out); break;
 	case MB_MIX_IMAD_IMADW: r = mb_run<MB_MIX_IMAD_IMADW>(iters, d_out); break;
 	case MB_MIX_IADDX_IMADW: r = mb_run<MB_MIX_IADDX_IMADW>(iters, d_out); break;

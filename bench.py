@@ -410,7 +410,8 @@ def main():
     if rank == 0:
         for name, kind in (("lop3", 0), ("shf", 1), ("prmt", 2), ("imad", 4), ("imad_wide", 5), ("lds32", 6), ("lop3+imad_wide", 7),
                            ("lop3+imad", 8), ("lop3+ffma", 9), ("imad_hi", 10), ("lop3+lds32", 11), ("ffma", 12), ("dfma", 13), ("dfma+imad_wide", 14),
-                           ("imad+imad_wide", 15), ("2iadd.x+imad_wide", 16)):
+                           ("imad+imad_wide", 15), ("2iadd.x+imad_wide", 16), ("imad_wide.cc chain", 17),
+                           ("iadd3.cc chain", 18), ("imad_wide x8", 19)):
             issue[name] = b.b2g_microbench(kind, 0) / 1e12
     arm = None
     if rank == 0 and not args.no_cpu_baseline:
