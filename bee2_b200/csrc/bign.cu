@@ -18,6 +18,7 @@
 //   * variable base Q: signed 5-bit windows, per-thread table {1..16}Q in local memory
 //     (ecp.cuh pt_mul_var) -> 5 doublings + 1 addition per window.
 // The reference's interleaved wNAF (ec.c:1206-1268) is irregular and would diverge.
+#include <atomic>
 #include <mutex>
 #include "ecp.cuh"
 #include "belt_dev.cuh"
@@ -70,7 +71,7 @@ template <> struct bign_c<16>
 };
 
 // device: BIGN_GN(N) * BIGN_GE entries of 8 N octets (x || y) per level; entry j = 0 unused
-static uint4* g_gtab[3];
+static std::atomic<uint4*> g_gtab[3];
 
 struct OidArg { u8 der[BIGN_MAX_OID]; u32 len; };
 struct TArg { u8 t[BIGN_MAX_T]; u32 len; };
@@ -652,7 +653,7 @@ ecp_mul_kernel(u8* __restrict__ out, int* __restrict__ ok, const u8* __restrict_
 // q and yG are static constants, GTAB is built lazily; only the belt S-box needs uploading
 extern "C" u32 b2g_bign_upload_tables(const u8 H[256]) { return belt_upload_H(H); }
 
-template <int N> static u32 bign_build_gtab(cudaStream_t st, uint4** slot)
+template <int N> static u32 bign_build_gtab(cudaStream_t st, uint4** out)
 {
 	uint4* p = 0;
 	const size_t entries = (size_t)BIGN_GN(N) * BIGN_GE;
@@ -673,24 +674,28 @@ template <int N> static u32 bign_build_gtab(cudaStream_t st, uint4** slot)
 		cudaFree(p);
 		return e ? e : B2G_ERR_CUDA;
 	}
-	*slot = p;
+	*out = p;
 	return B2G_OK;
 }
 // the device entry points may be called from several host threads: build each table once
+// (published with release / read with acquire; lives until the process exits)
 template <int N> static u32 bign_ensure_gtab(cudaStream_t st, const uint4** out)
 {
 	static std::mutex mu;
-	uint4** slot = &g_gtab[N / 4 - 2];
-	if (!*slot)
+	std::atomic<uint4*>& slot = g_gtab[N / 4 - 2];
+	uint4* p = slot.load(std::memory_order_acquire);
+	if (!p)
 	{
 		std::lock_guard<std::mutex> lock(mu);
-		if (!*slot)
+		p = slot.load(std::memory_order_relaxed);
+		if (!p)
 		{
-			const u32 e = bign_build_gtab<N>(st, slot);
+			const u32 e = bign_build_gtab<N>(st, &p);
 			if (e) return e;
+			slot.store(p, std::memory_order_release);
 		}
 	}
-	*out = *slot;
+	*out = p;
 	return B2G_OK;
 }
 

@@ -44,12 +44,16 @@ CFG = {
     "bign_verify": dict(metric="bign-curve256v1 verifies/s", unit="verifies/s",
                         workload="bign-curve256v1 batch verify: 2^18 signatures per GPU (1/16 corrupted)",
                         units=1 << 18, unit_bytes=148, dtype="u32"),
+    "bign_sign2": dict(metric="bign-curve256v1 deterministic signatures/s", unit="signatures/s",
+                       workload="bign-curve256v1 batch bignSign2: 2^18 (hash, private key) pairs per GPU",
+                       units=1 << 18, unit_bytes=112, dtype="u32"),
 }
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the bench
 # configuration, from the committed `ncu --set full` captures (profiles/r01_ncu_raw_*.csv)
-NCU_TRAFFIC = {"belt_dwp": None, "belt_ecb": None, "belt_ctr": 0.13e6 + 1.0142e9, "bash512": 4.4244e9 + 14.5e6, "bign_verify": 151.7e6 + 340.8e6}
+NCU_BIGN_WIDE_PER_VERIFY = 103300   # IMAD.WIDE(.X) executed per verify (profiles/r01_bign_opcode_mix.json)
+NCU_TRAFFIC = {"bign_sign2": 29.4e6 + 66.6e6, "belt_dwp": None, "belt_ecb": None, "belt_ctr": 0.13e6 + 1.0142e9, "bash512": 4.4244e9 + 14.5e6, "bign_verify": 2.0209e9 + 515.6e6}
 
 
 def hbm_peak():
@@ -187,6 +191,17 @@ class CpuArm:
             dt, _ = self.bash(msgs)
             state["last"] = msgs
             units, desc = n * 4096, f"{n} messages x 4 KiB via bashHash ({self.bash_name})"
+        elif path == "bign_sign2":
+            n = 16 * self.threads if rate is None else int(min(max(rate * target_s, 16), 1 << 18))
+            key = ("keys", n)
+            if key not in state:
+                priv = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+                priv[:, 31] &= 0x7F
+                state[key] = (rng.integers(0, 256, (n, 32), dtype=np.uint8), priv)
+            dt, st, _ = self.sign2(*state[key])
+            state["last"] = state[key]
+            assert not st.any()
+            units, desc = n, f"{n} signatures via " + ("bign128Sign2" if not self.is_port else "orc_bignSign2_128")
         else:
             n = 16 * self.threads if rate is None else int(min(max(rate * target_s, 16), 1 << 18))
             key = ("sigs", n)
@@ -228,6 +243,8 @@ class CpuArm:
             return self.ecb_multikey(*last)
         if path == "belt_dwp":
             return self.belt_dwp(last, bytes(range(32)), bytes(16))
+        if path == "bign_sign2":
+            return self.sign2(*last)[0]
         return self.verify(*last)[0]
 
     def baseline(self, path, target_s=4.0):
@@ -321,7 +338,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--paths", default="belt_ctr,bash512,bign_verify,belt_ecb,belt_dwp",
+    ap.add_argument("--paths", default="belt_ctr,bash512,bign_verify,belt_ecb,belt_dwp,bign_sign2",
                     help="comma list; the first one is the headline metric of the JSON line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -553,6 +570,35 @@ def main():
                 assert np.array_equal(ho[:4096], out[:4096].cpu().numpy())
                 del hmsgs, hout, hm, ho
             del msgs, out
+        elif path == "bign_sign2":
+            rng = np.random.default_rng(20 + rank)
+            priv = rng.integers(0, 256, (units, 32), dtype=np.uint8)
+            priv[:, 31] &= 0x7F
+            hashes = rng.integers(0, 256, (units, 32), dtype=np.uint8)
+            params = b.bignParamsStd()
+            oid = shard.broadcast_bytes(OID if rank == 0 else None, len(OID), device=dev)
+            d_h, d_k = (torch.from_numpy(x).to(dev) for x in (hashes, priv))
+            d_sig = torch.zeros(units * 48, dtype=torch.uint8, device=dev)
+            d_st = torch.empty(units, dtype=torch.int32, device=dev)
+            fn = lambda: b.bignSign2Batch_dev(d_st.data_ptr(), d_sig.data_ptr(), oid, d_h.data_ptr(), d_k.data_ptr(), units, stream)  # noqa: E731
+            total, launches = timed(fn, args.steps, args.warmup, flush=True)
+            r["l2"] = "inputs 16 MiB < L2: 256 MiB flush write between steps (outside the events)"
+            algo_bytes = units * 112
+            assert not d_st.cpu().numpy().any(), "sign2 statuses off"
+            # parity on the spot: the signatures verify on the device
+            d_pub = torch.zeros(units * 64, dtype=torch.uint8, device=dev)
+            b.bignPubkeyCalcBatch_dev(d_st.data_ptr(), d_pub.data_ptr(), d_k.data_ptr(), units, stream)
+            b.bignVerifyBatch_dev(d_st.data_ptr(), oid, d_h.data_ptr(), d_sig.data_ptr(), d_pub.data_ptr(), units, stream)
+            assert not d_st.cpu().numpy().any(), "signatures do not verify"
+            r["checksum"] = int(d_sig[:: 97].to(torch.int64).sum().item())
+            if not args.no_e2e:
+                ph, pk = (torch.from_numpy(x).pin_memory() for x in (hashes, priv))
+                nh, nk = ph.numpy(), pk.numpy()
+                e2e_fn = lambda: b.bignSign2Batch(params, oid, nh, nk)  # noqa: E731
+                t = timed_host(e2e_fn, e2e_steps, 1)
+                r["e2e"] = {"value": world * units * e2e_steps / t / scale, "unit": cfg["unit"],
+                            "h2d_bytes_per_step": units * 64, "d2h_bytes_per_step": units * 52,
+                            "call": "bignSign2Batch(pinned host hashes/privkeys -> sigs[], status[])", "steps": e2e_steps}
         else:
             # inputs made by the engine's own batch signer (parity-tested against the oracle), then
             # 1/16 of the items corrupted
@@ -633,6 +679,22 @@ def main():
         r["issue_roofline"] = {"bound": "imad.wide (2000 field mults x 72 wide multiply-adds per verify, SURVEY §8d)",
                                "achieved_Tops": v_s * 144000 / 1e12, "peak_Tops": issue.get("imad_wide"),
                                "frac": v_s * 144000 / 1e12 / issue["imad_wide"] if issue.get("imad_wide", 0) > 0 else None}
+    if "bign_verify" in results and issue.get("imad_wide.cc chain", 0) > 0:
+        # what the kernel really issues: carry-chained IMAD.WIDE.X runs at half the rate of the plain
+        # form (microbench "imad_wide.cc chain"); executed count per verify from the committed ncu
+        # source-page capture (profiles/README.md)
+        v_s = results["bign_verify"]["value"] / world
+        results["bign_verify"]["issue_roofline"]["carry_chain"] = {
+            "executed_wide_mads_per_verify": NCU_BIGN_WIDE_PER_VERIFY, "achieved_Tops": v_s * NCU_BIGN_WIDE_PER_VERIFY / 1e12,
+            "peak_Tops": issue["imad_wide.cc chain"], "frac": v_s * NCU_BIGN_WIDE_PER_VERIFY / 1e12 / issue["imad_wide.cc chain"]}
+    if "bign_sign2" in results:
+        r = results["bign_sign2"]
+        v_s = r["value"] / world
+        # 20 mixed additions (7M + 4S) from the fixed-base table + 2 log2(128) tree products + x = X/Z^2:
+        # ~240 field products x 72 wide multiply-adds
+        r["issue_roofline"] = {"bound": "imad.wide (240 field mults x 72 wide multiply-adds per signature)",
+                               "achieved_Tops": v_s * 240 * 72 / 1e12, "peak_Tops": issue.get("imad_wide"),
+                               "frac": v_s * 240 * 72 / 1e12 / issue["imad_wide"] if issue.get("imad_wide", 0) > 0 else None}
     if arm is not None:
         for path in args.paths:
             results[path]["cpu_baseline"] = arm.baseline(path)
