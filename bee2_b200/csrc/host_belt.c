@@ -428,27 +428,54 @@ static err_t dwp_run(void* dest, octet mac_out[8], const void* src1, size_t coun
 	if ((code = b2g_slot_buf(sl, 0, (count1 + 15) & ~(size_t)15, &d_crit)) ||
 		(code = b2g_slot_buf(sl, 1, count2, &d_open)) || (code = b2g_slot_buf(sl, 2, 64, &d_small)))
 		goto done;
-	if (count1)
-		CU(cudaMemcpyAsync(d_crit, src1, count1, cudaMemcpyHostToDevice, sl->stream), "H2D(dwp data)");
 	if (count2)
 		CU(cudaMemcpyAsync(d_open, src2, count2, cudaMemcpyHostToDevice, sl->stream), "H2D(dwp open)");
 	if (!expect_mac)
 	{
-		/* wrap: encrypt, then authenticate the ciphertext (belt_dwp.c:277-282) */
-		if (count1 && (code = crypt(d_crit, d_crit, count1, st.key, st.ctr, 0, sl->stream)))
-			goto done;
+		/* wrap: encrypt, then authenticate the ciphertext (belt_dwp.c:277-282). The critical data
+		   move in chunks that alternate between the two streams — upload, encrypt (counter offset =
+		   chunk offset) and download of one chunk overlap the neighbours' transfers in the other PCIe
+		   direction — while the ciphertext stays resident for ONE tag launch over the whole buffer. */
+		b2g_slot* s2 = b2g_slot_get(1);
+		const size_t chunk = b2g_chunk_units(16, CHUNK_BYTES) * 16;
+		size_t off, c;
+		cudaEvent_t ev;
+		for (off = 0, c = 0; off < count1; off += chunk, ++c)
+		{
+			const size_t n = count1 - off < chunk ? count1 - off : chunk;
+			cudaStream_t stc = (c & 1) ? s2->stream : sl->stream;
+			octet* d = (octet*)d_crit + off;
+			CU(cudaMemcpyAsync(d, (const octet*)src1 + off, n, cudaMemcpyHostToDevice, stc), "H2D(dwp data)");
+			if ((code = crypt(d, d, n, st.key, st.ctr, off / 16, stc)))
+				goto done;
+			CU(cudaMemcpyAsync((octet*)dest + off, d, n, cudaMemcpyDeviceToHost, stc), "D2H(dwp data)");
+		}
+		if (c > 1)
+		{
+			/* the tag pass (first stream) reads what the second stream encrypted */
+			CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate(dwp)");
+			if (cudaEventRecord(ev, s2->stream) != cudaSuccess || cudaStreamWaitEvent(sl->stream, ev, 0) != cudaSuccess)
+			{
+				code = b2g_check_launch("event(dwp)");
+				cudaEventDestroy(ev);
+				if (!code) code = ERR_B2G_CUDA;
+				goto done;
+			}
+			cudaEventDestroy(ev);
+		}
 		if ((code = tag(d_small, d_crit, count1, d_open, count2, st.key, st.ctr,
 				(octet*)d_small + 16, sl->stream)))
 			goto done;
 		CU(cudaMemcpyAsync(mac, d_small, 8, cudaMemcpyDeviceToHost, sl->stream), "D2H(dwp mac)");
-		if (count1)
-			CU(cudaMemcpyAsync(dest, d_crit, count1, cudaMemcpyDeviceToHost, sl->stream), "D2H(dwp data)");
 		CU(cudaStreamSynchronize(sl->stream), "sync(dwp)");
+		CU(cudaStreamSynchronize(s2->stream), "sync(dwp)");
 		memcpy(mac_out, mac, 8);
 	}
 	else
 	{
 		/* unwrap: check the tag first; a wrong tag leaves dest untouched (belt_dwp.c:316-324) */
+		if (count1)
+			CU(cudaMemcpyAsync(d_crit, src1, count1, cudaMemcpyHostToDevice, sl->stream), "H2D(dwp data)");
 		if ((code = tag(d_small, d_crit, count1, d_open, count2, st.key, st.ctr,
 				(octet*)d_small + 16, sl->stream)))
 			goto done;
@@ -469,7 +496,7 @@ static err_t dwp_run(void* dest, octet mac_out[8], const void* src1, size_t coun
 	}
 done:
 	if (code && code != ERR_BAD_MAC)
-		cudaStreamSynchronize(sl->stream);
+		cudaStreamSynchronize(sl->stream), cudaStreamSynchronize(b2g_slot_get(1)->stream);
 	b2g_unlock();
 	return code;
 }

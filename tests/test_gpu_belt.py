@@ -112,6 +112,22 @@ def test_dwp_che_random_sizes_vs_oracle(mode):
             assert unwrap(want[0], op[:-1] + bytes([op[-1] ^ 1]), want[1], key, iv)[0] == b.ERR_BAD_MAC
 
 
+@pytest.mark.parametrize("mode", ["DWP", "CHE"])
+def test_dwp_che_multi_chunk_pipeline(mode):
+    """More than two 32 MiB pipeline stages with a ragged tail: the chunks are encrypted on alternating
+    streams from their own counter offsets and authenticated by one tag launch over the whole buffer."""
+    rng = np.random.default_rng(77)
+    n1, n2 = (70 << 20) + 13, 4097
+    key = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+    iv = rng.integers(0, 256, 16, dtype=np.uint8).tobytes()
+    a = rng.integers(0, 256, n1, dtype=np.uint8).tobytes()
+    op = rng.integers(0, 256, n2, dtype=np.uint8).tobytes()
+    want = getattr(o, f"belt{mode}Wrap")(a, op, key, iv)
+    got = getattr(b, f"belt{mode}Wrap")(a, op, key, iv)
+    assert got[1] == want[1] and got[0] == want[0]
+    assert getattr(b, f"belt{mode}Unwrap")(want[0], op, want[1], key, iv) == (0, a)
+
+
 def test_che_sharded_by_block_offset():
     """belt-CHE gamma from any block offset equals the slice of the whole stream (multi-GPU sharding)."""
     torch = pytest.importorskip("torch")
