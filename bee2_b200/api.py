@@ -20,7 +20,7 @@ __all__ = [
     "bashF", "bashHash", "bashHashBatch", "bashHashBatchV", "bashFBatch", "BashHash",
     "beltH", "beltKeyExpand2", "beltBlockEncr", "beltBlockDecr", "beltECBEncr", "beltECBDecr",
     "beltECBEncrBatch", "BeltECB", "BeltCTR", "beltCTR", "beltCTRKeystream", "beltHash", "beltHashBatch",
-    "beltDWPWrap", "beltDWPUnwrap", "beltDWPMac_dev", "beltCHEWrap", "beltCHEUnwrap", "beltCHE_dev",
+    "beltDWPWrap", "beltDWPUnwrap", "BeltDWP", "beltDWPMac_dev", "beltCHEWrap", "beltCHEUnwrap", "beltCHE_dev",
     "bignParamsStd", "bignVerify", "bignVerifyBatch", "bignSign2", "bignSign2Batch",
     "bignPubkeyCalc", "bignPubkeyCalcBatch", "ecMulABatch", "ecAddMulABatch", "OID_BELT_HASH_DER",
     "bashHashBatch_dev", "bashFBatch_dev", "beltCTR_dev", "beltECB_dev", "beltECBEncrBatch_dev",
@@ -112,6 +112,11 @@ def _declare(L: C.CDLL) -> None:
         "beltCTRKeystream": (u32, [vp, sz, vp, sz, vp]), "beltECBEncrBatch": (u32, [vp, vp, sz]),
         "beltHashBatch": (u32, [vp, vp, sz, sz, sz]),
         "beltDWPWrap": (u32, [vp, vp, vp, sz, vp, sz, vp, sz, vp]),
+        **{f"belt{m}_keep": (sz, []) for m in ("DWP", "CHE")},
+        **{f"belt{m}Start": (None, [vp, vp, sz, vp]) for m in ("DWP", "CHE")},
+        **{f"belt{m}Step{x}": (None, [vp, sz, vp]) for m in ("DWP", "CHE") for x in "EDIA"},
+        **{f"belt{m}StepG": (None, [vp, vp]) for m in ("DWP", "CHE")},
+        **{f"belt{m}StepV": (ci, [vp, vp]) for m in ("DWP", "CHE")},
         "beltDWPUnwrap": (u32, [vp, vp, sz, vp, sz, vp, vp, sz, vp]),
         "beltCHEWrap": (u32, [vp, vp, vp, sz, vp, sz, vp, sz, vp]),
         "beltCHEUnwrap": (u32, [vp, vp, sz, vp, sz, vp, vp, sz, vp]),
@@ -386,6 +391,46 @@ class BeltCTR:
     @property
     def ctr_words(self) -> np.ndarray:
         return self.state[32:48].view(np.uint32).copy()
+
+
+class BeltDWP:
+    """beltDWPStart/StepE/StepI/StepA/StepD/StepG/StepV (belt.h:850-983); ``mode="CHE"`` binds the
+    belt-CHE twins. Step methods take bytes and return bytes where data are transformed."""
+
+    def __init__(self, key: bytes, iv: bytes, mode: str = "DWP"):
+        self.L, self.pre = lib(), f"belt{mode}"
+        self.state = np.zeros(getattr(self.L, self.pre + "_keep")(), dtype=np.uint8)
+        k, p, n = _buf(key)
+        k2, ivp, _ = _buf(iv)
+        getattr(self.L, self.pre + "Start")(self.state.ctypes.data, p, n, ivp)
+
+    def _xform(self, which: str, data: bytes) -> bytes:
+        buf = np.frombuffer(bytes(data), dtype=np.uint8).copy()
+        getattr(self.L, self.pre + which)(buf.ctypes.data if buf.size else 0, buf.size, self.state.ctypes.data)
+        return buf.tobytes()
+
+    def step_e(self, data: bytes) -> bytes:
+        return self._xform("StepE", data)
+
+    def step_d(self, data: bytes) -> bytes:
+        return self._xform("StepD", data)
+
+    def step_i(self, data: bytes) -> None:
+        k, p, n = _buf(data)
+        getattr(self.L, self.pre + "StepI")(p, n, self.state.ctypes.data)
+
+    def step_a(self, data: bytes) -> None:
+        k, p, n = _buf(data)
+        getattr(self.L, self.pre + "StepA")(p, n, self.state.ctypes.data)
+
+    def step_g(self) -> bytes:
+        mac = _out(8)
+        getattr(self.L, self.pre + "StepG")(mac.ctypes.data, self.state.ctypes.data)
+        return mac.tobytes()
+
+    def step_v(self, mac: bytes) -> bool:
+        k, p, n = _buf(mac)
+        return bool(getattr(self.L, self.pre + "StepV")(p, self.state.ctypes.data))
 
 
 def beltCTR(src, key: bytes, iv: bytes, out: Optional[np.ndarray] = None):

@@ -30,6 +30,9 @@ struct DwpArgs
 	uint4 s;           // E_K(iv)
 	u32 r_is_s;        // belt-CHE: r = s = E_K(iv) (belt_che.c:54-57); belt-DWP: r = E_K(s)
 	u32* acc;          // 4 words, zeroed: XOR of the weighted chunk values
+	uint4 t0;          // streaming form: running value t the chain starts from ...
+	u32 t0_given;      // ... instead of t_0 = beltH()[0..16)
+	u32 no_len;        // streaming form: no length block after the data
 };
 
 // block i (0-based) of the sequence open || critical || length, zero-padded
@@ -100,10 +103,12 @@ __global__ void __launch_bounds__(DWP_THREADS) belt_dwp_mac_kernel(const DwpArgs
 		gf128 acc = {{0, 0, 0, 0}};
 		if (j == 0)
 		{
-			// t_0 = beltH()[0..16) (belt_dwp.c:60)
+			// t_0 = beltH()[0..16) (belt_dwp.c:60), or the running t of a streaming state
 			const u32* H32 = reinterpret_cast<const u32*>(c_beltH);
 #pragma unroll
 			for (int i = 0; i < 4; ++i) acc.w[i] = H32[i];
+			if (a.t0_given)
+				acc.w[0] = a.t0.x, acc.w[1] = a.t0.y, acc.w[2] = a.t0.z, acc.w[3] = a.t0.w;
 		}
 #pragma unroll 1
 		for (u64 i = b0; i < b1; ++i)
@@ -179,6 +184,7 @@ static u32 dwp_mac_launch(void* d_mac, const void* d_crit, size_t n1, const void
 	DwpArgs a;
 	a.open = (const u8*)d_open, a.n2 = n2, a.crit = (const u8*)d_crit, a.n1 = n1;
 	a.nI = ((u64)n2 + 15) / 16, a.nA = ((u64)n1 + 15) / 16, a.N = a.nI + a.nA + 1;
+	a.t0 = make_uint4(0, 0, 0, 0), a.t0_given = 0, a.no_len = 0;
 	for (int i = 0; i < 8; ++i) a.key.k[i] = key[i];
 	a.s = make_uint4(ctr0[0], ctr0[1], ctr0[2], ctr0[3]);
 	a.acc = (u32*)d_scratch;
@@ -198,4 +204,44 @@ static u32 dwp_mac_launch(void* d_mac, const void* d_crit, size_t n1, const void
 	belt_dwp_fin_kernel<<<1, 32, 0, st>>>((u8*)d_mac, (const u32*)d_scratch, a.key);
 	b2g_note_launch();
 	return b2g_check_launch("belt_dwp_fin_kernel");
+}
+
+// Streaming form (beltDWPStepI / StepA / StepG, belt_dwp.c:73-207; belt-CHE twins belt_che.c:122-239):
+// t <- Horner(t; blocks) with the given r, over nbytes octets (zero-padded to whole blocks), no length
+// block, no final encryption. d_t receives the 16 octets of the new t.
+extern "C" u32 b2g_beltPolyAbsorb_dev(void* d_t, const void* d_blocks, size_t nbytes, const u32 r[4],
+	const u32 t0[4], void* d_scratch, void* stream)
+{
+	u32 e = b2g_ensure_device();
+	if (e) return e;
+	if (((uintptr_t)d_scratch & 3) || ((uintptr_t)d_t & 3)) return B2G_BAD_INPUT;
+	cudaStream_t st = (cudaStream_t)stream;
+	DwpArgs a;
+	a.open = 0, a.n2 = 0, a.crit = (const u8*)d_blocks, a.n1 = nbytes;
+	a.nI = 0, a.nA = ((u64)nbytes + 15) / 16, a.N = a.nA;
+	for (int i = 0; i < 8; ++i) a.key.k[i] = 0;
+	a.s = make_uint4(r[0], r[1], r[2], r[3]);
+	a.r_is_s = 1;
+	a.t0 = make_uint4(t0[0], t0[1], t0[2], t0[3]), a.t0_given = 1, a.no_len = 1;
+	a.acc = (u32*)d_scratch;
+	if (a.N == 0)
+	{
+		if (cudaMemcpyAsync(d_t, t0, 16, cudaMemcpyHostToDevice, st) != cudaSuccess)
+			return b2g_check_launch("cudaMemcpyAsync(poly t)");
+		return B2G_OK;
+	}
+	const u64 tmax = (u64)b2g_sm_count() * 2 * DWP_THREADS;
+	u64 K = (a.N + tmax - 1) / tmax;
+	if (K < DWP_MIN_CHUNK) K = DWP_MIN_CHUNK;
+	a.K = K;
+	const u64 nthreads = (a.N + K - 1) / K;
+	const u32 grid = (u32)((nthreads + DWP_THREADS - 1) / DWP_THREADS);
+	if (cudaMemsetAsync(d_scratch, 0, 16, st) != cudaSuccess)
+		return b2g_check_launch("cudaMemsetAsync(poly)");
+	belt_dwp_mac_kernel<<<grid, DWP_THREADS, GF_TAB_BYTES + 2048, st>>>(a);
+	b2g_note_launch();
+	if ((e = b2g_check_launch("belt_dwp_mac_kernel(absorb)"))) return e;
+	if (cudaMemcpyAsync(d_t, d_scratch, 16, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+		return b2g_check_launch("cudaMemcpyAsync(poly t)");
+	return B2G_OK;
 }

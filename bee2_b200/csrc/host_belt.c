@@ -501,6 +501,319 @@ done:
 	return code;
 }
 
+/* ---------------------------------------------------------------- belt-DWP / belt-CHE, streaming forms
+   (belt_dwp.c:27-207, belt_che.c:27-239). State layouts follow the reference's belt_dwp_st /
+   belt_che_st field for field (without the multiplication stack, which lives on the device here). The
+   block chain t <- (t ^ B) * r of every StepI / StepA / StepG call runs on the device
+   (b2g_beltPolyAbsorb_dev); the host side only buffers ragged tails and counts bits. */
+typedef struct
+{
+	belt_ctr_st ctr[1];
+	u32 r[4], t[4], t1[4];
+	u32 len[4];            /* bits of open data (low half) || bits of critical data (high half) */
+	octet block[16];
+	size_t filled;
+} belt_dwp_st;
+
+typedef struct
+{
+	u32 key[8];
+	u32 s[4];
+	u32 r[4], t[4], t1[4];
+	u32 len[4];
+	octet block[16];       /* pending authenticated data */
+	octet block1[16];      /* keystream block */
+	size_t filled;
+	size_t reserved;
+} belt_che_st;
+
+/* the part both states share once located: r, t, t1, len, block, filled */
+typedef struct { u32 *r, *t, *t1, *len; octet* block; size_t* filled; const u32* key; } aead_view;
+
+static aead_view dwp_view(belt_dwp_st* st)
+{
+	aead_view v = {st->r, st->t, st->t1, st->len, st->block, &st->filled, st->ctr->key};
+	return v;
+}
+static aead_view che_view(belt_che_st* st)
+{
+	aead_view v = {st->r, st->t, st->t1, st->len, st->block, &st->filled, st->key};
+	return v;
+}
+
+/* t <- Horner(t; head16 (optional) || data[0..nbytes)), nbytes a multiple of 16 */
+static err_t poly_absorb(u32 t[4], const u32 r[4], const octet* head16, const octet* data, size_t nbytes)
+{
+	err_t code;
+	b2g_slot* sl;
+	void *d, *d_small;
+	const size_t total = nbytes + (head16 ? 16 : 0);
+	if (!total)
+		return ERR_OK;
+	if ((code = b2g_ensure_device()))
+		return code;
+	b2g_lock();
+	sl = b2g_slot_get(0);
+	if ((code = b2g_slot_buf(sl, 0, total, &d)) || (code = b2g_slot_buf(sl, 2, 64, &d_small)))
+		goto done;
+	if (head16)
+		CU(cudaMemcpyAsync(d, head16, 16, cudaMemcpyHostToDevice, sl->stream), "H2D(poly head)");
+	if (nbytes)
+		CU(cudaMemcpyAsync((octet*)d + (head16 ? 16 : 0), data, nbytes, cudaMemcpyHostToDevice, sl->stream), "H2D(poly data)");
+	if ((code = b2g_beltPolyAbsorb_dev(d_small, d, total, r, t, (octet*)d_small + 16, sl->stream)))
+		goto done;
+	CU(cudaMemcpyAsync(t, d_small, 16, cudaMemcpyDeviceToHost, sl->stream), "D2H(poly t)");
+	CU(cudaStreamSynchronize(sl->stream), "sync(poly)");
+done:
+	if (code)
+		cudaStreamSynchronize(sl->stream);
+	b2g_unlock();
+	return code;
+}
+
+/* half <- half + 8 count mod 2^64 (beltHalfBlockAddBitSizeW, belt_lcl.c:53-98) */
+static void add_bit_size(u32 half[2], size_t count)
+{
+	u64 v = (u64)half[0] | (u64)half[1] << 32;
+	v += (u64)count << 3;
+	half[0] = (u32)v, half[1] = (u32)(v >> 32);
+}
+
+/* the common tail of StepI / StepA (belt_dwp.c:81-113, :131-163): complete a pending block, run the
+   whole blocks, keep the ragged rest */
+static void aead_absorb(aead_view v, const void* buf, size_t count, const char* who)
+{
+	const octet* p = (const octet*)buf;
+	const octet* head = 0;
+	size_t full;
+	err_t code;
+	if (*v.filled)
+	{
+		if (count < 16 - *v.filled)
+		{
+			memcpy(v.block + *v.filled, p, count);
+			*v.filled += count;
+			return;
+		}
+		memcpy(v.block + *v.filled, p, 16 - *v.filled);
+		count -= 16 - *v.filled, p += 16 - *v.filled;
+		*v.filled = 0;
+		head = v.block;
+	}
+	full = count & ~(size_t)15;
+	if ((code = poly_absorb(v.t, v.r, head, p, full)))
+		b2g_die(who, code);
+	p += full, count -= full;
+	if (count)
+		memcpy(v.block, p, *v.filled = count);
+}
+
+static void aead_step_i(aead_view v, const void* buf, size_t count, const char* who)
+{
+	add_bit_size(v.len, count);
+	aead_absorb(v, buf, count, who);
+}
+
+static void aead_step_a(aead_view v, const void* buf, size_t count, const char* who)
+{
+	/* first non-empty fragment of critical data: close the open data with zeros (belt_dwp.c:121-131) */
+	if (count && v.len[2] == 0 && v.len[3] == 0 && *v.filled)
+	{
+		err_t code;
+		memset(v.block + *v.filled, 0, 16 - *v.filled);
+		if ((code = poly_absorb(v.t, v.r, v.block, 0, 0)))
+			b2g_die(who, code);
+		*v.filled = 0;
+	}
+	add_bit_size(v.len + 2, count);
+	aead_absorb(v, buf, count, who);
+}
+
+/* t1 <- E_K(((t [^ padded block] * r) ^ len) * r); t itself is kept (belt_dwp.c:172-196) */
+static void aead_step_g(aead_view v, const char* who)
+{
+	octet tail[32];
+	size_t n = 0;
+	err_t code;
+	if (*v.filled)
+	{
+		memcpy(tail, v.block, *v.filled);
+		memset(tail + *v.filled, 0, 16 - *v.filled);
+		n = 16;
+	}
+	memcpy(tail + n, v.len, 16), n += 16;
+	memcpy(v.t1, v.t, 16);
+	if ((code = poly_absorb(v.t1, v.r, 0, tail, n)) || (code = blocks_small(v.t1, 1, v.key, 0)))
+		b2g_die(who, code);
+}
+
+size_t beltDWP_keep(void) { return sizeof(belt_dwp_st); }
+
+void beltDWPStart(void* state, const octet key[], size_t len, const octet iv[16])
+{
+	belt_dwp_st* st = (belt_dwp_st*)state;
+	err_t code;
+	beltCTRStart(st->ctr, key, len, iv);
+	/* r <- E_K(s), t <- beltH()[0..16) (belt_dwp.c:50-60) */
+	memcpy(st->r, st->ctr->ctr, 16);
+	if ((code = blocks_small(st->r, 1, st->ctr->key, 0)))
+		b2g_die("beltDWPStart", code);
+	memcpy(st->t, beltH(), 16);
+	memset(st->len, 0, sizeof st->len);
+	st->filled = 0;
+}
+void beltDWPStepE(void* buf, size_t count, void* state) { beltCTRStepE(buf, count, state); }
+void beltDWPStepD(void* buf, size_t count, void* state) { beltCTRStepE(buf, count, state); }
+void beltDWPStepI(const void* buf, size_t count, void* state)
+{
+	aead_step_i(dwp_view((belt_dwp_st*)state), buf, count, "beltDWPStepI");
+}
+void beltDWPStepA(const void* buf, size_t count, void* state)
+{
+	aead_step_a(dwp_view((belt_dwp_st*)state), buf, count, "beltDWPStepA");
+}
+void beltDWPStepG(octet mac[8], void* state)
+{
+	belt_dwp_st* st = (belt_dwp_st*)state;
+	aead_step_g(dwp_view(st), "beltDWPStepG");
+	memcpy(mac, st->t1, 8);
+}
+bool_t beltDWPStepV(const octet mac[8], void* state)
+{
+	belt_dwp_st* st = (belt_dwp_st*)state;
+	aead_step_g(dwp_view(st), "beltDWPStepV");
+	return memcmp(mac, st->t1, 8) == 0;
+}
+
+/* ---- belt-CHE: the counter is the LFSR s <- s x ^ 1 over GF(2^128) (belt_che.c:86-88, belt_lcl.c:99-108) */
+/* c <- a b mod x^128 + x^7 + x^2 + x + 1, bit i of the little-endian 128-bit integer = coefficient of x^i */
+static void gf128_mul_host(u32 c[4], const u32 a[4], const u32 b[4])
+{
+	u32 acc[4] = {0, 0, 0, 0}, v[4];
+	int i, k;
+	memcpy(v, a, 16);
+	for (i = 0; i < 128; ++i)
+	{
+		if (b[i >> 5] >> (i & 31) & 1)
+			for (k = 0; k < 4; ++k) acc[k] ^= v[k];
+		{
+			const u32 top = v[3] >> 31;
+			v[3] = v[3] << 1 | v[2] >> 31, v[2] = v[2] << 1 | v[1] >> 31, v[1] = v[1] << 1 | v[0] >> 31;
+			v[0] = v[0] << 1 ^ (top ? 0x87u : 0u);
+		}
+	}
+	memcpy(c, acc, 16);
+}
+/* s <- the LFSR state n steps later: the map s -> s x ^ 1 iterated n times is s -> s x^n ^ c_n; maps
+   compose as (A, c) o (B, d) = (A B, A d ^ c), so n is consumed by square-and-multiply */
+static void che_advance(u32 s[4], u64 n)
+{
+	u32 A[4] = {1, 0, 0, 0}, c[4] = {0, 0, 0, 0};     /* identity */
+	u32 B[4] = {2, 0, 0, 0}, d[4] = {1, 0, 0, 0};     /* one step: s x ^ 1 */
+	u32 t[4];
+	int k;
+	for (; n; n >>= 1)
+	{
+		if (n & 1)
+		{
+			/* (A, c) <- (B, d) o (A, c) */
+			gf128_mul_host(t, B, c);
+			for (k = 0; k < 4; ++k) c[k] = t[k] ^ d[k];
+			gf128_mul_host(A, A, B);
+		}
+		/* (B, d) <- (B, d) o (B, d) */
+		gf128_mul_host(t, B, d);
+		for (k = 0; k < 4; ++k) d[k] ^= t[k];
+		gf128_mul_host(B, B, B);
+	}
+	gf128_mul_host(t, A, s);
+	for (k = 0; k < 4; ++k) s[k] = t[k] ^ c[k];
+}
+
+size_t beltCHE_keep(void) { return sizeof(belt_che_st); }
+
+void beltCHEStart(void* state, const octet key[], size_t len, const octet iv[16])
+{
+	belt_che_st* st = (belt_che_st*)state;
+	err_t code;
+	beltKeyExpand2(st->key, key, len);
+	/* r <- s <- E_K(iv), t <- beltH()[0..16) (belt_che.c:52-62) */
+	memcpy(st->r, iv, 16);
+	if ((code = blocks_small(st->r, 1, st->key, 0)))
+		b2g_die("beltCHEStart", code);
+	memcpy(st->s, st->r, 16);
+	memcpy(st->t, beltH(), 16);
+	memset(st->len, 0, sizeof st->len);
+	st->reserved = 0;
+	st->filled = 0;
+}
+
+void beltCHEStepE(void* buf, size_t count, void* state)
+{
+	belt_che_st* st = (belt_che_st*)state;
+	octet* p = (octet*)buf;
+	b2g_slot* sl;
+	void* d;
+	size_t i, padded, rem;
+	err_t code;
+	/* reserve of keystream octets left from the previous call (belt_che.c:70-82) */
+	if (st->reserved)
+	{
+		const size_t take = st->reserved < count ? st->reserved : count;
+		for (i = 0; i < take; ++i)
+			p[i] ^= st->block1[16 - st->reserved + i];
+		st->reserved -= take, p += take, count -= take;
+	}
+	if (!count)
+		return;
+	if ((code = b2g_ensure_device()))
+		b2g_die("beltCHEStepE", code);
+	padded = (count + 15) & ~(size_t)15, rem = count % 16;
+	b2g_lock();
+	sl = b2g_slot_get(0);
+	if ((code = b2g_slot_buf(sl, 0, padded, &d)))
+		goto done;
+	if (rem)
+		CU(cudaMemsetAsync((octet*)d + padded - 16, 0, 16, sl->stream), "memset(belt che)");
+	CU(cudaMemcpyAsync(d, p, count, cudaMemcpyHostToDevice, sl->stream), "H2D(belt che)");
+	if ((code = b2g_beltCHE_dev(d, d, padded, st->key, st->s, 0, sl->stream)))
+		goto done;
+	CU(cudaMemcpyAsync(p, d, count, cudaMemcpyDeviceToHost, sl->stream), "D2H(belt che)");
+	if (rem)
+		CU(cudaMemcpyAsync(st->block1, (octet*)d + padded - 16, 16, cudaMemcpyDeviceToHost, sl->stream), "D2H(belt che tail)");
+	CU(cudaStreamSynchronize(sl->stream), "sync(belt che)");
+done:
+	if (code)
+		cudaStreamSynchronize(sl->stream);
+	b2g_unlock();
+	if (code)
+		b2g_die("beltCHEStepE", code);
+	che_advance(st->s, padded / 16);
+	if (rem)
+		st->reserved = 16 - rem;   /* block1[rem..16) = unused keystream of the last block (its data part was 0) */
+}
+void beltCHEStepD(void* buf, size_t count, void* state) { beltCHEStepE(buf, count, state); }
+void beltCHEStepI(const void* buf, size_t count, void* state)
+{
+	aead_step_i(che_view((belt_che_st*)state), buf, count, "beltCHEStepI");
+}
+void beltCHEStepA(const void* buf, size_t count, void* state)
+{
+	aead_step_a(che_view((belt_che_st*)state), buf, count, "beltCHEStepA");
+}
+void beltCHEStepG(octet mac[8], void* state)
+{
+	belt_che_st* st = (belt_che_st*)state;
+	aead_step_g(che_view(st), "beltCHEStepG");
+	memcpy(mac, st->t1, 8);
+}
+bool_t beltCHEStepV(const octet mac[8], void* state)
+{
+	belt_che_st* st = (belt_che_st*)state;
+	aead_step_g(che_view(st), "beltCHEStepV");
+	return memcmp(mac, st->t1, 8) == 0;
+}
+
 err_t beltDWPWrap(void* dest, octet mac[8], const void* src1, size_t count1, const void* src2,
 	size_t count2, const octet key[], size_t len, const octet iv[16])
 {

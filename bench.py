@@ -422,6 +422,26 @@ def main():
         barrier()
         return shard.max_over_ranks(total, device=dev)
 
+    def gather_info(local):
+        """The final gather of SURVEY §8e: every rank's output to all ranks with one NCCL all-gather
+        over NVLink/NVSwitch, timed on the device (max over ranks). Outside the throughput metric."""
+        if world == 1:
+            return None
+        flat = local.reshape(-1).view(torch.uint8)
+        dst = torch.empty(world * flat.numel(), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(dst, flat)            # warm-up (communicator, buffers)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_gather_into_tensor(dst, flat)
+        e1.record()
+        torch.cuda.synchronize()
+        sec = shard.max_over_ranks(e0.elapsed_time(e1) * 1e-3, device=dev)
+        ok = bool(torch.equal(dst[rank * flat.numel():(rank + 1) * flat.numel()], flat))
+        del dst
+        return {"collective": "ncclAllGather", "bytes_per_rank": int(flat.numel()), "ms": sec * 1e3,
+                "GB/s_per_rank_received": (world - 1) * flat.numel() / sec / 1e9, "own_slice_intact": ok}
+
     results = {}
     issue = {}
     if rank == 0:
@@ -465,6 +485,8 @@ def main():
                             "call": "beltCTRKeystream(dest=pinned host, 1 GiB)", "steps": e2e_steps}
                 assert harr[: 1 << 20].tobytes() == out[: 1 << 20].cpu().numpy().tobytes() or rank != 0
                 del host, harr
+            if world <= 4:                             # 1 GiB per rank: keep the gathered copy under 4 GiB
+                r["gather"] = gather_info(out)
             del out
         elif path == "belt_dwp":
             secret = np.random.default_rng(11).integers(0, 256, 48, dtype=np.uint8).tobytes() if rank == 0 else None
@@ -569,6 +591,7 @@ def main():
                             "call": "bashHashBatch(pinned host msgs 4 GiB -> pinned host digests)", "steps": e2e_steps}
                 assert np.array_equal(ho[:4096], out[:4096].cpu().numpy())
                 del hmsgs, hout, hm, ho
+            r["gather"] = gather_info(out)
             del msgs, out
         elif path == "bign_sign2":
             rng = np.random.default_rng(20 + rank)
@@ -622,6 +645,7 @@ def main():
             stc = d_st.cpu().numpy()
             assert (stc[bad] == 510).all() and int((stc == 0).sum()) == units - len(bad), "verify statuses off"
             r["checksum"] = int(stc.astype(np.int64).sum())
+            r["gather"] = gather_info(d_st)
             if not args.no_e2e:
                 ph, ps, pp = (torch.from_numpy(x).pin_memory() for x in (hashes, sigs, pubs))
                 nh, ns, npb = ph.numpy(), ps.numpy(), pp.numpy()

@@ -177,6 +177,27 @@ err_t beltCHEWrap(void* dest, octet mac[8], const void* src1, size_t count1, con
 	size_t count2, const octet key[], size_t len, const octet iv[16]);
 err_t beltCHEUnwrap(void* dest, const void* src1, size_t count1, const void* src2, size_t count2,
 	const octet mac[8], const octet key[], size_t len, const octet iv[16]);
+/* drop-in: belt.h:850-983 (belt_dwp.c:27-207) and the belt-CHE twins (belt_che.c:27-239) — the
+   streaming forms: StepE / StepD transform critical data in place, StepI absorbs open data, StepA
+   absorbs critical data (ciphertext), StepG / StepV produce / check the tag without closing the
+   state. Field order of the states follows belt_dwp_st / belt_che_st (the multiplication stack
+   of the reference is not needed: the block chain runs on the device). */
+size_t beltDWP_keep(void);
+void beltDWPStart(void* state, const octet key[], size_t len, const octet iv[16]);
+void beltDWPStepE(void* buf, size_t count, void* state);
+void beltDWPStepI(const void* buf, size_t count, void* state);
+void beltDWPStepA(const void* buf, size_t count, void* state);
+void beltDWPStepD(void* buf, size_t count, void* state);
+void beltDWPStepG(octet mac[8], void* state);
+bool_t beltDWPStepV(const octet mac[8], void* state);
+size_t beltCHE_keep(void);
+void beltCHEStart(void* state, const octet key[], size_t len, const octet iv[16]);
+void beltCHEStepE(void* buf, size_t count, void* state);
+void beltCHEStepI(const void* buf, size_t count, void* state);
+void beltCHEStepA(const void* buf, size_t count, void* state);
+void beltCHEStepD(void* buf, size_t count, void* state);
+void beltCHEStepG(octet mac[8], void* state);
+bool_t beltCHEStepV(const octet mac[8], void* state);
 /* batch: pure keystream (beltCTR of zeros) */
 err_t beltCTRKeystream(void* dest, size_t count, const octet key[], size_t len,
 	const octet iv[16]);

@@ -888,6 +888,120 @@ u32 orc_beltCHEUnwrap(void* dest, const void* src1, size_t n1, const void* src2,
 	return ORC_OK;
 }
 
+/* ======================================================================= belt-DWP / belt-CHE, streaming
+   (belt_dwp.c:45-207, belt_che.c:48-239): one state for both modes; `che` selects the LFSR counter
+   and r = E_K(iv) (belt-CHE) instead of the incrementing counter and r = E_K(E_K(iv)) (belt-DWP). */
+
+void orc_beltAEADStart(orc_belt_aead_st* st, int che, const u8* key, size_t len, const u8 iv[16])
+{
+	u32 w[4];
+	memset(st, 0, sizeof *st);
+	st->che = che;
+	orc_beltKeyExpand2(st->key, key, len);
+	memcpy(w, iv, 16);
+	orc_beltBlockEncr2(w, st->key);                 /* s = E_K(iv) */
+	memcpy(st->s, w, 16);
+	if (!che)
+		orc_beltBlockEncr2(w, st->key);             /* DWP: r = E_K(s) (belt_dwp.c:52-55); CHE: r = s */
+	memcpy(st->r, w, 16);
+	memcpy(st->t, orc_beltH(), 16);
+}
+
+/* StepE == StepD: XOR with the keystream, block by block, keeping the unused rest of the last block */
+void orc_beltAEADStepE(void* buf, size_t n, orc_belt_aead_st* st)
+{
+	u8* p = (u8*)buf;
+	while (n)
+	{
+		if (!st->reserved)
+		{
+			u32 w[4];
+			if (st->che)
+			{
+				/* s <- s x ^ 1 (belt_che.c:86-88) */
+				u64 v[2];
+				u64 top;
+				memcpy(v, st->s, 16);
+				top = v[1] >> 63;
+				v[1] = v[1] << 1 | v[0] >> 63;
+				v[0] = (v[0] << 1 ^ (top ? 0x87 : 0)) ^ 1;
+				memcpy(st->s, v, 16);
+			}
+			else
+			{
+				/* s <- s + 1 as a 128-bit little-endian integer (belt_ctr.c:27-35) */
+				int i;
+				for (i = 0; i < 4 && ++st->s[i] == 0; ++i)
+					;
+			}
+			memcpy(w, st->s, 16);
+			orc_beltBlockEncr2(w, st->key);
+			memcpy(st->ks, w, 16);
+			st->reserved = 16;
+		}
+		*p++ ^= st->ks[16 - st->reserved];
+		--st->reserved, --n;
+	}
+}
+
+static void aead_block(orc_belt_aead_st* st, u64 t[2], const u8 blk[16])
+{
+	u64 x[2];
+	memcpy(x, blk, 16);
+	t[0] ^= x[0], t[1] ^= x[1];
+	gf128_mul(t, t, st->r);
+}
+
+static void aead_absorb(orc_belt_aead_st* st, const u8* p, size_t n)
+{
+	while (n)
+	{
+		const size_t take = n < 16 - st->filled ? n : 16 - st->filled;
+		memcpy(st->block + st->filled, p, take);
+		st->filled += take, p += take, n -= take;
+		if (st->filled == 16)
+			aead_block(st, st->t, st->block), st->filled = 0;
+	}
+}
+
+void orc_beltAEADStepI(const void* buf, size_t n, orc_belt_aead_st* st)
+{
+	st->len[0] += (u64)n << 3;
+	aead_absorb(st, (const u8*)buf, n);
+}
+
+void orc_beltAEADStepA(const void* buf, size_t n, orc_belt_aead_st* st)
+{
+	/* first non-empty critical fragment closes the open data with zeros (belt_dwp.c:121-131) */
+	if (n && st->len[1] == 0 && st->filled)
+	{
+		memset(st->block + st->filled, 0, 16 - st->filled);
+		aead_block(st, st->t, st->block), st->filled = 0;
+	}
+	st->len[1] += (u64)n << 3;
+	aead_absorb(st, (const u8*)buf, n);
+}
+
+/* the state itself is not changed: more data may follow (belt_dwp.c:172-196) */
+void orc_beltAEADStepG(u8 mac[8], const orc_belt_aead_st* cst)
+{
+	orc_belt_aead_st* st = (orc_belt_aead_st*)cst;
+	u64 t1[2];
+	u32 w[4];
+	u8 blk[16];
+	memcpy(t1, st->t, 16);
+	if (st->filled)
+	{
+		memset(blk, 0, 16), memcpy(blk, st->block, st->filled);
+		aead_block(st, t1, blk);
+	}
+	memcpy(blk, st->len, 16);
+	aead_block(st, t1, blk);
+	memcpy(w, t1, 16);
+	orc_beltBlockEncr2(w, st->key);
+	memcpy(mac, w, 8);
+}
+
 /* ======================================================================= bash-prg (bash_prg.c:56-385) */
 /* programmable sponge automaton; own state layout (the semantics of bash_prg_st, :54-62) */
 

@@ -72,6 +72,23 @@ uint32_t orc_beltDWPUnwrap(void* dest, const void* src1, size_t n1, const void* 
 /* key-agility batch: block i under key i (config 5) */
 void orc_beltECBEncrMultiKey(uint8_t* blocks, const uint8_t* keys32, size_t count);
 
+/* ---- belt-DWP / belt-CHE streaming (belt_dwp.c:45-207, belt_che.c:48-239); che = 0: DWP, 1: CHE ---- */
+typedef struct
+{
+	uint32_t key[8], s[4];
+	uint64_t r[2], t[2], len[2];
+	uint8_t block[16];
+	size_t filled;
+	uint8_t ks[16];
+	size_t reserved;
+	int che;
+} orc_belt_aead_st;
+void orc_beltAEADStart(orc_belt_aead_st* st, int che, const uint8_t* key, size_t len, const uint8_t iv[16]);
+void orc_beltAEADStepE(void* buf, size_t n, orc_belt_aead_st* st);      /* also StepD */
+void orc_beltAEADStepI(const void* buf, size_t n, orc_belt_aead_st* st);
+void orc_beltAEADStepA(const void* buf, size_t n, orc_belt_aead_st* st);
+void orc_beltAEADStepG(uint8_t mac[8], const orc_belt_aead_st* st);
+
 /* ---- bign on bign-curve256v1 (STB 34.101.45, l = 128) ---- */
 uint32_t orc_bignVerify128(const uint8_t* oid_der, size_t oid_len, const uint8_t hash[32],
 	const uint8_t sig[48], const uint8_t pubkey[64]);                       /* bign_sign.c:268-347 */

@@ -141,6 +141,41 @@ def beltDWPUnwrap(src1: bytes, src2: bytes, mac: bytes, key: bytes, iv: bytes, f
     return code, (d.raw[: len(src1)] if code == 0 else None)
 
 
+class _AeadSt(C.Structure):
+    _fields_ = [("key", C.c_uint32 * 8), ("s", C.c_uint32 * 4), ("r", C.c_uint64 * 2), ("t", C.c_uint64 * 2),
+                ("len", C.c_uint64 * 2), ("block", C.c_ubyte * 16), ("filled", C.c_size_t), ("ks", C.c_ubyte * 16),
+                ("reserved", C.c_size_t), ("che", C.c_int)]
+
+
+class BeltDWP:
+    """The oracle's streaming belt-DWP / belt-CHE behind the interface of bee2_b200.BeltDWP."""
+
+    def __init__(self, key: bytes, iv: bytes, mode: str = "DWP"):
+        self.L, self.st = port(), _AeadSt()
+        self.L.orc_beltAEADStart(C.byref(self.st), 1 if mode == "CHE" else 0, bytes(key), sz(len(key)), bytes(iv))
+
+    def step_e(self, data: bytes) -> bytes:
+        buf = C.create_string_buffer(bytes(data), max(len(data), 1))
+        self.L.orc_beltAEADStepE(buf, sz(len(data)), C.byref(self.st))
+        return buf.raw[: len(data)]
+
+    step_d = step_e
+
+    def step_i(self, data: bytes) -> None:
+        self.L.orc_beltAEADStepI(bytes(data), sz(len(data)), C.byref(self.st))
+
+    def step_a(self, data: bytes) -> None:
+        self.L.orc_beltAEADStepA(bytes(data), sz(len(data)), C.byref(self.st))
+
+    def step_g(self) -> bytes:
+        mac = C.create_string_buffer(8)
+        self.L.orc_beltAEADStepG(mac, C.byref(self.st))
+        return mac.raw
+
+    def step_v(self, mac: bytes) -> bool:
+        return self.step_g() == bytes(mac)
+
+
 def beltHash(src: bytes) -> bytes:
     out = C.create_string_buffer(32)
     port().orc_beltHash(out, bytes(src), sz(len(src)))

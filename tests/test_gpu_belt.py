@@ -113,6 +113,38 @@ def test_dwp_che_random_sizes_vs_oracle(mode):
 
 
 @pytest.mark.parametrize("mode", ["DWP", "CHE"])
+def test_dwp_che_streaming(mode):
+    """The drop-in streaming forms (belt_test.c:474-560): A.19 incremental sequences, then random
+    programs of split StepI / StepE / StepA / StepG calls against the oracle's sequential chain."""
+    key, iv, steps, want_buf, want_mac = v.aead_incremental_program(mode, H)
+    st = b.BeltDWP(key, iv, mode)
+    buf, tags = v.run_aead_program(st, steps)
+    assert buf.hex().upper() == want_buf and tags[-1].hex().upper() == want_mac
+    assert st.step_v(tags[-1]) and not st.step_v(tags[0])
+    assert (buf, tags[-1]) == getattr(b, f"belt{mode}Wrap")(H[:len(buf)], H[16:48], key, iv)
+    rng = np.random.default_rng(41)
+    rb = lambda n: rng.integers(0, 256, n, dtype=np.uint8).tobytes()  # noqa: E731
+    for trial in range(12):
+        key, iv = rb(int(rng.choice([16, 24, 32]))), rb(16)
+        g, w = b.BeltDWP(key, iv, mode), o.BeltDWP(key, iv, mode)
+        for _ in range(int(rng.integers(0, 4))):
+            d = rb(int(rng.choice([0, 1, 5, 16, 17, 40, 100, 5000])))
+            g.step_i(d), w.step_i(d)
+            if rng.random() < 0.3:
+                assert g.step_g() == w.step_g()
+        for _ in range(int(rng.integers(1, 5))):
+            d = rb(int(rng.choice([0, 1, 7, 16, 33, 64, 129, 70001])))
+            c = g.step_e(d)
+            assert c == w.step_e(d)
+            g.step_a(c), w.step_a(c)
+            if rng.random() < 0.4:
+                assert g.step_g() == w.step_g()
+        mac = w.step_g()
+        assert g.step_g() == mac and g.step_v(mac)
+        assert not g.step_v(bytes([mac[0] ^ 1]) + mac[1:])
+
+
+@pytest.mark.parametrize("mode", ["DWP", "CHE"])
 def test_dwp_che_multi_chunk_pipeline(mode):
     """More than two 32 MiB pipeline stages with a ragged tail: the chunks are encrypted on alternating
     streams from their own counter offsets and authenticated by one tag launch over the whole buffer."""

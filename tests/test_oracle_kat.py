@@ -82,6 +82,30 @@ def test_belt_dwp_che_A19_A20(mode):
             assert unwrap(src, op, bad, key, iv) == (511, None)
 
 
+@pytest.mark.parametrize("mode", ["DWP", "CHE"])
+def test_belt_dwp_che_streaming_A19(mode):
+    """belt_test.c:474-520: the incremental forms (split StepE / StepI / StepA, tag taken four times)."""
+    key, iv, steps, want_buf, want_mac = v.aead_incremental_program(mode, H)
+    st = o.BeltDWP(key, iv, mode)
+    buf, tags = v.run_aead_program(st, steps)
+    assert buf.hex().upper() == want_buf and tags[-1].hex().upper() == want_mac
+    assert st.step_v(tags[-1]) and not st.step_v(tags[0])
+    # the one-shot form gives the same (belt_test.c:494-497)
+    n = len(buf)
+    assert getattr(o, f"belt{mode}Wrap")(H[:n], H[16:48], key, iv) == (buf, tags[-1])
+    # A.20: StepI, StepA over the ciphertext, StepD (belt_test.c:524-560)
+    key2, iv2 = H[160:192], H[208:224]
+    n = 16 if mode == "DWP" else 20
+    t = [t for t in KAT[f"belt{mode}"] if t["id"].startswith("A.20")][0] if f"belt{mode}" in KAT else None
+    st = o.BeltDWP(key2, iv2, mode)
+    st.step_i(H[80:112])
+    st.step_a(H[64:64 + n])
+    plain = st.step_d(H[64:64 + n])
+    assert getattr(o, f"belt{mode}Unwrap")(H[64:64 + n], H[80:112], st.step_g(), key2, iv2) == (0, plain)
+    if t is not None:
+        assert plain.hex().upper() == t["out"] and st.step_g().hex().upper() == t["mac"]
+
+
 def test_belt_hash_A23():
     for t in KAT["beltHash"]:
         assert o.beltHash(R(t["in"])).hex().upper() == t["out"], t["id"]
