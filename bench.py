@@ -732,7 +732,7 @@ def main():
             "config": {"workload": cfg["workload"], "l2": h["l2"], "units_per_gpu": cfg["units"],
                        "sharding": "rank r takes units [r*U,(r+1)*U); key/iv/oid broadcast from rank 0 over NCCL; no data-path collective"},
             "roofline": h["roofline"], "issue_roofline": h.get("issue_roofline"),
-            "cpu_baseline": h.get("cpu_baseline"), "e2e": h.get("e2e"), "gpu_launches": h["gpu_launches"],
+            "cpu_baseline": h.get("cpu_baseline"), "e2e": h.get("e2e"), "gather": h.get("gather"), "gpu_launches": h["gpu_launches"],
             "clocks": clocks, "issue_peaks_Tops": issue,
             "paths": {k: v for k, v in results.items() if k != head}}
     sys.stdout.flush()
