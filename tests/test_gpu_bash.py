@@ -118,3 +118,48 @@ def test_config3_shape_device_level():
     host, hmsg = out.cpu().numpy(), msgs.cpu().numpy()
     for i in list(range(0, cnt, 997)) + [cnt - 1]:
         assert host[i].tobytes() == o.bashHash(256, hmsg[i].tobytes())
+
+
+def test_concurrent_host_threads():
+    """SURVEY §8b threading: every entry point may be called from many host threads at once (ctypes drops
+    the GIL); results must equal the single-threaded ones."""
+    import threading
+    rng = np.random.default_rng(99)
+    msgs = rng.integers(0, 256, size=(512, 1000), dtype=np.uint8)
+    key, iv = o.beltH()[128:160], o.beltH()[192:208]
+    data = rng.integers(0, 256, size=100_003, dtype=np.uint8).tobytes()
+    params = b.bignParamsStd()
+    priv = rng.integers(0, 256, size=(64, 32), dtype=np.uint8)
+    priv[:, 31] &= 0x7F
+    hashes = rng.integers(0, 256, size=(64, 32), dtype=np.uint8)
+    _, pubs = b.bignPubkeyCalcBatch(params, priv)
+    _, sigs = b.bignSign2Batch(params, b.OID_BELT_HASH_DER, hashes, priv)
+    want = (b.bashHashBatch(256, msgs), b.beltCTR(data, key, iv), b.beltDWPWrap(data, data[:77], key, iv),
+            b.bignVerifyBatch(params, b.OID_BELT_HASH_DER, hashes, sigs, pubs))
+    errors = []
+
+    def worker(kind):
+        try:
+            for _ in range(6):
+                if kind == 0:
+                    assert np.array_equal(b.bashHashBatch(256, msgs), want[0])
+                elif kind == 1:
+                    assert b.beltCTR(data, key, iv) == want[1]
+                elif kind == 2:
+                    assert b.beltDWPWrap(data, data[:77], key, iv) == want[2]
+                    st = b.BeltDWP(key, iv)
+                    st.step_i(data[:77])
+                    c = st.step_e(data[:50_000]) + st.step_e(data[50_000:])
+                    st.step_a(c)
+                    assert (c, st.step_g()) == want[2]
+                else:
+                    assert np.array_equal(b.bignVerifyBatch(params, b.OID_BELT_HASH_DER, hashes, sigs, pubs), want[3])
+        except Exception as e:  # noqa: BLE001
+            errors.append((kind, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k % 4,)) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
