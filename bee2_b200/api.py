@@ -25,7 +25,8 @@ __all__ = [
     "bignPubkeyCalc", "bignPubkeyCalcBatch", "ecMulABatch", "ecAddMulABatch", "OID_BELT_HASH_DER",
     "bashHashBatch_dev", "bashFBatch_dev", "beltCTR_dev", "beltECB_dev", "beltECBEncrBatch_dev",
     "beltHashBatch_dev", "bignVerifyBatch_dev", "bignSign2Batch_dev", "bignPubkeyCalcBatch_dev",
-    "ecMulABatch_dev", "bignVerifyBatchL_dev", "pinned_empty", "BIGN_CURVES",
+    "ecMulABatch_dev", "bignVerifyBatchL_dev", "bignKeypairGenBatch", "bignKeypairValBatch", "bignPubkeyValBatch",
+    "bignDHBatch", "bignDH", "bignPubkeyVal", "bignKeypairVal", "ERR_BAD_RNG", "ERR_BAD_SHAREDKEY", "pinned_empty", "BIGN_CURVES",
 ]
 
 ERR_OK = 0
@@ -34,9 +35,11 @@ ERR_OUTOFMEMORY = 110
 ERR_NOT_IMPLEMENTED = 119
 ERR_FILE_NOT_FOUND = 202
 ERR_BAD_OID = 301
+ERR_BAD_RNG = 304
 ERR_BAD_PARAMS = 502
 ERR_BAD_PRIVKEY = 504
 ERR_BAD_PUBKEY = 505
+ERR_BAD_SHAREDKEY = 507
 ERR_BAD_SIG = 510
 ERR_BAD_MAC = 511
 ERR_B2G_NO_DEVICE = 9001
@@ -136,6 +139,12 @@ def _declare(L: C.CDLL) -> None:
         "b2g_ecMulABatch_dev": (u32, [vp, vp, vp, vp, sz, sz, vp]),
         "ecAddMulABatch": (u32, [vp, vp, vp, vp, sz, vp, sz]),
         "b2g_ecAddMulABatch_dev": (u32, [vp, vp, vp, vp, sz, vp, sz, vp]),
+        "bignKeypairGen": (u32, [vp, vp, vp, vp, vp]), "bignKeypairGenBatch": (u32, [vp, vp, vp, vp, vp, sz]),
+        "bignKeypairVal": (u32, [vp, vp, vp]), "bignKeypairValBatch": (u32, [vp, vp, vp, vp, sz]),
+        "bignPubkeyVal": (u32, [vp, vp]), "bignPubkeyValBatch": (u32, [vp, vp, vp, sz]),
+        "bignDH": (u32, [vp, vp, vp, vp, sz]), "bignDHBatch": (u32, [vp, vp, vp, vp, vp, sz, sz]),
+        "b2g_bignDHBatchL_dev": (u32, [sz, vp, vp, vp, vp, sz, vp]),
+        "b2g_bignPubkeyValBatchL_dev": (u32, [sz, vp, vp, sz, vp]),
         "ecMulABatchL": (u32, [sz, vp, vp, vp, vp, sz, sz]), "ecAddMulABatchL": (u32, [sz, vp, vp, vp, vp, sz, vp, sz]),
         "b2g_bignVerifyBatchL_dev": (u32, [sz, vp, vp, sz, vp, vp, vp, sz, vp]),
         "b2g_bignSign2BatchL_t_dev": (u32, [sz, vp, vp, vp, sz, vp, vp, sz, vp, sz, vp]),
@@ -565,6 +574,75 @@ def bignPubkeyCalcBatch(params: BignParams, privkeys: np.ndarray):
     _chk("bignPubkeyCalcBatch", lib().bignPubkeyCalcBatch(status.ctypes.data, pub.ctypes.data, C.addressof(params),
                                                           privkeys.ctypes.data, count))
     return status, pub
+
+
+GEN_I = C.CFUNCTYPE(None, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+def _rng_callback(stream: bytes):
+    """A gen_i (defs.h:520-524) that hands out the octets of `stream` in order."""
+    pos = [0]
+
+    def fn(buf, count, state):
+        chunk = stream[pos[0]:pos[0] + count]
+        assert len(chunk) == count, "rng stream exhausted"
+        C.memmove(buf, chunk, count)
+        pos[0] += count
+    return GEN_I(fn), pos
+
+
+def bignKeypairGenBatch(params: BignParams, rng_stream: bytes, count: int):
+    """`count` key pairs from the octets of rng_stream (consumed as the reference's generator calls
+    would consume them); returns (privkeys [count,l/4], pubkeys [count,l/2], octets consumed)."""
+    no = params.l // 4
+    priv = np.zeros((count, no), dtype=np.uint8)
+    pub = np.zeros((count, 2 * no), dtype=np.uint8)
+    cb, pos = _rng_callback(bytes(rng_stream))
+    _chk("bignKeypairGenBatch", lib().bignKeypairGenBatch(priv.ctypes.data, pub.ctypes.data, C.addressof(params),
+                                                          C.cast(cb, C.c_void_p), None, count))
+    return priv, pub, pos[0]
+
+
+def bignKeypairValBatch(params: BignParams, privkeys: np.ndarray, pubkeys: np.ndarray) -> np.ndarray:
+    count = privkeys.size // (params.l // 4)
+    status = np.full(count, 0xFFFFFFFF, dtype=np.uint32)
+    _chk("bignKeypairValBatch", lib().bignKeypairValBatch(status.ctypes.data, C.addressof(params), privkeys.ctypes.data,
+                                                          pubkeys.ctypes.data, count))
+    return status
+
+
+def bignPubkeyValBatch(params: BignParams, pubkeys: np.ndarray) -> np.ndarray:
+    count = pubkeys.size // (params.l // 2)
+    status = np.full(count, 0xFFFFFFFF, dtype=np.uint32)
+    _chk("bignPubkeyValBatch", lib().bignPubkeyValBatch(status.ctypes.data, C.addressof(params), pubkeys.ctypes.data, count))
+    return status
+
+
+def bignDHBatch(params: BignParams, privkeys: np.ndarray, pubkeys: np.ndarray, key_len: int):
+    count = privkeys.size // (params.l // 4)
+    status = np.full(count, 0xFFFFFFFF, dtype=np.uint32)
+    keys = np.zeros((count, key_len), dtype=np.uint8)
+    _chk("bignDHBatch", lib().bignDHBatch(status.ctypes.data, keys.ctypes.data, C.addressof(params), privkeys.ctypes.data,
+                                          pubkeys.ctypes.data, key_len, count))
+    return status, keys
+
+
+def bignDH(params: BignParams, privkey: bytes, pubkey: bytes, key_len: int):
+    """bign.h bignDH — returns (err_t, key)."""
+    ks = [_buf(x) for x in (privkey, pubkey)]
+    key = _out(max(key_len, 1))
+    code = lib().bignDH(key.ctypes.data, C.addressof(params), ks[0][1], ks[1][1], key_len)
+    return code, key.tobytes()[:key_len]
+
+
+def bignPubkeyVal(params: BignParams, pubkey: bytes) -> int:
+    k = _buf(pubkey)
+    return lib().bignPubkeyVal(C.addressof(params), k[1])
+
+
+def bignKeypairVal(params: BignParams, privkey: bytes, pubkey: bytes) -> int:
+    ks = [_buf(x) for x in (privkey, pubkey)]
+    return lib().bignKeypairVal(C.addressof(params), ks[0][1], ks[1][1])
 
 
 def ecMulABatch(points: np.ndarray, scalars: np.ndarray, l: int = 128):

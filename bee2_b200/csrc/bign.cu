@@ -53,21 +53,29 @@ __constant__ u32 c_q16[16] = {0x0D068EF1u, 0xDCFFAD49u, 0x9556DF32u, 0x361BCAE5u
 __constant__ u32 c_yG16[16] = {0xCEEFEDBDu, 0xB792AE6Fu, 0xC94C0D04u, 0x67AA83B9u, 0xEEE82261u, 0xFF777395u, 0x0EFA6FD2u, 0x6973DDE2u,
 	0x00CCCADAu, 0xD2EDF81Bu, 0xB361BCE2u, 0xB0AB41B3u, 0xA0D18FABu, 0xB182E6F7u, 0xE4037681u, 0xA826FF7Au};
 
+// the coefficient b (bign_params.c:50-55, :94-101, :151-160): only the on-curve check of bignPubkeyVal / bignDH uses it
+__constant__ u32 c_b8[8] = {0xD69C03F1u, 0xB22E7D6Bu, 0x978B9253u, 0x4CF55069u, 0xE4D8FBBEu, 0xD2C13AABu, 0x15F3A8EDu, 0x77CE6C15u};
+__constant__ u32 c_b12[12] = {0x6873BF64u, 0xBCA7FC23u, 0xF3CEBD7Cu, 0x14BDE2F0u, 0xE9712E3Au, 0xA6216AF9u, 0x0FFBB196u, 0x712748BBu, 0x655D34D2u, 0x33075AABu, 0x959CEF20u, 0x3C75DFE1u};
+__constant__ u32 c_b16[16] = {0xD6139C90u, 0x09346998u, 0x3A49A27Au, 0xEA862227u, 0x87ACA243u, 0x2933008Cu, 0xC4245E95u, 0x2711DCB5u, 0xDAADB088u, 0x17CE13E3u, 0xDD5D2551u, 0x5BC6A9EEu, 0x60FD5889u, 0xD88C5D6Au, 0x933B8C43u, 0x6CB45944u};
+
 template <int N> struct bign_c;
 template <> struct bign_c<8>
 {
 	static __device__ __forceinline__ const u32* q() { return c_q8; }
 	static __device__ __forceinline__ const u32* yG() { return c_yG8; }
+	static __device__ __forceinline__ const u32* b() { return c_b8; }
 };
 template <> struct bign_c<12>
 {
 	static __device__ __forceinline__ const u32* q() { return c_q12; }
 	static __device__ __forceinline__ const u32* yG() { return c_yG12; }
+	static __device__ __forceinline__ const u32* b() { return c_b12; }
 };
 template <> struct bign_c<16>
 {
 	static __device__ __forceinline__ const u32* q() { return c_q16; }
 	static __device__ __forceinline__ const u32* yG() { return c_yG16; }
+	static __device__ __forceinline__ const u32* b() { return c_b16; }
 };
 
 // device: BIGN_GN(N) * BIGN_GE entries of 8 N octets (x || y) per level; entry j = 0 unused
@@ -649,6 +657,75 @@ ecp_mul_kernel(u8* __restrict__ out, int* __restrict__ ok, const u8* __restrict_
 		ok[i] = live ? 1 : 0;
 }
 
+// bignPubkeyVal (bign_misc.c:317-352) and bignDH (bign_misc.c:437-500) per item:
+//   status BAD_PRIVKEY unless 0 < d < q (DH only), BAD_PUBKEY unless x, y < p and y^2 = x^3 - 3x + b
+//   (qrFrom + ecpIsOnA), then K = d Q (BAD_PARAMS if O) and out = K.x || K.y, 2 no octets.
+template <int N> __global__ void __launch_bounds__(BIGN_THREADS, BIGN_BLOCKS(N))
+bign_dh_kernel(u32* __restrict__ status, u8* __restrict__ out, const u8* __restrict__ privkeys,
+	const u8* __restrict__ pubkeys, u64 count, u32 validate_only)
+{
+	constexpr int NO = 4 * N;
+	__shared__ u32 tree[BIGN_TREE_WORDS(N)];
+	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	bool live = i < count;
+	u32 st = B2G_OK;
+	pt<N> R;
+	if (live)
+	{
+		fe<N> x, y;
+		sc<N> d;
+		fe_load<N>(x, pubkeys + 2 * NO * i), fe_load<N>(y, pubkeys + 2 * NO * i + NO);
+		if (!validate_only)
+		{
+			load_uN<N>(d.w, privkeys + NO * i);
+			if (uN_is_zero<N>(d.w) || geq_q<N>(d.w))
+				st = B2G_BAD_PRIVKEY, live = false;
+		}
+		if (live)
+		{
+			fe<N> cx = x, cy = y, l, r, t, bb;
+			fe_canon<N>(cx), fe_canon<N>(cy);
+			bool ok = true;
+#pragma unroll
+			for (int k = 0; k < N; ++k) ok &= cx.v[k] == x.v[k] && cy.v[k] == y.v[k];
+			// y^2 == x^3 - 3x + b ?
+#pragma unroll
+			for (int k = 0; k < N; ++k) bb.v[k] = bign_c<N>::b()[k];
+			fe_sqr<N>(l, y);
+			fe_sqr<N>(t, x), fe_mul<N>(r, t, x);
+			fe_dbl<N>(t, x), fe_add<N>(t, t, x);
+			fe_sub<N>(r, r, t), fe_add<N>(r, r, bb);
+			fe_sub<N>(t, l, r);
+			ok &= fe_is_zero<N>(t);
+			if (!ok)
+				st = B2G_BAD_PUBKEY, live = false;
+		}
+		if (live && !validate_only)
+		{
+			pt_mul_var<N>(R, d, 32 * N, x, y);
+			if (pt_is_inf<N>(R))
+				st = B2G_BAD_PARAMS, live = false;
+		}
+	}
+	if (!validate_only)
+	{
+		fe<N> z;
+		if (live)
+			z = R.Z;
+		else
+			fe_set_u32<N>(z, 1);
+		const fe<N> zi = block_inv<N>(z, tree);
+		if (live)
+		{
+			fe<N> x, y;
+			pt_affine_xy_zi<N>(x, y, R, zi);
+			fe_store<N>(out + 2 * NO * i, x), fe_store<N>(out + 2 * NO * i + NO, y);
+		}
+	}
+	if (i < count)
+		status[i] = st;
+}
+
 // ---------------------------------------------------------------- launchers (C ABI)
 // q and yG are static constants, GTAB is built lazily; only the belt S-box needs uploading
 extern "C" u32 b2g_bign_upload_tables(const u8 H[256]) { return belt_upload_H(H); }
@@ -879,4 +956,42 @@ extern "C" u32 b2g_ecAddMulABatch_dev(void* d_b, void* d_ok, const void* d_a, co
 	const void* d_k, size_t count, void* stream)
 {
 	return b2g_ecAddMulABatchL_dev(128, d_b, d_ok, d_a, d_d, d_len, d_k, count, stream);
+}
+
+template <int N> static u32 dh_launch(void* d_status, void* d_out, const void* d_privkeys, const void* d_pubkeys,
+	size_t count, u32 validate_only, cudaStream_t st)
+{
+	bign_dh_kernel<N><<<bign_grid(count), BIGN_THREADS, 0, st>>>((u32*)d_status, (u8*)d_out,
+		(const u8*)d_privkeys, (const u8*)d_pubkeys, count, validate_only);
+	b2g_note_launch();
+	return b2g_check_launch("bign_dh_kernel");
+}
+
+// bignDH on a batch: d_out receives K.x || K.y (l/2 octets per item) for items with status 0
+extern "C" u32 b2g_bignDHBatchL_dev(size_t l, void* d_status, void* d_out, const void* d_privkeys,
+	const void* d_pubkeys, size_t count, void* stream)
+{
+	u32 e = b2g_ensure_device();
+	if (e) return e;
+	if (l != 128 && l != 192 && l != 256) return 119u;
+	if (count == 0) return B2G_OK;
+	if ((uintptr_t)d_status & 3) return B2G_BAD_INPUT;
+	cudaStream_t st = (cudaStream_t)stream;
+#define CALL(N) dh_launch<N>(d_status, d_out, d_privkeys, d_pubkeys, count, 0u, st)
+	return BIGN_DISPATCH(l, CALL);
+#undef CALL
+}
+
+// bignPubkeyVal on a batch
+extern "C" u32 b2g_bignPubkeyValBatchL_dev(size_t l, void* d_status, const void* d_pubkeys, size_t count, void* stream)
+{
+	u32 e = b2g_ensure_device();
+	if (e) return e;
+	if (l != 128 && l != 192 && l != 256) return 119u;
+	if (count == 0) return B2G_OK;
+	if ((uintptr_t)d_status & 3) return B2G_BAD_INPUT;
+	cudaStream_t st = (cudaStream_t)stream;
+#define CALL(N) dh_launch<N>(d_status, (void*)0, (const void*)0, d_pubkeys, count, 1u, st)
+	return BIGN_DISPATCH(l, CALL);
+#undef CALL
 }

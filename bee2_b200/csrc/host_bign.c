@@ -466,3 +466,211 @@ err_t ecAddMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d
 {
 	return ecAddMulABatchL(128, b, ok, a, d, d_len, k, count);
 }
+
+/* ---------------------------------------------------------------- key generation / validation / DH
+   (bign_misc.c:182-300, :317-352, :437-515) */
+
+/* d <-R {1, ..., p - 1}: zzRandNZMod over the FIELD modulus exactly as bignKeypairGenEc calls it
+   (bign_misc.c:213 hands ec->f->mod, zz_mod.c:463-484): no octets from rng per attempt, at most
+   B_PER_IMPOSSIBLE + 1 attempts. For d in [q, p) (probability ~2^-l) the engine then reports
+   ERR_BAD_PRIVKEY where the reference would go on with d mod q. */
+static int rand_nz_mod_p(octet d[], const bign_params* params, gen_i rng, void* rng_state)
+{
+	const size_t no = params->l / 4;
+	size_t tries = 64 + 1, i;
+	while (tries--)
+	{
+		int zero = 1, less = 0;
+		rng(d, no, rng_state);
+		for (i = 0; i < no; ++i)
+			zero &= d[i] == 0;
+		for (i = no; i-- > 0;)
+			if (d[i] != params->p[i])
+			{
+				less = d[i] < params->p[i];
+				break;
+			}
+		if (!zero && less)
+			return 1;
+	}
+	return 0;
+}
+
+err_t bignKeypairGenBatch(octet* privkeys, octet* pubkeys, const bign_params* params, gen_i rng,
+	void* rng_state, size_t count)
+{
+	err_t code, *st;
+	size_t no, i;
+	if ((code = params_check(params)))
+		return code;
+	if (count && (!privkeys || !pubkeys))
+		return ERR_BAD_INPUT;
+	if (!rng)
+		return ERR_BAD_RNG;
+	no = params->l / 4;
+	/* the private keys are drawn in item order, like `count` successive bignKeypairGen calls */
+	for (i = 0; i < count; ++i)
+		if (!rand_nz_mod_p(privkeys + no * i, params, rng, rng_state))
+			return ERR_BAD_RNG;
+	if (!count)
+		return ERR_OK;
+	if (!(st = (err_t*)malloc(count * sizeof *st)))
+		return ERR_OUTOFMEMORY;
+	code = bignPubkeyCalcBatch(st, pubkeys, params, privkeys, count);
+	for (i = 0; !code && i < count; ++i)
+		code = st[i];
+	free(st);
+	return code;
+}
+
+err_t bignKeypairGen(octet privkey[], octet pubkey[], const bign_params* params, gen_i rng, void* rng_state)
+{
+	err_t code;
+	if ((code = params_check(params)))
+		return code;
+	if (!privkey || !pubkey)
+		return ERR_BAD_INPUT;
+	return bignKeypairGenBatch(privkey, pubkey, params, rng, rng_state, 1);
+}
+
+/* status[i] = ERR_OK / ERR_BAD_PRIVKEY / ERR_BAD_PARAMS / ERR_BAD_PUBKEY (Q != d G) */
+err_t bignKeypairValBatch(err_t* status, const bign_params* params, const octet* privkeys,
+	const octet* pubkeys, size_t count)
+{
+	err_t code;
+	octet* calc;
+	size_t no, i;
+	if ((code = params_check(params)))
+		return code;
+	if (count && (!status || !privkeys || !pubkeys))
+		return ERR_BAD_INPUT;
+	if (!count)
+		return ERR_OK;
+	no = params->l / 4;
+	if (!(calc = (octet*)malloc(2 * no * count)))
+		return ERR_OUTOFMEMORY;
+	if (!(code = bignPubkeyCalcBatch(status, calc, params, privkeys, count)))
+		for (i = 0; i < count; ++i)
+			if (status[i] == ERR_OK && memcmp(calc + 2 * no * i, pubkeys + 2 * no * i, 2 * no) != 0)
+				status[i] = ERR_BAD_PUBKEY;
+	free(calc);
+	return code;
+}
+
+err_t bignKeypairVal(const bign_params* params, const octet privkey[], const octet pubkey[])
+{
+	err_t st = ERR_BAD_INPUT, code;
+	if ((code = params_check(params)))
+		return code;
+	if (!privkey || !pubkey)
+		return ERR_BAD_INPUT;
+	if ((code = bignKeypairValBatch(&st, params, privkey, pubkey, 1)))
+		return code;
+	return st;
+}
+
+/* status[i] = ERR_OK / ERR_BAD_PUBKEY: coordinates < p and the point on the curve (ecpIsOnA) */
+err_t bignPubkeyValBatch(err_t* status, const bign_params* params, const octet* pubkeys, size_t count)
+{
+	err_t code;
+	b2g_slot* s0;
+	void *d_p, *d_st;
+	size_t no;
+	if ((code = params_check(params)))
+		return code;
+	if (count && (!status || !pubkeys))
+		return ERR_BAD_INPUT;
+	if ((code = b2g_ensure_device()))
+		return code;
+	if (!count)
+		return ERR_OK;
+	no = params->l / 4;
+	b2g_lock();
+	s0 = b2g_slot_get(0);
+	if ((code = stage_in(s0, 0, pubkeys, 2 * no * count, &d_p)) || (code = b2g_slot_buf(s0, 1, 4 * count, &d_st)))
+		goto done;
+	if ((code = b2g_bignPubkeyValBatchL_dev(params->l, d_st, d_p, count, s0->stream)))
+		goto done;
+	CU(cudaMemcpyAsync(status, d_st, 4 * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(bign status)");
+	CU(cudaStreamSynchronize(s0->stream), "sync(bign pubkey val)");
+done:
+	if (code)
+		cudaStreamSynchronize(s0->stream);
+	b2g_unlock();
+	return code;
+}
+
+err_t bignPubkeyVal(const bign_params* params, const octet pubkey[])
+{
+	err_t st = ERR_BAD_INPUT, code;
+	if ((code = params_check(params)))
+		return code;
+	if (!pubkey)
+		return ERR_BAD_INPUT;
+	if ((code = bignPubkeyValBatch(&st, params, pubkey, 1)))
+		return code;
+	return st;
+}
+
+/* keys + key_len i <- the first key_len octets of (K.x || K.y), K = d_i Q_i, for items with status 0 */
+err_t bignDHBatch(err_t* status, octet* keys, const bign_params* params, const octet* privkeys,
+	const octet* pubkeys, size_t key_len, size_t count)
+{
+	err_t code;
+	b2g_slot *s0, *s1;
+	void *d_k, *d_p, *d_out, *d_st;
+	octet* full = 0;
+	size_t no, i;
+	if ((code = params_check(params)))
+		return code;
+	if (count && (!status || !privkeys || !pubkeys || (key_len && !keys)))
+		return ERR_BAD_INPUT;
+	no = params->l / 4;
+	if (key_len > 2 * no)
+		return ERR_BAD_SHAREDKEY;
+	if ((code = b2g_ensure_device()))
+		return code;
+	if (!count)
+		return ERR_OK;
+	if (!(full = (octet*)malloc(2 * no * count)))
+		return ERR_OUTOFMEMORY;
+	b2g_lock();
+	s0 = b2g_slot_get(0), s1 = b2g_slot_get(1);
+	if ((code = stage_in(s0, 0, privkeys, no * count, &d_k)) || (code = stage_in(s0, 1, pubkeys, 2 * no * count, &d_p)) ||
+		(code = b2g_slot_buf(s0, 2, 2 * no * count, &d_out)) || (code = b2g_slot_buf(s1, 0, 4 * count, &d_st)))
+		goto done;
+	CU(cudaMemsetAsync(d_out, 0, 2 * no * count, s0->stream), "memset(bign dh out)");
+	if ((code = b2g_bignDHBatchL_dev(params->l, d_st, d_out, d_k, d_p, count, s0->stream)))
+		goto done;
+	CU(cudaMemcpyAsync(status, d_st, 4 * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(bign status)");
+	CU(cudaMemcpyAsync(full, d_out, 2 * no * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(bign dh)");
+	/* private keys and shared points were staged on the device: wipe them */
+	CU(cudaMemsetAsync(d_k, 0, no * count, s0->stream), "memset(bign keys)");
+	CU(cudaMemsetAsync(d_out, 0, 2 * no * count, s0->stream), "memset(bign dh out)");
+	CU(cudaStreamSynchronize(s0->stream), "sync(bign dh)");
+	for (i = 0; i < count; ++i)
+		if (status[i] == ERR_OK)
+			memcpy(keys + key_len * i, full + 2 * no * i, key_len);
+done:
+	if (code)
+		cudaStreamSynchronize(s0->stream);
+	b2g_unlock();
+	if (full)
+	{
+		memset(full, 0, 2 * no * count);
+		free(full);
+	}
+	return code;
+}
+
+err_t bignDH(octet key[], const bign_params* params, const octet privkey[], const octet pubkey[], size_t key_len)
+{
+	err_t st = ERR_BAD_INPUT, code;
+	if ((code = params_check(params)))
+		return code;
+	if (!privkey || !pubkey || (key_len && !key))
+		return ERR_BAD_INPUT;
+	if ((code = bignDHBatch(&st, key, params, privkey, pubkey, key_len, 1)))
+		return code;
+	return st;
+}

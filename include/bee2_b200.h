@@ -41,16 +41,18 @@ typedef uint64_t word;
 typedef int bool_t;
 typedef u32 err_t;
 
-/* ---- error codes: include/bee2/core/err.h:72,74,92,112,132,180,184,186,196 ---- */
+/* ---- error codes: include/bee2/core/err.h:72,74,92,112,132,138,180,184,186,190,196 ---- */
 #define ERR_OK 0u
 #define ERR_BAD_INPUT 109u
 #define ERR_OUTOFMEMORY 110u
 #define ERR_NOT_IMPLEMENTED 119u
 #define ERR_FILE_NOT_FOUND 202u
 #define ERR_BAD_OID 301u
+#define ERR_BAD_RNG 304u
 #define ERR_BAD_PARAMS 502u
 #define ERR_BAD_PRIVKEY 504u
 #define ERR_BAD_PUBKEY 505u
+#define ERR_BAD_SHAREDKEY 507u
 #define ERR_BAD_SIG 510u
 #define ERR_BAD_MAC 511u
 /* engine-specific (outside the reference's ranges) */
@@ -251,6 +253,22 @@ err_t bignVerify(const bign_params* params, const octet oid_der[], size_t oid_le
 err_t bignSign2(octet sig[], const bign_params* params, const octet oid_der[], size_t oid_len,
 	const octet hash[], const octet privkey[], const void* t, size_t t_len);
 err_t bignPubkeyCalc(octet pubkey[], const bign_params* params, const octet privkey[]);
+/* drop-in: bign.h (bign_misc.c:182-300, :317-352, :437-515). gen_i is the reference's generator
+   callback (defs.h:520-524); the private key is drawn on the host exactly as the reference draws it
+   (zzRandNZMod, no octets per attempt), the public key is computed on the device. */
+typedef void (*gen_i)(void* buf, size_t count, void* state);
+err_t bignKeypairGen(octet privkey[], octet pubkey[], const bign_params* params, gen_i rng, void* rng_state);
+err_t bignKeypairVal(const bign_params* params, const octet privkey[], const octet pubkey[]);
+err_t bignPubkeyVal(const bign_params* params, const octet pubkey[]);
+err_t bignDH(octet key[], const bign_params* params, const octet privkey[], const octet pubkey[], size_t key_len);
+/* batch forms: keys are drawn in item order; status[i] is what the one-shot call would return */
+err_t bignKeypairGenBatch(octet* privkeys, octet* pubkeys, const bign_params* params, gen_i rng,
+	void* rng_state, size_t count);
+err_t bignKeypairValBatch(err_t* status, const bign_params* params, const octet* privkeys,
+	const octet* pubkeys, size_t count);
+err_t bignPubkeyValBatch(err_t* status, const bign_params* params, const octet* pubkeys, size_t count);
+err_t bignDHBatch(err_t* status, octet* keys, const bign_params* params, const octet* privkeys,
+	const octet* pubkeys, size_t key_len, size_t count);
 /* batch: item i uses hashes + no i, sigs + (no + no/2) i, pubkeys + 2 no i (l = 128: 32, 48, 64
    octets per item); status[i] = the err_t the
    reference's bignVerify would return for that item. Return value: ERR_OK when the batch
@@ -290,6 +308,9 @@ err_t b2g_bignSign2BatchL_t_dev(size_t l, void* d_status, void* d_sigs, const oc
 	const void* d_hashes, const void* d_privkeys, size_t count, const void* t, size_t t_len, void* stream);
 err_t b2g_bignPubkeyCalcBatchL_dev(size_t l, void* d_status, void* d_pubkeys, const void* d_privkeys,
 	size_t count, void* stream);
+err_t b2g_bignDHBatchL_dev(size_t l, void* d_status, void* d_out, const void* d_privkeys,
+	const void* d_pubkeys, size_t count, void* stream);
+err_t b2g_bignPubkeyValBatchL_dev(size_t l, void* d_status, const void* d_pubkeys, size_t count, void* stream);
 err_t b2g_ecMulABatchL_dev(size_t l, void* d_b, void* d_ok, const void* d_a, const void* d_d, size_t d_len,
 	size_t count, void* stream);
 err_t b2g_ecAddMulABatchL_dev(size_t l, void* d_b, void* d_ok, const void* d_a, const void* d_d, size_t d_len,

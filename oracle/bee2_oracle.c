@@ -357,7 +357,7 @@ static void belt_wbl(u8* buf, size_t count, const u32 key[8])
 
 #define FE_MAXW 8
 typedef struct { u64 w[FE_MAXW]; } fe;           /* words above n are kept 0 */
-typedef struct { int n; size_t no; fe p, q, yG; } lvl;
+typedef struct { int n; size_t no; fe p, q, yG, b; } lvl;
 
 static const u8 Q128_LE[32] = { /* q of bign-curve256v1 */
 	0x07, 0x66, 0x3D, 0x26, 0x99, 0xBF, 0x5A, 0x7E, 0xFC, 0x4D, 0xFB, 0x0D, 0xD6, 0x8E, 0x5C, 0xD9,
@@ -384,6 +384,18 @@ static const u8 YG256_LE[64] = { /* base point G = (0, yG) */
 	0xDA, 0xCA, 0xCC, 0x00, 0x1B, 0xF8, 0xED, 0xD2, 0xE2, 0xBC, 0x61, 0xB3, 0xB3, 0x41, 0xAB, 0xB0,
 	0xAB, 0x8F, 0xD1, 0xA0, 0xF7, 0xE6, 0x82, 0xB1, 0x81, 0x76, 0x03, 0xE4, 0x7A, 0xFF, 0x26, 0xA8};
 
+static const u8 B128_LE[32] = { /* coefficient b of bign-curve256v1 */
+	0xF1, 0x03, 0x9C, 0xD6, 0x6B, 0x7D, 0x2E, 0xB2, 0x53, 0x92, 0x8B, 0x97, 0x69, 0x50, 0xF5, 0x4C,
+	0xBE, 0xFB, 0xD8, 0xE4, 0xAB, 0x3A, 0xC1, 0xD2, 0xED, 0xA8, 0xF3, 0x15, 0x15, 0x6C, 0xCE, 0x77};
+static const u8 B192_LE[48] = { /* coefficient b of bign-curve384v1 */
+	0x64, 0xBF, 0x73, 0x68, 0x23, 0xFC, 0xA7, 0xBC, 0x7C, 0xBD, 0xCE, 0xF3, 0xF0, 0xE2, 0xBD, 0x14,
+	0x3A, 0x2E, 0x71, 0xE9, 0xF9, 0x6A, 0x21, 0xA6, 0x96, 0xB1, 0xFB, 0x0F, 0xBB, 0x48, 0x27, 0x71,
+	0xD2, 0x34, 0x5D, 0x65, 0xAB, 0x5A, 0x07, 0x33, 0x20, 0xEF, 0x9C, 0x95, 0xE1, 0xDF, 0x75, 0x3C};
+static const u8 B256_LE[64] = { /* coefficient b of bign-curve512v1 */
+	0x90, 0x9C, 0x13, 0xD6, 0x98, 0x69, 0x34, 0x09, 0x7A, 0xA2, 0x49, 0x3A, 0x27, 0x22, 0x86, 0xEA,
+	0x43, 0xA2, 0xAC, 0x87, 0x8C, 0x00, 0x33, 0x29, 0x95, 0x5E, 0x24, 0xC4, 0xB5, 0xDC, 0x11, 0x27,
+	0x88, 0xB0, 0xAD, 0xDA, 0xE3, 0x13, 0xCE, 0x17, 0x51, 0x25, 0x5D, 0xDD, 0xEE, 0xA9, 0xC6, 0x5B,
+	0x89, 0x58, 0xFD, 0x60, 0x6A, 0x5D, 0x8C, 0xD8, 0x43, 0x8C, 0x3B, 0x93, 0x44, 0x59, 0xB4, 0x6C};
 static fe fe_from_n(const u8* b, size_t no) { fe r; memset(&r, 0, sizeof r); memcpy(r.w, b, no); return r; }
 static const lvl* level(size_t l)
 {
@@ -395,6 +407,7 @@ static const lvl* level(size_t l)
 		static const u64 cs[3] = {189, 317, 569};
 		static const u8* const qs[3] = {Q128_LE, Q192_LE, Q256_LE};
 		static const u8* const ys[3] = {YG128_LE, YG192_LE, YG256_LE};
+		static const u8* const bs[3] = {B128_LE, B192_LE, B256_LE};
 		int i, j;
 		for (i = 0; i < 3; ++i)
 		{
@@ -402,7 +415,7 @@ static const lvl* level(size_t l)
 			memset(&L[i].p, 0, sizeof(fe));
 			for (j = 0; j < L[i].n; ++j) L[i].p.w[j] = ~0ull;
 			L[i].p.w[0] -= cs[i] - 1;
-			L[i].q = fe_from_n(qs[i], L[i].no), L[i].yG = fe_from_n(ys[i], L[i].no);
+			L[i].q = fe_from_n(qs[i], L[i].no), L[i].yG = fe_from_n(ys[i], L[i].no), L[i].b = fe_from_n(bs[i], L[i].no);
 		}
 		ready = 1;
 	}
@@ -676,6 +689,39 @@ u32 orc_bignPubkeyCalc(size_t l, u8* pubkey, const u8* privkey)
 	return ORC_OK;
 }
 u32 orc_bignPubkeyCalc128(u8 pubkey[64], const u8 privkey[32]) { return orc_bignPubkeyCalc(128, pubkey, privkey); }
+
+/* bign_misc.c:317-352: coordinates < p and y^2 = x^3 - 3x + b (ecpIsOnA, ecp_j.c) */
+u32 orc_bignPubkeyVal(size_t l, const u8* pubkey)
+{
+	const lvl* L = level(l);
+	fe x, y, lhs, rhs, t;
+	if (!L) return 119u;
+	x = fe_from(L, pubkey), y = fe_from(L, pubkey + L->no);
+	if (fe_cmp(x, L->p) >= 0 || fe_cmp(y, L->p) >= 0) return ORC_BAD_PUBKEY;
+	lhs = fp_sqr(L, y);
+	t = fp_add(L, fp_add(L, x, x), x);
+	rhs = fp_add(L, fp_sub(L, fp_mul(L, fp_sqr(L, x), x), t), L->b);
+	return fe_cmp(lhs, rhs) == 0 ? ORC_OK : ORC_BAD_PUBKEY;
+}
+
+/* bign_misc.c:437-500: key <- the first key_len octets of (K.x || K.y), K = d Q */
+u32 orc_bignDH(size_t l, u8* key, const u8* privkey, const u8* pubkey, size_t key_len)
+{
+	const lvl* L = level(l);
+	fe d, x, y;
+	u8 xy[128];
+	u32 code;
+	if (!L) return 119u;
+	if (key_len > 2 * L->no) return 507u;
+	d = fe_from(L, privkey);
+	if (fe_is0(d) || fe_cmp(d, L->q) >= 0) return ORC_BAD_PRIVKEY;
+	if ((code = orc_bignPubkeyVal(l, pubkey))) return code;
+	if (!pt_to_affine(L, &x, &y, pt_mul(L, pt_affine(fe_from(L, pubkey), fe_from(L, pubkey + L->no)), privkey, L->no)))
+		return ORC_BAD_PARAMS;
+	fe_to(L, xy, x), fe_to(L, xy + L->no, y);
+	memcpy(key, xy, key_len);
+	return ORC_OK;
+}
 
 /* bign_sign.c:140-245 */
 u32 orc_bignSign2(size_t l, u8* sig, const u8* oid_der, size_t oid_len, const u8* hash,

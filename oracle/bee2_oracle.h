@@ -105,6 +105,8 @@ uint32_t orc_bignSign2(size_t l, uint8_t* sig, const uint8_t* oid_der, size_t oi
 	const uint8_t* hash, const uint8_t* privkey, const void* t, size_t t_len);
 uint32_t orc_bignPubkeyCalc(size_t l, uint8_t* pubkey, const uint8_t* privkey);
 int orc_ecMulA(size_t l, uint8_t* b, const uint8_t* a, const uint8_t* d, size_t d_len);
+uint32_t orc_bignPubkeyVal(size_t l, const uint8_t* pubkey);                        /* bign_misc.c:317-352 */
+uint32_t orc_bignDH(size_t l, uint8_t* key, const uint8_t* privkey, const uint8_t* pubkey, size_t key_len); /* :437-500 */
 /* field helpers exposed for unit tests of the device field layer (zm.c:214-253, gfp.c:33-44) */
 void orc_gfpMul(uint8_t c[32], const uint8_t a[32], const uint8_t b[32]);
 void orc_gfpInv(uint8_t c[32], const uint8_t a[32]);

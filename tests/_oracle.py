@@ -21,7 +21,7 @@ def port():
         L = C.CDLL(os.path.join(REF_DIR, "libbee2oracle.so"))
         L.orc_beltH.restype = C.c_void_p
         for n in ("orc_beltCHEWrap", "orc_beltCHEUnwrap", "orc_beltDWPWrap", "orc_beltDWPUnwrap", "orc_bashHash", "orc_beltCTR", "orc_beltECBEncr", "orc_beltECBDecr", "orc_bignVerify128",
-                  "orc_bignSign2_128", "orc_bignPubkeyCalc128", "orc_bignVerify", "orc_bignSign2", "orc_bignPubkeyCalc"):
+                  "orc_bignSign2_128", "orc_bignPubkeyCalc128", "orc_bignVerify", "orc_bignSign2", "orc_bignPubkeyCalc", "orc_bignPubkeyVal", "orc_bignDH"):
             getattr(L, n).restype = C.c_uint32
         L.orc_ecMulA128.restype = C.c_int
         L.orc_ecMulA.restype = C.c_int
@@ -204,6 +204,16 @@ def bignPubkeyCalc(priv: bytes, l: int = 128):
     return code, pub.raw
 
 
+def bignPubkeyVal(pub: bytes, l: int = 128) -> int:
+    return port().orc_bignPubkeyVal(sz(l), bytes(pub))
+
+
+def bignDH(priv: bytes, pub: bytes, key_len: int, l: int = 128):
+    key = C.create_string_buffer(max(key_len, 1))
+    code = port().orc_bignDH(sz(l), key, bytes(priv), bytes(pub), sz(key_len))
+    return code, key.raw[:key_len] if code == 0 else b""
+
+
 def ecMulA(a: bytes, d: bytes, l: int = 128):
     out = C.create_string_buffer(l // 2)
     ok = port().orc_ecMulA(sz(l), out, bytes(a), bytes(d), sz(len(d)))
@@ -259,6 +269,34 @@ def ref_bignSign2(hash_: bytes, priv: bytes, t: bytes = None, oid: bytes = OID, 
     code = ref().bignSign2(sig, C.byref(ref_params(l)), oid, sz(len(oid)), bytes(hash_), bytes(priv), t,
                            sz(len(t) if t else 0))
     return code, sig.raw
+
+
+def ref_bignPubkeyVal(pub: bytes, l: int = 128) -> int:
+    return ref().bignPubkeyVal(C.byref(ref_params(l)), bytes(pub))
+
+
+def ref_bignKeypairVal(priv: bytes, pub: bytes, l: int = 128) -> int:
+    return ref().bignKeypairVal(C.byref(ref_params(l)), bytes(priv), bytes(pub))
+
+
+def ref_bignDH(priv: bytes, pub: bytes, key_len: int, l: int = 128):
+    key = C.create_string_buffer(max(key_len, 1))
+    code = ref().bignDH(key, C.byref(ref_params(l)), bytes(priv), bytes(pub), sz(key_len))
+    return code, key.raw[:key_len] if code == 0 else b""
+
+
+def ref_bignKeypairGen(stream: bytes, l: int = 128):
+    """bignKeypairGen of the reference fed from `stream`; returns (code, priv, pub, octets consumed)."""
+    pos = [0]
+
+    def fn(buf, count, state):
+        chunk = stream[pos[0]:pos[0] + count]
+        C.memmove(buf, chunk, count)
+        pos[0] += count
+    cb = C.CFUNCTYPE(None, C.c_void_p, sz, C.c_void_p)(fn)
+    priv, pub = C.create_string_buffer(l // 4), C.create_string_buffer(l // 2)
+    code = ref().bignKeypairGen(priv, pub, C.byref(ref_params(l)), cb, None)
+    return code, priv.raw, pub.raw, pos[0]
 
 
 def ref_bignPubkeyCalc(priv: bytes, l: int = 128):

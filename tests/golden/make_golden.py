@@ -229,6 +229,33 @@ def main():
             rec["bad"] = {"hash": bytes(bad_h).hex(), "sig": bytes(bad_sig).hex(), "pubkey": bytes(bad_pub).hex(),
                           "verify": o.ref_bignVerify(bytes(bad_h), bytes(bad_sig), bytes(bad_pub), oid, l)}
             out["bignL"].append(rec)
+    # key generation / validation / Diffie-Hellman (bign_misc.c), all three levels; own generator again
+    rng3 = np.random.default_rng(20261019)
+    rb3 = lambda n: rng3.integers(0, 256, size=n, dtype=np.uint8).tobytes()  # noqa: E731
+    out["bignMisc"] = []
+    for l in (128, 192, 256):
+        no = l // 4
+        # generator stream: an all-ones draw (>= p, rejected), an all-zero draw (rejected), then real octets
+        stream = b"\xff" * no + bytes(no) + rb3(3 * no)
+        code, priv, pub, used = o.ref_bignKeypairGen(stream, l)
+        assert code == 0 and used == 3 * no
+        rec = {"l": l, "stream": stream.hex(), "privkey": priv.hex(), "pubkey": pub.hex(), "used": used, "dh": [], "val": []}
+        for i in range(4):
+            u = bytearray(rb3(no))
+            u[no - 1] &= 0x7F
+            if i == 3:
+                u = bytearray(no)                       # d = 0 -> ERR_BAD_PRIVKEY
+            key_len = [2 * no, no, 7, no + 9][i]
+            code, key = o.ref_bignDH(bytes(u), pub, key_len, l)
+            rec["dh"].append({"privkey": bytes(u).hex(), "key_len": key_len, "code": code, "key": key.hex()})
+        offcurve = bytearray(pub)
+        offcurve[1] ^= 4
+        big = b"\xff" * no + pub[no:]
+        for name, pk in (("ok", pub), ("offcurve", bytes(offcurve)), ("x>=p", big)):
+            rec["val"].append({"case": name, "pubkey": pk.hex(), "pubkey_val": o.ref_bignPubkeyVal(pk, l),
+                               "keypair_val": o.ref_bignKeypairVal(priv, pk, l),
+                               "dh": o.ref_bignDH(priv, pk, no, l)[0]})
+        out["bignMisc"].append(rec)
     with open(os.path.join(HERE, "ref_vectors.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote ref_vectors.json")

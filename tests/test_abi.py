@@ -18,6 +18,7 @@ def _declared():
     src = open(os.path.join(ROOT, "include", "bee2_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     src = "\n".join(l for l in src.splitlines() if not l.strip().startswith("#"))
+    src = re.sub(r"typedef\s+[^;{]*\(\s*\*\s*\w+\s*\)\s*\([^;]*\)\s*;", "", src)      # function-pointer typedefs (gen_i)
     names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", src))
     names |= set(re.findall(r"extern\s+const\s+char\s+([A-Za-z_][A-Za-z0-9_]*)\s*\[", src))
     return names - {"defined", "sizeof"}

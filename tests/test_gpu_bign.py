@@ -202,6 +202,59 @@ def test_levels_ecMulA_vs_oracle(l):
             assert ok[i] == 1 and (0, got[i].tobytes()) == o.bignPubkeyCalc(e.to_bytes(no, "little"), l)
 
 
+@pytest.mark.parametrize("l", [128, 192, 256])
+def test_keypair_gen_val_dh_fixtures(l):
+    """bignKeypairGen / KeypairVal / PubkeyVal / DH (bign_misc.c:182-515) against outputs of the unmodified
+    reference (ref_vectors.json "bignMisc"), incl. rejected generator draws and invalid public keys."""
+    p = b.bignParamsStd(b.BIGN_CURVES[l])
+    no = l // 4
+    t = [t for t in REF["bignMisc"] if t["l"] == l][0]
+    priv, pub, used = b.bignKeypairGenBatch(p, bytes.fromhex(t["stream"]), 1)
+    assert (priv[0].tobytes().hex(), pub[0].tobytes().hex(), used) == (t["privkey"], t["pubkey"], t["used"])
+    priv_b, pub_b = bytes.fromhex(t["privkey"]), bytes.fromhex(t["pubkey"])
+    for d in t["dh"]:
+        code, key = b.bignDH(p, bytes.fromhex(d["privkey"]), pub_b, d["key_len"])
+        assert code == d["code"] and (code != 0 or key.hex() == d["key"])
+    assert b.bignDH(p, priv_b, pub_b, 2 * no + 1)[0] == b.ERR_BAD_SHAREDKEY
+    for v_ in t["val"]:
+        pk = bytes.fromhex(v_["pubkey"])
+        assert b.bignPubkeyVal(p, pk) == v_["pubkey_val"], v_["case"]
+        assert b.bignKeypairVal(p, priv_b, pk) == v_["keypair_val"], v_["case"]
+        assert b.bignDH(p, priv_b, pk, no)[0] == v_["dh"], v_["case"]
+
+
+@pytest.mark.parametrize("l", [128, 256])
+def test_dh_batch_vs_oracle(l):
+    """d_i Q_j = d_j Q_i (both sides of the exchange agree), keys equal the oracle's, statuses item by item."""
+    rng = np.random.default_rng(300 + l)
+    p, n, no = b.bignParamsStd(b.BIGN_CURVES[l]), 96, l // 4
+    stream = rng.integers(0, 256, 2 * n * no, dtype=np.uint8).tobytes()
+    priv, pub, used = b.bignKeypairGenBatch(p, stream, n)
+    assert used <= len(stream) and (b.bignKeypairValBatch(p, priv, pub) == 0).all()
+    assert (b.bignPubkeyValBatch(p, pub) == 0).all()
+    peer = np.roll(pub, 1, axis=0).copy()
+    st1, k1 = b.bignDHBatch(p, priv, peer, 2 * no)
+    st2, k2 = b.bignDHBatch(p, np.roll(priv, 1, axis=0).copy(), pub, 2 * no)
+    assert (st1 == 0).all() and (st2 == 0).all() and np.array_equal(k1, k2)
+    for i in range(0, n, 12):
+        assert o.bignDH(priv[i].tobytes(), peer[i].tobytes(), 2 * no, l) == (0, k1[i].tobytes())
+    # corrupted items: off-curve points, d = 0, d = q, x >= p
+    q = (CURVE_Q[l] if l != 128 else Q)
+    bad_pub, bad_priv = peer.copy(), priv.copy()
+    bad_pub[::7, 5] ^= 1
+    bad_priv[3] = 0
+    bad_priv[10] = A(q.to_bytes(no, "little"))
+    bad_pub[20, :no] = 0xFF
+    st, keys = b.bignDHBatch(p, bad_priv, bad_pub, no)
+    want = [o.bignDH(bad_priv[i].tobytes(), bad_pub[i].tobytes(), no, l) for i in range(n)]
+    assert [int(x) for x in st] == [w[0] for w in want]
+    assert all(keys[i].tobytes() == want[i][1] for i in range(n) if want[i][0] == 0)
+    assert {0, 504, 505} <= set(int(x) for x in st)
+    assert [int(x) for x in b.bignPubkeyValBatch(p, bad_pub)] == [o.bignPubkeyVal(bad_pub[i].tobytes(), l) for i in range(n)]
+    kv = b.bignKeypairValBatch(p, bad_priv, pub)
+    assert kv[3] == 504 and kv[10] == 504 and kv[0] == 0
+
+
 def _corrupt(rng, hashes, sigs, pubs):
     """~1/3 of the items get one of the SURVEY §8d corruptions."""
     n = hashes.shape[0]

@@ -178,6 +178,21 @@ def test_reference_fixtures_levels_192_256():
                             oid, l) == bad["verify"]
 
 
+def test_reference_fixtures_dh_pubkeyval():
+    """orc_bignDH / orc_bignPubkeyVal against reference outputs for the three levels (ref_vectors.json "bignMisc")."""
+    for t in REF["bignMisc"]:
+        l, no = t["l"], t["l"] // 4
+        priv, pub = bytes.fromhex(t["privkey"]), bytes.fromhex(t["pubkey"])
+        assert o.bignPubkeyCalc(priv, l) == (0, pub)
+        for d in t["dh"]:
+            code, key = o.bignDH(bytes.fromhex(d["privkey"]), pub, d["key_len"], l)
+            assert code == d["code"] and (code != 0 or key.hex() == d["key"])
+        for v_ in t["val"]:
+            pk = bytes.fromhex(v_["pubkey"])
+            assert o.bignPubkeyVal(pk, l) == v_["pubkey_val"]
+            assert o.bignDH(priv, pk, no, l)[0] == v_["dh"]
+
+
 @pytest.mark.skipif(o.ref() is None, reason="oracle/_ref/libbee2ref_64.so not built here")
 def test_live_differential_against_reference():
     rng = np.random.default_rng(5)
