@@ -26,7 +26,7 @@ __all__ = [
     "bashHashBatch_dev", "bashFBatch_dev", "beltCTR_dev", "beltECB_dev", "beltECBEncrBatch_dev",
     "beltHashBatch_dev", "bignVerifyBatch_dev", "bignSign2Batch_dev", "bignPubkeyCalcBatch_dev",
     "ecMulABatch_dev", "bignVerifyBatchL_dev", "bignKeypairGenBatch", "bignKeypairValBatch", "bignPubkeyValBatch",
-    "bignDHBatch", "bignDH", "bignPubkeyVal", "bignKeypairVal", "ERR_BAD_RNG", "ERR_BAD_SHAREDKEY", "pinned_empty", "BIGN_CURVES",
+    "bignDHBatch", "bignSignBatch", "GEN_I", "bignDH", "bignPubkeyVal", "bignKeypairVal", "ERR_BAD_RNG", "ERR_BAD_SHAREDKEY", "pinned_empty", "BIGN_CURVES",
 ]
 
 ERR_OK = 0
@@ -142,6 +142,11 @@ def _declare(L: C.CDLL) -> None:
         "bignKeypairGen": (u32, [vp, vp, vp, vp, vp]), "bignKeypairGenBatch": (u32, [vp, vp, vp, vp, vp, sz]),
         "bignKeypairVal": (u32, [vp, vp, vp]), "bignKeypairValBatch": (u32, [vp, vp, vp, vp, sz]),
         "bignPubkeyVal": (u32, [vp, vp]), "bignPubkeyValBatch": (u32, [vp, vp, vp, sz]),
+        "bignSign": (u32, [vp, vp, vp, sz, vp, vp, vp, vp]), "bignSignBatch": (u32, [vp, vp, vp, vp, sz, vp, vp, vp, vp, sz]),
+        **{f"bign{lv}{fn}": sig_ for lv in (128, 192, 256) for fn, sig_ in (
+            ("KeypairGen", (u32, [vp, vp, vp, vp])), ("KeypairVal", (u32, [vp, vp])), ("PubkeyVal", (u32, [vp])),
+            ("PubkeyCalc", (u32, [vp, vp])), ("DH", (u32, [vp, vp, vp, sz])), ("Sign", (u32, [vp, vp, vp, vp, vp])),
+            ("Sign2", (u32, [vp, vp, vp, vp, sz])), ("Verify", (u32, [vp, vp, vp])))},
         "bignDH": (u32, [vp, vp, vp, vp, sz]), "bignDHBatch": (u32, [vp, vp, vp, vp, vp, sz, sz]),
         "b2g_bignDHBatchL_dev": (u32, [sz, vp, vp, vp, vp, sz, vp]),
         "b2g_bignPubkeyValBatchL_dev": (u32, [sz, vp, vp, sz, vp]),
@@ -601,6 +606,19 @@ def bignKeypairGenBatch(params: BignParams, rng_stream: bytes, count: int):
     _chk("bignKeypairGenBatch", lib().bignKeypairGenBatch(priv.ctypes.data, pub.ctypes.data, C.addressof(params),
                                                           C.cast(cb, C.c_void_p), None, count))
     return priv, pub, pos[0]
+
+
+def bignSignBatch(params: BignParams, oid_der: bytes, hashes: np.ndarray, privkeys: np.ndarray, rng_stream: bytes):
+    """bignSign on a batch with the generator octets taken from rng_stream; returns (status, sigs, consumed)."""
+    no = params.l // 4
+    count = hashes.size // no
+    status = np.full(count, 0xFFFFFFFF, dtype=np.uint32)
+    sigs = np.zeros((count, no + no // 2), dtype=np.uint8)
+    ko = _buf(oid_der)
+    cb, pos = _rng_callback(bytes(rng_stream))
+    _chk("bignSignBatch", lib().bignSignBatch(status.ctypes.data, sigs.ctypes.data, C.addressof(params), ko[1], ko[2],
+                                              hashes.ctypes.data, privkeys.ctypes.data, C.cast(cb, C.c_void_p), None, count))
+    return status, sigs, pos[0]
 
 
 def bignKeypairValBatch(params: BignParams, privkeys: np.ndarray, pubkeys: np.ndarray) -> np.ndarray:

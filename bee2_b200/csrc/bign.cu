@@ -485,7 +485,7 @@ template <int NB> __device__ __forceinline__ void wbl(const BeltSmallT& S, u32 (
 template <int N> __global__ void __launch_bounds__(BIGN_THREADS, BIGN_BLOCKS(N))
 bign_sign2_kernel(u32* __restrict__ status, u8* __restrict__ sigs, const u8* __restrict__ hashes,
 	const u8* __restrict__ privkeys, u64 count, const OidArg oid, const TArg targ,
-	const uint4* __restrict__ gtab)
+	const uint4* __restrict__ gtab, const u8* __restrict__ nonces)
 {
 	constexpr int NO = 4 * N, H2 = N / 2;
 	__shared__ u32 tab[256];
@@ -508,14 +508,22 @@ bign_sign2_kernel(u32* __restrict__ status, u8* __restrict__ sigs, const u8* __r
 	}
 	if (live)
 	{
-		// theta <- belt-hash(oid || d || t); k <- H; k <- WBL_theta(k) until 0 < k < q (:198-218)
-		u32 theta[8];
-		hash_oid_ab<N>(S, theta, oid, d, (const u32*)0, targ.t, targ.len);
+		if (nonces)
+		{
+			// bignSign (bign_sign.c:27-125): the one-time key was drawn by the caller's generator
+			load_uN<N>(k, nonces + NO * i);
+		}
+		else
+		{
+			// theta <- belt-hash(oid || d || t); k <- H; k <- WBL_theta(k) until 0 < k < q (:198-218)
+			u32 theta[8];
+			hash_oid_ab<N>(S, theta, oid, d, (const u32*)0, targ.t, targ.len);
 #pragma unroll
-		for (int j = 0; j < N; ++j) k[j] = H[j];
-		do
-			wbl<N / 4>(S, k, theta);
-		while (uN_is_zero<N>(k) || geq_q<N>(k));
+			for (int j = 0; j < N; ++j) k[j] = H[j];
+			do
+				wbl<N / 4>(S, k, theta);
+			while (uN_is_zero<N>(k) || geq_q<N>(k));
+		}
 		// R <- k G (:219-224)
 		pt_set_inf<N>(R);
 		{
@@ -825,13 +833,13 @@ extern "C" u32 b2g_bignVerifyBatch_dev(void* d_status, const u8 oid_der[], size_
 }
 
 template <int N> static u32 sign2_launch(void* d_status, void* d_sigs, const OidArg& oid, const TArg& ta,
-	const void* d_hashes, const void* d_privkeys, size_t count, cudaStream_t st)
+	const void* d_hashes, const void* d_privkeys, size_t count, cudaStream_t st, const void* d_nonces = 0)
 {
 	const uint4* gtab;
 	u32 e = bign_ensure_gtab<N>(st, &gtab);
 	if (e) return e;
 	bign_sign2_kernel<N><<<bign_grid(count), BIGN_THREADS, 0, st>>>((u32*)d_status, (u8*)d_sigs,
-		(const u8*)d_hashes, (const u8*)d_privkeys, count, oid, ta, gtab);
+		(const u8*)d_hashes, (const u8*)d_privkeys, count, oid, ta, gtab, (const u8*)d_nonces);
 	b2g_note_launch();
 	return b2g_check_launch("bign_sign2_kernel");
 }
@@ -992,6 +1000,28 @@ extern "C" u32 b2g_bignPubkeyValBatchL_dev(size_t l, void* d_status, const void*
 	if ((uintptr_t)d_status & 3) return B2G_BAD_INPUT;
 	cudaStream_t st = (cudaStream_t)stream;
 #define CALL(N) dh_launch<N>(d_status, (void*)0, (const void*)0, d_pubkeys, count, 1u, st)
+	return BIGN_DISPATCH(l, CALL);
+#undef CALL
+}
+
+// bignSign on a batch: like sign2 but the one-time keys k_i (l/4 octets each, 0 < k_i < q, drawn by the
+// caller's generator) come from d_nonces
+extern "C" u32 b2g_bignSignBatchL_k_dev(size_t l, void* d_status, void* d_sigs, const u8 oid_der[], size_t oid_len,
+	const void* d_hashes, const void* d_privkeys, const void* d_nonces, size_t count, void* stream)
+{
+	u32 e = b2g_ensure_device();
+	if (e) return e;
+	OidArg oid;
+	TArg ta;
+	if ((e = make_oid(oid, oid_der, oid_len))) return e;
+	if (l != 128 && l != 192 && l != 256) return 119u;
+	if (!d_nonces) return B2G_BAD_INPUT;
+	for (size_t i = 0; i < BIGN_MAX_T; ++i) ta.t[i] = 0;
+	ta.len = 0;
+	if (count == 0) return B2G_OK;
+	if ((uintptr_t)d_status & 3) return B2G_BAD_INPUT;
+	cudaStream_t st = (cudaStream_t)stream;
+#define CALL(N) sign2_launch<N>(d_status, d_sigs, oid, ta, d_hashes, d_privkeys, count, st, d_nonces)
 	return BIGN_DISPATCH(l, CALL);
 #undef CALL
 }

@@ -474,9 +474,9 @@ err_t ecAddMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d
    (bign_misc.c:213 hands ec->f->mod, zz_mod.c:463-484): no octets from rng per attempt, at most
    B_PER_IMPOSSIBLE + 1 attempts. For d in [q, p) (probability ~2^-l) the engine then reports
    ERR_BAD_PRIVKEY where the reference would go on with d mod q. */
-static int rand_nz_mod_p(octet d[], const bign_params* params, gen_i rng, void* rng_state)
+/* a <-R {1, ..., mod - 1} (zzRandNZMod, zz_mod.c:463-484; mod has 8 no bits here) */
+static int rand_nz_mod(octet d[], const octet mod[], size_t no, gen_i rng, void* rng_state)
 {
-	const size_t no = params->l / 4;
 	size_t tries = 64 + 1, i;
 	while (tries--)
 	{
@@ -485,9 +485,9 @@ static int rand_nz_mod_p(octet d[], const bign_params* params, gen_i rng, void* 
 		for (i = 0; i < no; ++i)
 			zero &= d[i] == 0;
 		for (i = no; i-- > 0;)
-			if (d[i] != params->p[i])
+			if (d[i] != mod[i])
 			{
-				less = d[i] < params->p[i];
+				less = d[i] < mod[i];
 				break;
 			}
 		if (!zero && less)
@@ -510,7 +510,7 @@ err_t bignKeypairGenBatch(octet* privkeys, octet* pubkeys, const bign_params* pa
 	no = params->l / 4;
 	/* the private keys are drawn in item order, like `count` successive bignKeypairGen calls */
 	for (i = 0; i < count; ++i)
-		if (!rand_nz_mod_p(privkeys + no * i, params, rng, rng_state))
+		if (!rand_nz_mod(privkeys + no * i, params->p, no, rng, rng_state))
 			return ERR_BAD_RNG;
 	if (!count)
 		return ERR_OK;
@@ -674,3 +674,120 @@ err_t bignDH(octet key[], const bign_params* params, const octet privkey[], cons
 		return code;
 	return st;
 }
+
+/* ---------------------------------------------------------------- bignSign (bign_sign.c:27-138) */
+/* status[i] = what bignSign would return for item i. One-time keys are drawn on the host with the
+   caller's generator in item order and only for items whose private key is valid — the order in
+   which `count` successive bignSign calls would consume the generator (:78-91). */
+err_t bignSignBatch(err_t* status, octet* sigs, const bign_params* params, const octet oid_der[],
+	size_t oid_len, const octet* hashes, const octet* privkeys, gen_i rng, void* rng_state, size_t count)
+{
+	err_t code;
+	b2g_slot *s0, *s1;
+	void *d_h, *d_k, *d_n, *d_sig, *d_st;
+	octet* nonces;
+	size_t no, so, i, j;
+	if ((code = params_check(params)))
+		return code;
+	no = params->l / 4, so = no + no / 2;
+	if (count && (!status || !sigs || !hashes || !privkeys))
+		return ERR_BAD_INPUT;
+	if (!oid_der_valid(oid_der, oid_len))
+		return ERR_BAD_OID;
+	if (!rng)
+		return ERR_BAD_RNG;
+	if ((code = b2g_ensure_device()))
+		return code;
+	if (!count)
+		return ERR_OK;
+	if (!(nonces = (octet*)calloc(count, no)))
+		return ERR_OUTOFMEMORY;
+	for (i = 0; i < count; ++i)
+	{
+		/* 0 < d < q ? (the device repeats the check and sets the status) */
+		const octet* d = privkeys + no * i;
+		int zero = 1, less = 0;
+		for (j = 0; j < no; ++j)
+			zero &= d[j] == 0;
+		for (j = no; j-- > 0;)
+			if (d[j] != params->q[j])
+			{
+				less = d[j] < params->q[j];
+				break;
+			}
+		if (zero || !less)
+			nonces[no * i] = 1;   /* a placeholder: the item ends with ERR_BAD_PRIVKEY */
+		else if (!rand_nz_mod(nonces + no * i, params->q, no, rng, rng_state))
+		{
+			memset(nonces, 0, count * no), free(nonces);
+			return ERR_BAD_RNG;
+		}
+	}
+	b2g_lock();
+	s0 = b2g_slot_get(0), s1 = b2g_slot_get(1);
+	if ((code = stage_in(s0, 0, hashes, no * count, &d_h)) || (code = stage_in(s0, 1, privkeys, no * count, &d_k)) ||
+		(code = stage_in(s0, 3, nonces, no * count, &d_n)) ||
+		(code = b2g_slot_buf(s0, 2, so * count, &d_sig)) || (code = b2g_slot_buf(s1, 0, 4 * count, &d_st)))
+		goto done;
+	if ((code = b2g_bignSignBatchL_k_dev(params->l, d_st, d_sig, oid_der, oid_len, d_h, d_k, d_n, count, s0->stream)))
+		goto done;
+	CU(cudaMemcpyAsync(status, d_st, 4 * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(bign status)");
+	CU(cudaStreamSynchronize(s0->stream), "sync(bign sign)");
+	for (i = 0; i < count; ++i)
+		if (status[i] == ERR_OK)
+			CU(cudaMemcpyAsync(sigs + so * i, (octet*)d_sig + so * i, so, cudaMemcpyDeviceToHost, s0->stream), "D2H(bign sig)");
+	/* private and one-time keys were staged on the device: wipe them */
+	CU(cudaMemsetAsync(d_k, 0, no * count, s0->stream), "memset(bign keys)");
+	CU(cudaMemsetAsync(d_n, 0, no * count, s0->stream), "memset(bign nonces)");
+	CU(cudaStreamSynchronize(s0->stream), "sync(bign sign)");
+done:
+	if (code)
+		cudaStreamSynchronize(s0->stream);
+	b2g_unlock();
+	memset(nonces, 0, count * no), free(nonces);
+	return code;
+}
+
+err_t bignSign(octet sig[], const bign_params* params, const octet oid_der[], size_t oid_len,
+	const octet hash[], const octet privkey[], gen_i rng, void* rng_state)
+{
+	err_t st = ERR_BAD_INPUT, code;
+	if ((code = params_check(params)))
+		return code;
+	if (!hash || !privkey || !sig)
+		return ERR_BAD_INPUT;
+	if ((code = bignSignBatch(&st, sig, params, oid_der, oid_len, hash, privkey, rng, rng_state, 1)))
+		return code;
+	return st;
+}
+
+/* ---------------------------------------------------------------- fixed-level wrappers
+   bign128.c:96-185, bign192.c, bign256.c: the standard curve of the level and the OID of its hash
+   algorithm (belt-hash / bash384 / bash512). The reference keeps a lazily created curve per level
+   (bign128.c:34-88); here the parameter block is a constant and the per-level tables live on the device. */
+static const octet oid_belt_hash[] = {0x06, 0x09, 0x2A, 0x70, 0x00, 0x02, 0x00, 0x22, 0x65, 0x1F, 0x51};
+static const octet oid_bash384[] = {0x06, 0x09, 0x2A, 0x70, 0x00, 0x02, 0x00, 0x22, 0x65, 0x4D, 0x0C};
+static const octet oid_bash512[] = {0x06, 0x09, 0x2A, 0x70, 0x00, 0x02, 0x00, 0x22, 0x65, 0x4D, 0x0D};
+
+#define BIGN_LEVEL_WRAPPERS(PFX, IDX, OID)                                                                   \
+	static const bign_params* PFX##_params(bign_params* p) { std_fill(p, &std_curves[IDX]); return p; }     \
+	err_t PFX##KeypairGen(octet privkey[], octet pubkey[], gen_i rng, void* rng_state)                       \
+	{ bign_params p; return bignKeypairGen(privkey, pubkey, PFX##_params(&p), rng, rng_state); }             \
+	err_t PFX##KeypairVal(const octet privkey[], const octet pubkey[])                                       \
+	{ bign_params p; return bignKeypairVal(PFX##_params(&p), privkey, pubkey); }                             \
+	err_t PFX##PubkeyVal(const octet pubkey[])                                                               \
+	{ bign_params p; return bignPubkeyVal(PFX##_params(&p), pubkey); }                                       \
+	err_t PFX##PubkeyCalc(octet pubkey[], const octet privkey[])                                             \
+	{ bign_params p; return bignPubkeyCalc(pubkey, PFX##_params(&p), privkey); }                             \
+	err_t PFX##DH(octet key[], const octet privkey[], const octet pubkey[], size_t key_len)                  \
+	{ bign_params p; return bignDH(key, PFX##_params(&p), privkey, pubkey, key_len); }                       \
+	err_t PFX##Sign(octet sig[], const octet hash[], const octet privkey[], gen_i rng, void* rng_state)      \
+	{ bign_params p; return bignSign(sig, PFX##_params(&p), OID, sizeof(OID), hash, privkey, rng, rng_state); } \
+	err_t PFX##Sign2(octet sig[], const octet hash[], const octet privkey[], const void* t, size_t t_len)    \
+	{ bign_params p; return bignSign2(sig, PFX##_params(&p), OID, sizeof(OID), hash, privkey, t, t_len); }   \
+	err_t PFX##Verify(const octet hash[], const octet sig[], const octet pubkey[])                           \
+	{ bign_params p; return bignVerify(PFX##_params(&p), OID, sizeof(OID), hash, sig, pubkey); }
+
+BIGN_LEVEL_WRAPPERS(bign128, 0, oid_belt_hash)
+BIGN_LEVEL_WRAPPERS(bign192, 1, oid_bash384)
+BIGN_LEVEL_WRAPPERS(bign256, 2, oid_bash512)

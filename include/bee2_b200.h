@@ -261,6 +261,39 @@ err_t bignKeypairGen(octet privkey[], octet pubkey[], const bign_params* params,
 err_t bignKeypairVal(const bign_params* params, const octet privkey[], const octet pubkey[]);
 err_t bignPubkeyVal(const bign_params* params, const octet pubkey[]);
 err_t bignDH(octet key[], const bign_params* params, const octet privkey[], const octet pubkey[], size_t key_len);
+/* drop-in: bign.h bignSign (bign_sign.c:27-138) — the randomised signature; the one-time key comes
+   from the caller's generator (zzRandNZMod over q), everything else runs on the device */
+err_t bignSign(octet sig[], const bign_params* params, const octet oid_der[], size_t oid_len,
+	const octet hash[], const octet privkey[], gen_i rng, void* rng_state);
+err_t bignSignBatch(err_t* status, octet* sigs, const bign_params* params, const octet oid_der[],
+	size_t oid_len, const octet* hashes, const octet* privkeys, gen_i rng, void* rng_state, size_t count);
+/* drop-in: bign128.h / bign192.h / bign256.h (bign128.c:96-185, bign192.c, bign256.c): the fixed-level
+   forms — standard curve of the level, OID of belt-hash / bash384 / bash512; with no = 32 / 48 / 64 octets:
+   privkey, hash: no; pubkey: 2 no; sig: no/2 + no */
+err_t bign128KeypairGen(octet privkey[], octet pubkey[], gen_i rng, void* rng_state);
+err_t bign128KeypairVal(const octet privkey[], const octet pubkey[]);
+err_t bign128PubkeyVal(const octet pubkey[]);
+err_t bign128PubkeyCalc(octet pubkey[], const octet privkey[]);
+err_t bign128DH(octet key[], const octet privkey[], const octet pubkey[], size_t key_len);
+err_t bign128Sign(octet sig[], const octet hash[], const octet privkey[], gen_i rng, void* rng_state);
+err_t bign128Sign2(octet sig[], const octet hash[], const octet privkey[], const void* t, size_t t_len);
+err_t bign128Verify(const octet hash[], const octet sig[], const octet pubkey[]);
+err_t bign192KeypairGen(octet privkey[], octet pubkey[], gen_i rng, void* rng_state);
+err_t bign192KeypairVal(const octet privkey[], const octet pubkey[]);
+err_t bign192PubkeyVal(const octet pubkey[]);
+err_t bign192PubkeyCalc(octet pubkey[], const octet privkey[]);
+err_t bign192DH(octet key[], const octet privkey[], const octet pubkey[], size_t key_len);
+err_t bign192Sign(octet sig[], const octet hash[], const octet privkey[], gen_i rng, void* rng_state);
+err_t bign192Sign2(octet sig[], const octet hash[], const octet privkey[], const void* t, size_t t_len);
+err_t bign192Verify(const octet hash[], const octet sig[], const octet pubkey[]);
+err_t bign256KeypairGen(octet privkey[], octet pubkey[], gen_i rng, void* rng_state);
+err_t bign256KeypairVal(const octet privkey[], const octet pubkey[]);
+err_t bign256PubkeyVal(const octet pubkey[]);
+err_t bign256PubkeyCalc(octet pubkey[], const octet privkey[]);
+err_t bign256DH(octet key[], const octet privkey[], const octet pubkey[], size_t key_len);
+err_t bign256Sign(octet sig[], const octet hash[], const octet privkey[], gen_i rng, void* rng_state);
+err_t bign256Sign2(octet sig[], const octet hash[], const octet privkey[], const void* t, size_t t_len);
+err_t bign256Verify(const octet hash[], const octet sig[], const octet pubkey[]);
 /* batch forms: keys are drawn in item order; status[i] is what the one-shot call would return */
 err_t bignKeypairGenBatch(octet* privkeys, octet* pubkeys, const bign_params* params, gen_i rng,
 	void* rng_state, size_t count);
@@ -308,6 +341,8 @@ err_t b2g_bignSign2BatchL_t_dev(size_t l, void* d_status, void* d_sigs, const oc
 	const void* d_hashes, const void* d_privkeys, size_t count, const void* t, size_t t_len, void* stream);
 err_t b2g_bignPubkeyCalcBatchL_dev(size_t l, void* d_status, void* d_pubkeys, const void* d_privkeys,
 	size_t count, void* stream);
+err_t b2g_bignSignBatchL_k_dev(size_t l, void* d_status, void* d_sigs, const octet oid_der[], size_t oid_len,
+	const void* d_hashes, const void* d_privkeys, const void* d_nonces, size_t count, void* stream);
 err_t b2g_bignDHBatchL_dev(size_t l, void* d_status, void* d_out, const void* d_privkeys,
 	const void* d_pubkeys, size_t count, void* stream);
 err_t b2g_bignPubkeyValBatchL_dev(size_t l, void* d_status, const void* d_pubkeys, size_t count, void* stream);

@@ -723,39 +723,22 @@ u32 orc_bignDH(size_t l, u8* key, const u8* privkey, const u8* pubkey, size_t ke
 	return ORC_OK;
 }
 
-/* bign_sign.c:140-245 */
-u32 orc_bignSign2(size_t l, u8* sig, const u8* oid_der, size_t oid_len, const u8* hash,
-	const u8* privkey, const void* t, size_t t_len)
+/* the part bignSign and bignSign2 share once the one-time key k is known (bign_sign.c:92-122, :219-243):
+   R = k G, s0 = belt-hash(oid || R.x || H)[0..no/2), s1 = (k - (s0 + 2^l) d - H) mod q */
+static u32 sign_with_k(const lvl* L, u8* sig, const u8* oid_der, size_t oid_len, const u8* hash, fe d, const u8* kb)
 {
-	const lvl* L = level(l);
-	size_t no;
-	fe d, k, x, y, s0d, s1, Hh, s0w;
+	const size_t no = L->no;
+	fe k = fe_from(L, kb), x, y, s0d, s1, Hh, s0w;
 	u8* buf;
-	u8 theta[32], kb[64], hv[32];
-	u32 tk[8];
+	u8 hv[32];
 	u64 prod[2 * FE_MAXW];
-	if (!L) return 119u;
-	no = L->no;
-	d = fe_from(L, privkey);
-	if (fe_is0(d) || fe_cmp(d, L->q) >= 0) return ORC_BAD_PRIVKEY;
-	buf = (u8*)malloc(oid_len + 2 * no + t_len + 1);
+	if (!pt_to_affine(L, &x, &y, pt_mul(L, pt_base(L), kb, no))) return ORC_BAD_PARAMS;
+	buf = (u8*)malloc(oid_len + 2 * no + 1);
 	if (!buf) return 110u;
-	/* theta = belt-hash(oid || d || t) */
-	memcpy(buf, oid_der, oid_len), memcpy(buf + oid_len, privkey, no);
-	if (t) memcpy(buf + oid_len + no, t, t_len);
-	orc_beltHash(theta, buf, oid_len + no + (t ? t_len : 0));
-	orc_beltKeyExpand2(tk, theta, 32);
-	/* k = H; k = WBL(k) until 0 < k < q */
-	memcpy(kb, hash, no);
-	do belt_wbl(kb, no, tk), k = fe_from(L, kb);
-	while (fe_is0(k) || fe_cmp(k, L->q) >= 0);
-	if (!pt_to_affine(L, &x, &y, pt_mul(L, pt_base(L), kb, no))) { free(buf); return ORC_BAD_PARAMS; }
-	/* s0 = belt-hash(oid || R.x || H)[0..no/2) */
 	memcpy(buf, oid_der, oid_len), fe_to(L, buf + oid_len, x), memcpy(buf + oid_len + no, hash, no);
 	orc_beltHash(hv, buf, oid_len + 2 * no);
 	free(buf);
 	memcpy(sig, hv, no / 2);
-	/* s1 = (k - (s0 + 2^l) d - H) mod q */
 	memset(&s0w, 0, sizeof s0w), memcpy(s0w.w, hv, no / 2), s0w.w[L->n / 2] = 1;
 	mul_wide(prod, s0w.w, L->n, d.w, L->n);
 	s0d = fold_mod(L, prod, L->q);
@@ -764,6 +747,47 @@ u32 orc_bignSign2(size_t l, u8* sig, const u8* oid_der, size_t oid_len, const u8
 	s1 = submod(L, s1, Hh, L->q);
 	fe_to(L, sig + no / 2, s1);
 	return ORC_OK;
+}
+
+/* bign_sign.c:27-125 with the one-time key k (0 < k < q, what zzRandNZMod drew from the generator) given */
+u32 orc_bignSignK(size_t l, u8* sig, const u8* oid_der, size_t oid_len, const u8* hash,
+	const u8* privkey, const u8* k)
+{
+	const lvl* L = level(l);
+	fe d;
+	if (!L) return 119u;
+	d = fe_from(L, privkey);
+	if (fe_is0(d) || fe_cmp(d, L->q) >= 0) return ORC_BAD_PRIVKEY;
+	return sign_with_k(L, sig, oid_der, oid_len, hash, d, k);
+}
+
+/* bign_sign.c:140-245 */
+u32 orc_bignSign2(size_t l, u8* sig, const u8* oid_der, size_t oid_len, const u8* hash,
+	const u8* privkey, const void* t, size_t t_len)
+{
+	const lvl* L = level(l);
+	size_t no;
+	fe d, k;
+	u8* buf;
+	u8 theta[32], kb[64];
+	u32 tk[8];
+	if (!L) return 119u;
+	no = L->no;
+	d = fe_from(L, privkey);
+	if (fe_is0(d) || fe_cmp(d, L->q) >= 0) return ORC_BAD_PRIVKEY;
+	buf = (u8*)malloc(oid_len + no + t_len + 1);
+	if (!buf) return 110u;
+	/* theta = belt-hash(oid || d || t) */
+	memcpy(buf, oid_der, oid_len), memcpy(buf + oid_len, privkey, no);
+	if (t) memcpy(buf + oid_len + no, t, t_len);
+	orc_beltHash(theta, buf, oid_len + no + (t ? t_len : 0));
+	free(buf);
+	orc_beltKeyExpand2(tk, theta, 32);
+	/* k = H; k = WBL(k) until 0 < k < q */
+	memcpy(kb, hash, no);
+	do belt_wbl(kb, no, tk), k = fe_from(L, kb);
+	while (fe_is0(k) || fe_cmp(k, L->q) >= 0);
+	return sign_with_k(L, sig, oid_der, oid_len, hash, d, kb);
 }
 u32 orc_bignSign2_128(u8 sig[48], const u8* oid_der, size_t oid_len, const u8 hash[32],
 	const u8 privkey[32], const void* t, size_t t_len)

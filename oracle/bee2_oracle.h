@@ -104,6 +104,9 @@ uint32_t orc_bignVerify(size_t l, const uint8_t* oid_der, size_t oid_len, const 
 uint32_t orc_bignSign2(size_t l, uint8_t* sig, const uint8_t* oid_der, size_t oid_len,
 	const uint8_t* hash, const uint8_t* privkey, const void* t, size_t t_len);
 uint32_t orc_bignPubkeyCalc(size_t l, uint8_t* pubkey, const uint8_t* privkey);
+/* bignSign (bign_sign.c:27-125) with the one-time key the generator produced */
+uint32_t orc_bignSignK(size_t l, uint8_t* sig, const uint8_t* oid_der, size_t oid_len,
+	const uint8_t* hash, const uint8_t* privkey, const uint8_t* k);
 int orc_ecMulA(size_t l, uint8_t* b, const uint8_t* a, const uint8_t* d, size_t d_len);
 uint32_t orc_bignPubkeyVal(size_t l, const uint8_t* pubkey);                        /* bign_misc.c:317-352 */
 uint32_t orc_bignDH(size_t l, uint8_t* key, const uint8_t* privkey, const uint8_t* pubkey, size_t key_len); /* :437-500 */

@@ -21,7 +21,7 @@ def port():
         L = C.CDLL(os.path.join(REF_DIR, "libbee2oracle.so"))
         L.orc_beltH.restype = C.c_void_p
         for n in ("orc_beltCHEWrap", "orc_beltCHEUnwrap", "orc_beltDWPWrap", "orc_beltDWPUnwrap", "orc_bashHash", "orc_beltCTR", "orc_beltECBEncr", "orc_beltECBDecr", "orc_bignVerify128",
-                  "orc_bignSign2_128", "orc_bignPubkeyCalc128", "orc_bignVerify", "orc_bignSign2", "orc_bignPubkeyCalc", "orc_bignPubkeyVal", "orc_bignDH"):
+                  "orc_bignSign2_128", "orc_bignPubkeyCalc128", "orc_bignVerify", "orc_bignSign2", "orc_bignPubkeyCalc", "orc_bignPubkeyVal", "orc_bignDH", "orc_bignSignK"):
             getattr(L, n).restype = C.c_uint32
         L.orc_ecMulA128.restype = C.c_int
         L.orc_ecMulA.restype = C.c_int
@@ -198,6 +198,12 @@ def bignSign2(hash_: bytes, priv: bytes, t: bytes = None, oid: bytes = OID, l: i
     return code, sig.raw
 
 
+def bignSignK(hash_: bytes, priv: bytes, k: bytes, oid: bytes = OID, l: int = 128):
+    sig = C.create_string_buffer(3 * l // 8)
+    code = port().orc_bignSignK(sz(l), sig, oid, sz(len(oid)), bytes(hash_), bytes(priv), bytes(k))
+    return code, sig.raw
+
+
 def bignPubkeyCalc(priv: bytes, l: int = 128):
     pub = C.create_string_buffer(l // 2)
     code = port().orc_bignPubkeyCalc(sz(l), pub, bytes(priv))
@@ -297,6 +303,19 @@ def ref_bignKeypairGen(stream: bytes, l: int = 128):
     priv, pub = C.create_string_buffer(l // 4), C.create_string_buffer(l // 2)
     code = ref().bignKeypairGen(priv, pub, C.byref(ref_params(l)), cb, None)
     return code, priv.raw, pub.raw, pos[0]
+
+
+def ref_bignSign(hash_: bytes, priv: bytes, stream: bytes, oid: bytes = OID, l: int = 128):
+    """bignSign of the reference fed from `stream`; returns (code, sig, octets consumed)."""
+    pos = [0]
+
+    def fn(buf, count, state):
+        C.memmove(buf, stream[pos[0]:pos[0] + count], count)
+        pos[0] += count
+    cb = C.CFUNCTYPE(None, C.c_void_p, sz, C.c_void_p)(fn)
+    sig = C.create_string_buffer(3 * l // 8)
+    code = ref().bignSign(sig, C.byref(ref_params(l)), oid, sz(len(oid)), bytes(hash_), bytes(priv), cb, None)
+    return code, sig.raw, pos[0]
 
 
 def ref_bignPubkeyCalc(priv: bytes, l: int = 128):

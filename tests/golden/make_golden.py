@@ -255,6 +255,12 @@ def main():
             rec["val"].append({"case": name, "pubkey": pk.hex(), "pubkey_val": o.ref_bignPubkeyVal(pk, l),
                                "keypair_val": o.ref_bignKeypairVal(priv, pk, l),
                                "dh": o.ref_bignDH(priv, pk, no, l)[0]})
+        # bignSign with a generator stream whose first draws are rejected (>= q, zero)
+        h = rb3(no)
+        sstream = b"\xff" * no + bytes(no) + rb3(2 * no)
+        code, sig, used = o.ref_bignSign(h, priv, sstream, o.OIDS[l], l)
+        assert code == 0 and used == 3 * no and o.ref_bignVerify(h, sig, pub, o.OIDS[l], l) == 0
+        rec["sign"] = {"hash": h.hex(), "stream": sstream.hex(), "sig": sig.hex(), "used": used}
         out["bignMisc"].append(rec)
     with open(os.path.join(HERE, "ref_vectors.json"), "w") as f:
         json.dump(out, f, indent=1)

@@ -223,6 +223,48 @@ def test_keypair_gen_val_dh_fixtures(l):
         assert b.bignDH(p, priv_b, pk, no)[0] == v_["dh"], v_["case"]
 
 
+@pytest.mark.parametrize("l", [128, 192, 256])
+def test_sign_with_generator_and_level_wrappers(l):
+    """bignSign (bign_sign.c:27-138) with the caller's generator: reference fixture (rejected draws incl.),
+    a batch against the oracle given the same one-time keys, and the fixed-level bign128/192/256 wrappers."""
+    import ctypes as C
+    p = b.bignParamsStd(b.BIGN_CURVES[l])
+    no, oid = l // 4, o.OIDS[l]
+    t = [t for t in REF["bignMisc"] if t["l"] == l][0]
+    priv, pub, sg = bytes.fromhex(t["privkey"]), bytes.fromhex(t["pubkey"]), t["sign"]
+    st, sigs, used = b.bignSignBatch(p, oid, A(bytes.fromhex(sg["hash"])), A(priv), bytes.fromhex(sg["stream"]))
+    assert (int(st[0]), sigs[0].tobytes().hex(), used) == (0, sg["sig"], sg["used"])
+    rng = np.random.default_rng(400 + l)
+    n = 40
+    privs = rng.integers(0, 256, (n, no), dtype=np.uint8)
+    privs[:, no - 1] &= 0x7F
+    privs[5] = 0                                                   # ERR_BAD_PRIVKEY: consumes no generator octets
+    hashes = rng.integers(0, 256, (n, no), dtype=np.uint8)
+    ks = rng.integers(0, 256, (n - 1, no), dtype=np.uint8)
+    ks[:, no - 1] &= 0x7F
+    st, sigs, used = b.bignSignBatch(p, oid, hashes, privs, ks.tobytes())
+    assert used == (n - 1) * no and st[5] == b.ERR_BAD_PRIVKEY
+    j = 0
+    for i in range(n):
+        if i == 5:
+            continue
+        assert o.bignSignK(hashes[i].tobytes(), privs[i].tobytes(), ks[j].tobytes(), oid, l) == (0, sigs[i].tobytes())
+        j += 1
+    # fixed-level wrappers through the C ABI
+    L, pre = b.lib(), f"bign{l}"
+    buf = C.create_string_buffer(2 * no)
+    assert getattr(L, pre + "PubkeyCalc")(buf, priv) == 0 and buf.raw == pub
+    assert getattr(L, pre + "PubkeyVal")(pub) == 0 and getattr(L, pre + "KeypairVal")(priv, pub) == 0
+    sig = C.create_string_buffer(no + no // 2)
+    h = bytes.fromhex(sg["hash"])
+    assert getattr(L, pre + "Sign2")(sig, h, priv, None, 0) == 0
+    assert (0, sig.raw) == o.bignSign2(h, priv, None, oid, l)
+    assert getattr(L, pre + "Verify")(h, sig.raw, pub) == 0
+    assert getattr(L, pre + "Verify")(h, sig.raw[:-1] + bytes([sig.raw[-1] ^ 1]), pub) == b.ERR_BAD_SIG
+    key = C.create_string_buffer(no)
+    assert getattr(L, pre + "DH")(key, priv, pub, no) == 0 and (0, key.raw) == o.bignDH(priv, pub, no, l)
+
+
 @pytest.mark.parametrize("l", [128, 256])
 def test_dh_batch_vs_oracle(l):
     """d_i Q_j = d_j Q_i (both sides of the exchange agree), keys equal the oracle's, statuses item by item."""

@@ -191,6 +191,10 @@ def test_reference_fixtures_dh_pubkeyval():
             pk = bytes.fromhex(v_["pubkey"])
             assert o.bignPubkeyVal(pk, l) == v_["pubkey_val"]
             assert o.bignDH(priv, pk, no, l)[0] == v_["dh"]
+        # bignSign: the accepted draw is the third no-octet chunk of the generator stream
+        sg = t["sign"]
+        k = bytes.fromhex(sg["stream"])[2 * no:3 * no]
+        assert o.bignSignK(bytes.fromhex(sg["hash"]), priv, k, o.OIDS[l], l) == (0, bytes.fromhex(sg["sig"]))
 
 
 @pytest.mark.skipif(o.ref() is None, reason="oracle/_ref/libbee2ref_64.so not built here")
