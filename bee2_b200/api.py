@@ -20,7 +20,7 @@ __all__ = [
     "bashF", "bashHash", "bashHashBatch", "bashHashBatchV", "bashFBatch", "BashHash",
     "beltH", "beltKeyExpand2", "beltBlockEncr", "beltBlockDecr", "beltECBEncr", "beltECBDecr",
     "beltECBEncrBatch", "BeltECB", "BeltCTR", "beltCTR", "beltCTRKeystream", "beltHash", "beltHashBatch",
-    "beltDWPWrap", "beltDWPUnwrap", "BeltDWP", "beltDWPMac_dev", "beltCHEWrap", "beltCHEUnwrap", "beltCHE_dev",
+    "beltDWPWrap", "beltDWPUnwrap", "BeltDWP", "BeltHash", "beltDWPMac_dev", "beltCHEWrap", "beltCHEUnwrap", "beltCHE_dev",
     "bignParamsStd", "bignVerify", "bignVerifyBatch", "bignSign2", "bignSign2Batch",
     "bignPubkeyCalc", "bignPubkeyCalcBatch", "ecMulABatch", "ecAddMulABatch", "OID_BELT_HASH_DER",
     "bashHashBatch_dev", "bashFBatch_dev", "beltCTR_dev", "beltECB_dev", "beltECBEncrBatch_dev",
@@ -115,6 +115,9 @@ def _declare(L: C.CDLL) -> None:
         "beltCTRKeystream": (u32, [vp, sz, vp, sz, vp]), "beltECBEncrBatch": (u32, [vp, vp, sz]),
         "beltHashBatch": (u32, [vp, vp, sz, sz, sz]),
         "beltDWPWrap": (u32, [vp, vp, vp, sz, vp, sz, vp, sz, vp]),
+        "beltHash_keep": (sz, []), "beltHashStart": (None, [vp]), "beltHashStepH": (None, [vp, sz, vp]),
+        "beltHashStepG": (None, [vp, vp]), "beltHashStepG2": (None, [vp, sz, vp]),
+        "beltHashStepV": (ci, [vp, vp]), "beltHashStepV2": (ci, [vp, sz, vp]),
         **{f"belt{m}_keep": (sz, []) for m in ("DWP", "CHE")},
         **{f"belt{m}Start": (None, [vp, vp, sz, vp]) for m in ("DWP", "CHE")},
         **{f"belt{m}Step{x}": (None, [vp, sz, vp]) for m in ("DWP", "CHE") for x in "EDIA"},
@@ -405,6 +408,33 @@ class BeltCTR:
     @property
     def ctr_words(self) -> np.ndarray:
         return self.state[32:48].view(np.uint32).copy()
+
+
+class BeltHash:
+    """beltHashStart/StepH/StepG/StepG2/StepV/StepV2 (belt.h, belt_hash.c:27-158)."""
+
+    def __init__(self):
+        self.L = lib()
+        self.state = np.zeros(self.L.beltHash_keep(), dtype=np.uint8)
+        self.L.beltHashStart(self.state.ctypes.data)
+
+    def step_h(self, data: bytes) -> None:
+        k, p, n = _buf(data)
+        self.L.beltHashStepH(p, n, self.state.ctypes.data)
+
+    def step_g(self, hash_len: int = 32) -> bytes:
+        out = _out(32)
+        if hash_len == 32:
+            self.L.beltHashStepG(out.ctypes.data, self.state.ctypes.data)
+        else:
+            self.L.beltHashStepG2(out.ctypes.data, hash_len, self.state.ctypes.data)
+        return out.tobytes()[:hash_len]
+
+    def step_v(self, digest: bytes) -> bool:
+        k, p, n = _buf(digest)
+        if n == 32:
+            return bool(self.L.beltHashStepV(p, self.state.ctypes.data))
+        return bool(self.L.beltHashStepV2(p, n, self.state.ctypes.data))
 
 
 class BeltDWP:

@@ -367,6 +367,59 @@ extern "C" u32 b2g_beltECBEncrBatch_dev(void* d_blocks, const void* d_keys32, si
 	return b2g_check_launch("belt_ecb_kernel<multikey>");
 }
 
+// ---------------------------------------------------------------- belt-hash, streaming form
+// One sponge-like chain (beltHashStepH / StepG, belt_hash.c:52-131): state = s (4 words) || h (8 words).
+// Absorbs nblocks 32-octet blocks; if `final`, then compresses the length block len || s without
+// touching s (belt_hash.c:118-120). Sequential by construction: one thread works.
+__global__ void belt_hash_step_kernel(u32* __restrict__ state, const u8* __restrict__ data, u64 nblocks,
+	u32 final, uint4 len)
+{
+	__shared__ u32 tab[256];
+	BeltSmallT::fill(tab);
+	__syncthreads();
+	if (threadIdx.x != 0)
+		return;
+	const BeltSmallT S(tab);
+	u32 s[4], h[8], X[8];
+#pragma unroll
+	for (int j = 0; j < 4; ++j) s[j] = state[j];
+#pragma unroll
+	for (int j = 0; j < 8; ++j) h[j] = state[4 + j];
+#pragma unroll 1
+	for (u64 i = 0; i < nblocks; ++i)
+	{
+		const u8* p = data + 32 * i;
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+			X[j] = (u32)p[4 * j] | (u32)p[4 * j + 1] << 8 | (u32)p[4 * j + 2] << 16 | (u32)p[4 * j + 3] << 24;
+		belt_compress(S, s, h, X);
+	}
+	if (final)
+	{
+		X[0] = len.x, X[1] = len.y, X[2] = len.z, X[3] = len.w;
+#pragma unroll
+		for (int j = 0; j < 4; ++j) X[4 + j] = s[j];
+		belt_compress(S, (u32*)0, h, X);
+	}
+#pragma unroll
+	for (int j = 0; j < 4; ++j) state[j] = s[j];
+#pragma unroll
+	for (int j = 0; j < 8; ++j) state[4 + j] = h[j];
+}
+
+extern "C" u32 b2g_beltHashStep_dev(void* d_state, const void* d_data, size_t nblocks, int final,
+	const u32 len[4], void* stream)
+{
+	u32 e = b2g_ensure_device();
+	if (e) return e;
+	if ((uintptr_t)d_state & 3) return B2G_BAD_INPUT;
+	const uint4 l = make_uint4(len[0], len[1], len[2], len[3]);
+	belt_hash_step_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((u32*)d_state, (const u8*)d_data, nblocks,
+		final ? 1u : 0u, l);
+	b2g_note_launch();
+	return b2g_check_launch("belt_hash_step_kernel");
+}
+
 extern "C" u32 b2g_beltHashBatch_dev(void* d_hashes, const void* d_msgs, size_t msg_len, size_t stride,
 	size_t count, void* stream)
 {

@@ -47,6 +47,8 @@ u32 b2g_bashSponge_dev(const void* d_msgs, size_t stride, size_t msg_len, size_t
 u32 b2g_beltPolyAbsorb_dev(void* d_t, const void* d_blocks, size_t nbytes, const u32 r[4], const u32 t0[4],
 	void* d_scratch, void* stream);
 
+u32 b2g_beltHashStep_dev(void* d_state, const void* d_data, size_t nblocks, int final, const u32 len[4], void* stream);
+
 /* units per pipeline chunk so that one chunk moves about `target_bytes` */
 size_t b2g_chunk_units(size_t unit_bytes, size_t target_bytes);
 

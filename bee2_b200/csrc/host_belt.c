@@ -401,6 +401,144 @@ err_t beltHash(octet hash[32], const void* src, size_t count)
 	return beltHashBatch(hash, src, count, count, 1);
 }
 
+/* ---------------------------------------------------------------- belt-hash, streaming forms
+   (belt_hash.c:27-158). State layout = belt_hash_st without the compression stack. The chain of
+   sigma-compressions runs on the device (b2g_beltHashStep_dev); the host buffers the ragged tail and
+   counts bits. */
+typedef struct
+{
+	u32 ls[8];             /* [4] length in bits || [4] s */
+	u32 s1[4];
+	u32 h[8];
+	u32 h1[8];
+	octet block[32];
+	size_t filled;
+} belt_hash_st;
+
+size_t beltHash_keep(void) { return sizeof(belt_hash_st); }
+
+void beltHashStart(void* state)
+{
+	belt_hash_st* st = (belt_hash_st*)state;
+	memset(st->ls, 0, sizeof st->ls);
+	memcpy(st->h, beltH(), 32);
+	st->filled = 0;
+}
+
+/* sh = s || h (12 words) <- after head32 (optional) || data[0..nbytes) (whole blocks) [|| length block] */
+static err_t hash_chain(u32 s[4], u32 h[8], const octet* head32, const octet* data, size_t nbytes,
+	int final, const u32 len[4])
+{
+	err_t code;
+	b2g_slot* sl;
+	void *d, *d_state;
+	u32 sh[12];
+	const size_t total = nbytes + (head32 ? 32 : 0);
+	if (!total && !final)
+		return ERR_OK;
+	if ((code = b2g_ensure_device()))
+		return code;
+	memcpy(sh, s, 16), memcpy(sh + 4, h, 32);
+	b2g_lock();
+	sl = b2g_slot_get(0);
+	if ((code = b2g_slot_buf(sl, 0, total ? total : 32, &d)) || (code = b2g_slot_buf(sl, 2, 64, &d_state)))
+		goto done;
+	if (head32)
+		CU(cudaMemcpyAsync(d, head32, 32, cudaMemcpyHostToDevice, sl->stream), "H2D(hash head)");
+	if (nbytes)
+		CU(cudaMemcpyAsync((octet*)d + (head32 ? 32 : 0), data, nbytes, cudaMemcpyHostToDevice, sl->stream), "H2D(hash data)");
+	CU(cudaMemcpyAsync(d_state, sh, 48, cudaMemcpyHostToDevice, sl->stream), "H2D(hash state)");
+	if ((code = b2g_beltHashStep_dev(d_state, d, total / 32, final, len, sl->stream)))
+		goto done;
+	CU(cudaMemcpyAsync(sh, d_state, 48, cudaMemcpyDeviceToHost, sl->stream), "D2H(hash state)");
+	CU(cudaStreamSynchronize(sl->stream), "sync(hash)");
+	memcpy(s, sh, 16), memcpy(h, sh + 4, 32);
+done:
+	if (code)
+		cudaStreamSynchronize(sl->stream);
+	b2g_unlock();
+	return code;
+}
+
+void beltHashStepH(const void* buf, size_t count, void* state)
+{
+	belt_hash_st* st = (belt_hash_st*)state;
+	const octet* p = (const octet*)buf;
+	const octet* head = 0;
+	size_t full;
+	err_t code;
+	/* 128-bit length in bits += 8 count (beltBlockAddBitSizeU32, belt_lcl.c:25-50) */
+	{
+		u64 lo = (u64)st->ls[0] | (u64)st->ls[1] << 32, hi = (u64)st->ls[2] | (u64)st->ls[3] << 32;
+		const u64 add_lo = (u64)count << 3, add_hi = (u64)count >> 61;
+		lo += add_lo;
+		hi += add_hi + (lo < add_lo);
+		st->ls[0] = (u32)lo, st->ls[1] = (u32)(lo >> 32), st->ls[2] = (u32)hi, st->ls[3] = (u32)(hi >> 32);
+	}
+	if (st->filled)
+	{
+		if (count < 32 - st->filled)
+		{
+			memcpy(st->block + st->filled, p, count);
+			st->filled += count;
+			return;
+		}
+		memcpy(st->block + st->filled, p, 32 - st->filled);
+		count -= 32 - st->filled, p += 32 - st->filled;
+		st->filled = 0;
+		head = st->block;
+	}
+	full = count & ~(size_t)31;
+	if ((code = hash_chain(st->ls + 4, st->h, head, p, full, 0, st->ls)))
+		b2g_die("beltHashStepH", code);
+	p += full, count -= full;
+	if (count)
+		memcpy(st->block, p, st->filled = count);
+}
+
+/* h1 <- the digest of what has been absorbed; s and h stay as they are (belt_hash.c:103-121) */
+static void hash_step_g(belt_hash_st* st, const char* who)
+{
+	octet last[32];
+	err_t code;
+	memcpy(st->s1, st->ls + 4, 16);
+	memcpy(st->h1, st->h, 32);
+	if (st->filled)
+	{
+		memcpy(last, st->block, st->filled);
+		memset(last + st->filled, 0, 32 - st->filled);
+	}
+	/* the padded block moves s, the length block is len || that s; then s is restored */
+	if ((code = hash_chain(st->ls + 4, st->h1, st->filled ? last : 0, 0, 0, 1, st->ls)))
+		b2g_die(who, code);
+	memcpy(st->ls + 4, st->s1, 16);
+}
+
+void beltHashStepG(octet hash[32], void* state)
+{
+	belt_hash_st* st = (belt_hash_st*)state;
+	hash_step_g(st, "beltHashStepG");
+	memcpy(hash, st->h1, 32);
+}
+void beltHashStepG2(octet hash[], size_t hash_len, void* state)
+{
+	belt_hash_st* st = (belt_hash_st*)state;
+	hash_step_g(st, "beltHashStepG2");
+	memcpy(hash, st->h1, hash_len < 32 ? hash_len : 32);
+}
+bool_t beltHashStepV(const octet hash[32], void* state)
+{
+	belt_hash_st* st = (belt_hash_st*)state;
+	hash_step_g(st, "beltHashStepV");
+	return memcmp(hash, st->h1, 32) == 0;
+}
+bool_t beltHashStepV2(const octet hash[], size_t hash_len, void* state)
+{
+	belt_hash_st* st = (belt_hash_st*)state;
+	hash_step_g(st, "beltHashStepV2");
+	return memcmp(hash, st->h1, hash_len < 32 ? hash_len : 32) == 0;
+}
+
 /* ---------------------------------------------------------------- belt-DWP (belt_dwp.c:250-330) */
 /* One-shot AEAD on whole buffers: the data stay on the device between the CTR pass (belt.cu) and
    the tag pass (belt_dwp.cu). */

@@ -164,8 +164,16 @@ void beltCTRStepE(void* buf, size_t count, void* state);
 #define beltCTRStepD beltCTRStepE
 err_t beltCTR(void* dest, const void* src, size_t count, const octet key[], size_t len,
 	const octet iv[16]);
-/* drop-in: belt.h (belt_hash.c:174-190) one-shot only */
+/* drop-in: belt.h (belt_hash.c:27-190): one-shot and streaming (hash-and-continue) forms; state layout =
+   belt_hash_st without the compression stack */
 err_t beltHash(octet hash[32], const void* src, size_t count);
+size_t beltHash_keep(void);
+void beltHashStart(void* state);
+void beltHashStepH(const void* buf, size_t count, void* state);
+void beltHashStepG(octet hash[32], void* state);
+void beltHashStepG2(octet hash[], size_t hash_len, void* state);
+bool_t beltHashStepV(const octet hash[32], void* state);
+bool_t beltHashStepV2(const octet hash[], size_t hash_len, void* state);
 /* drop-in: belt.h:984-1030 (belt_dwp.c:250-330) — authenticated encryption of (critical src1,
    open src2): dest = CTR(src1), mac = 8-octet tag; Unwrap returns ERR_BAD_MAC and leaves dest
    untouched when the tag differs. Whole buffers are staged on the device. */

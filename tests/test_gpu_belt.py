@@ -241,6 +241,35 @@ def test_ecb_multikey_batch_config5_shape():
     assert np.array_equal(b.beltECBEncrBatch(blocks, keys), o.beltECBEncrMultiKey(blocks, keys))
 
 
+def test_hash_streaming():
+    """belt_test.c:593-621 (A.23-1/2/3 with StepG, StepV, StepV2, StepG2 between StepH calls), then random
+    splits: the digest taken after any prefix equals the one-shot hash of that prefix and hashing goes on."""
+    st = b.BeltHash()
+    st.step_h(H[:13])
+    assert st.step_g().hex().upper() == "ABEF9725D4C5A83597A367D14494CC2542F20F659DDFECC961A3EC550CBA8C75"
+    st = b.BeltHash()
+    st.step_h(H[:32])
+    d = bytes.fromhex("749E4C3653AECE5E48DB4761227742EB6DBE13F4A80F7BEFF1A9CF8D10EE7786")
+    assert st.step_v(d) and st.step_v(d[:13]) and not st.step_v(d[:12] + b"\0")
+    st = b.BeltHash()
+    st.step_h(H[:11])
+    assert st.step_g(32) == o.beltHash(H[:11])
+    st.step_h(H[11:48])
+    assert st.step_v(bytes.fromhex("9D02EE446FB6A29FE5C982D4B13AF9D3E90861BC4CEF27CF306BFB0B174A154A"))
+    rng = np.random.default_rng(61)
+    for trial in range(6):
+        data = rng.integers(0, 256, int(rng.choice([0, 31, 32, 33, 1000, 100_003])), dtype=np.uint8).tobytes()
+        st, pos = b.BeltHash(), 0
+        while True:
+            assert st.step_g() == o.beltHash(data[:pos])
+            if pos == len(data):
+                break
+            n = min(len(data) - pos, int(rng.choice([0, 1, 5, 31, 32, 64, 97, 4096, 50_000])))
+            st.step_h(data[pos:pos + n])
+            pos += n
+        assert st.step_g(7) == o.beltHash(data)[:7]
+
+
 def test_hash_batch_random():
     rng = np.random.default_rng(4)
     for n in (0, 1, 31, 32, 33, 75, 96, 1001):
