@@ -568,9 +568,11 @@ def bignVerify(params: BignParams, oid_der: bytes, hash_: bytes, sig: bytes, pub
 
 
 def bignVerifyBatch(params: BignParams, oid_der: bytes, hashes: np.ndarray, sigs: np.ndarray,
-                    pubkeys: np.ndarray) -> np.ndarray:
+                    pubkeys: np.ndarray, status: Optional[np.ndarray] = None) -> np.ndarray:
+    """``status`` may be a caller-provided uint32 array (e.g. pinned) to avoid a pageable download."""
     count = hashes.size // (params.l // 4)
-    status = np.full(count, 0xFFFFFFFF, dtype=np.uint32)
+    if status is None:
+        status = np.full(count, 0xFFFFFFFF, dtype=np.uint32)
     ko = _buf(oid_der)
     _chk("bignVerifyBatch", lib().bignVerifyBatch(status.ctypes.data, C.addressof(params), ko[1], ko[2],
                                                   hashes.ctypes.data, sigs.ctypes.data, pubkeys.ctypes.data, count))
@@ -585,10 +587,13 @@ def bignSign2(params: BignParams, oid_der: bytes, hash_: bytes, privkey: bytes, 
     return sig.tobytes()
 
 
-def bignSign2Batch(params: BignParams, oid_der: bytes, hashes: np.ndarray, privkeys: np.ndarray):
+def bignSign2Batch(params: BignParams, oid_der: bytes, hashes: np.ndarray, privkeys: np.ndarray,
+                   status: Optional[np.ndarray] = None, sigs: Optional[np.ndarray] = None):
     count = hashes.size // (params.l // 4)
-    status = np.full(count, 0xFFFFFFFF, dtype=np.uint32)
-    sigs = np.zeros((count, 3 * params.l // 8), dtype=np.uint8)
+    if status is None:
+        status = np.full(count, 0xFFFFFFFF, dtype=np.uint32)
+    if sigs is None:
+        sigs = np.zeros((count, 3 * params.l // 8), dtype=np.uint8)
     ko = _buf(oid_der)
     _chk("bignSign2Batch", lib().bignSign2Batch(status.ctypes.data, sigs.ctypes.data, C.addressof(params), ko[1], ko[2],
                                                 hashes.ctypes.data, privkeys.ctypes.data, count))

@@ -733,9 +733,18 @@ err_t bignSignBatch(err_t* status, octet* sigs, const bign_params* params, const
 		goto done;
 	CU(cudaMemcpyAsync(status, d_st, 4 * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(bign status)");
 	CU(cudaStreamSynchronize(s0->stream), "sync(bign sign)");
-	for (i = 0; i < count; ++i)
-		if (status[i] == ERR_OK)
-			CU(cudaMemcpyAsync(sigs + so * i, (octet*)d_sig + so * i, so, cudaMemcpyDeviceToHost, s0->stream), "D2H(bign sig)");
+	{
+		/* only items that signed successfully overwrite the caller's sig buffer */
+		size_t all_ok = 1;
+		for (i = 0; i < count; ++i)
+			all_ok &= status[i] == ERR_OK;
+		if (all_ok)
+			CU(cudaMemcpyAsync(sigs, d_sig, so * count, cudaMemcpyDeviceToHost, s0->stream), "D2H(bign sigs)");
+		else
+			for (i = 0; i < count; ++i)
+				if (status[i] == ERR_OK)
+					CU(cudaMemcpyAsync(sigs + so * i, (octet*)d_sig + so * i, so, cudaMemcpyDeviceToHost, s0->stream), "D2H(bign sig)");
+	}
 	/* private and one-time keys were staged on the device: wipe them */
 	CU(cudaMemsetAsync(d_k, 0, no * count, s0->stream), "memset(bign keys)");
 	CU(cudaMemsetAsync(d_n, 0, no * count, s0->stream), "memset(bign nonces)");

@@ -617,7 +617,9 @@ def main():
             if not args.no_e2e:
                 ph, pk = (torch.from_numpy(x).pin_memory() for x in (hashes, priv))
                 nh, nk = ph.numpy(), pk.numpy()
-                e2e_fn = lambda: b.bignSign2Batch(params, oid, nh, nk)  # noqa: E731
+                pst = torch.empty(units, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+                psig = torch.empty((units, 48), dtype=torch.uint8).pin_memory().numpy()
+                e2e_fn = lambda: b.bignSign2Batch(params, oid, nh, nk, status=pst, sigs=psig)  # noqa: E731
                 t = timed_host(e2e_fn, e2e_steps, 1)
                 r["e2e"] = {"value": world * units * e2e_steps / t / scale, "unit": cfg["unit"],
                             "h2d_bytes_per_step": units * 64, "d2h_bytes_per_step": units * 52,
@@ -649,7 +651,8 @@ def main():
             if not args.no_e2e:
                 ph, ps, pp = (torch.from_numpy(x).pin_memory() for x in (hashes, sigs, pubs))
                 nh, ns, npb = ph.numpy(), ps.numpy(), pp.numpy()
-                e2e_fn = lambda: b.bignVerifyBatch(params, oid, nh, ns, npb)  # noqa: E731
+                pst = torch.empty(units, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+                e2e_fn = lambda: b.bignVerifyBatch(params, oid, nh, ns, npb, status=pst)  # noqa: E731
                 t = timed_host(e2e_fn, e2e_steps, 1)
                 r["e2e"] = {"value": world * units * e2e_steps / t / scale, "unit": cfg["unit"],
                             "h2d_bytes_per_step": units * 144, "d2h_bytes_per_step": units * 4,
