@@ -782,7 +782,9 @@ class BashPrg:
     def __init__(self, l: int, d: int, ann: bytes = b"", key: bytes = b"", _lib=None, _keep=None):
         self.L = _lib or lib()
         self.state = np.zeros(_keep or self.L.bashPrg_keep(), dtype=np.uint8)
-        self._call("Start", self.state.ctypes.data, C.c_size_t(l), C.c_size_t(d), bytes(ann), C.c_size_t(len(ann)),
+        # every argument is an explicit ctypes object: these entry points are called without argtypes (the
+        # oracle's orc_bashPrg* twins share this class), where a bare Python int would be cut to 32 bits
+        self._call("Start", self._sp(), C.c_size_t(l), C.c_size_t(d), bytes(ann), C.c_size_t(len(ann)),
                    bytes(key), C.c_size_t(len(key)))
 
     def _call(self, name, *args):
