@@ -191,3 +191,11 @@ def test_scalar_mul(exe, n):
             assert g == "inf", (nbits, hex(k))
         else:
             assert g != "inf" and tuple(int(h, 16) for h in g.split()) == w, (nbits, hex(k))
+
+
+def test_generated_header_is_current():
+    """bee2_b200/csrc/gfp_asm.cuh is the committed output of tools/gen_gfp_asm.py."""
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(HERE, "..", "tools", "gen_gfp_asm.py")], capture_output=True,
+                         text=True, check=True).stdout
+    assert out == open(os.path.join(HERE, "..", "bee2_b200", "csrc", "gfp_asm.cuh")).read()
