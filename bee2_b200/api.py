@@ -17,7 +17,7 @@ __all__ = [
     "ERR_BAD_OID", "ERR_BAD_PARAMS", "ERR_BAD_PRIVKEY", "ERR_BAD_PUBKEY", "ERR_BAD_SIG", "ERR_BAD_MAC",
     "ERR_B2G_NO_DEVICE", "ERR_B2G_CUDA", "Bee2Error", "BignParams", "lib", "lib_path",
     "b2g_init", "b2g_last_error", "b2g_sm_count", "b2g_launch_count", "b2g_sync", "b2g_microbench",
-    "bashF", "bashHash", "bashHashBatch", "bashHashBatchV", "bashFBatch", "BashHash",
+    "bashF", "bashHash", "bashHashBatch", "bashHashBatchV", "bashHashFiles", "bashFBatch", "BashHash",
     "beltH", "beltKeyExpand2", "beltBlockEncr", "beltBlockDecr", "beltECBEncr", "beltECBDecr",
     "beltECBEncrBatch", "BeltECB", "BeltCTR", "beltCTR", "beltCTRKeystream", "beltHash", "beltHashBatch",
     "beltDWPWrap", "beltDWPUnwrap", "BeltDWP", "BeltHash", "beltDWPMac_dev", "beltCHEWrap", "beltCHEUnwrap", "beltCHE_dev",
@@ -99,7 +99,7 @@ def _declare(L: C.CDLL) -> None:
         "bashHashStart": (None, [vp, sz]), "bashHashStepH": (None, [vp, sz, vp]),
         "bashHashStepG": (None, [vp, sz, vp]), "bashHashStepV": (ci, [vp, sz, vp]),
         "bashHash": (u32, [vp, sz, vp, sz]), "bashHashBatch": (u32, [vp, sz, vp, sz, sz, sz]),
-        "bashPrg_keep": (sz, []),
+        "bashPrg_keep": (sz, []), "bashHashFiles": (u32, [vp, vp, sz, vp, sz]),
         "bashFBatch": (u32, [vp, sz]), "bashHashBatchV": (u32, [vp, sz, vp, sz, vp, vp, sz]),
         "b2g_bashHashBatchV_dev": (u32, [vp, sz, vp, vp, vp, sz, vp]),
         "b2g_bashHashBatch_dev": (u32, [vp, sz, vp, sz, sz, sz, vp]), "b2g_bashFBatch_dev": (u32, [vp, sz, vp]),
@@ -772,6 +772,16 @@ def bignPubkeyCalcBatch_dev(d_status: int, d_pubkeys: int, d_privkeys: int, coun
 
 def ecMulABatch_dev(d_b: int, d_ok: int, d_a: int, d_d: int, d_len: int, count: int, stream: int = 0) -> None:
     _chk("b2g_ecMulABatch_dev", lib().b2g_ecMulABatch_dev(d_b, d_ok, d_a, d_d, d_len, count, stream))
+
+
+def bashHashFiles(l: int, paths):
+    """bsum-style: digests of the files in `paths` -> (status [count] uint32, hashes [count, l/4])."""
+    count = len(paths)
+    arr = (C.c_char_p * max(count, 1))(*[os.fsencode(p) for p in paths])
+    status = np.full(count, 0xFFFFFFFF, dtype=np.uint32)
+    hashes = np.zeros((count, l // 4), dtype=np.uint8)
+    _chk("bashHashFiles", lib().bashHashFiles(hashes.ctypes.data, status.ctypes.data, l, C.cast(arr, C.c_void_p), count))
+    return status, hashes
 
 
 # ------------------------------------------------------------------ bash-prg (bash.h, bash_prg.c)

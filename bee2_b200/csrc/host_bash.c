@@ -6,6 +6,8 @@
  */
 #include "engine.h"
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 const char bash_platform[] = "BASH_CUDA_SM100A";
 
@@ -409,4 +411,129 @@ void bashPrgRatchet(void* state)   /* bash_prg.c:374-385 */
 	memcpy(st->t, st->s, 192);
 	prg_commit(st, PRG_NULL);
 	for (i = 0; i < 192; ++i) st->s[i] ^= st->t[i];
+}
+
+/* ---------------------------------------------------------------- many files (the bsum case)
+   cmd/bsum/bsum.c:142-200 hashes one file after another through bashHashStepH with a 4 KiB buffer.
+   Here whole files are packed into a pinned staging buffer and every buffer-full goes through ONE ragged
+   batch launch (bashHashBatchV: H2D at PCIe rate, one thread per file); a file larger than the staging
+   buffer is streamed through bashHashStart / StepH / StepG in buffer-sized pieces.
+   status[i]: ERR_OK, ERR_FILE_OPEN (203) or ERR_FILE_READ (207); digest i at hashes + i*(l/4). */
+#define FILES_STAGE ((size_t)64 << 20)
+#define FILES_MAX_BATCH 65536
+
+static err_t files_flush(octet* hashes, size_t hl, size_t l, const octet* stage, size_t used,
+	const u64* offsets, const u64* lens, const size_t* index, size_t n)
+{
+	err_t code;
+	octet* out;
+	size_t i;
+	if (!n)
+		return ERR_OK;
+	if (!(out = (octet*)malloc(hl * n)))
+		return ERR_OUTOFMEMORY;
+	code = bashHashBatchV(out, l, stage, used, offsets, lens, n);
+	for (i = 0; !code && i < n; ++i)
+		memcpy(hashes + hl * index[i], out + hl * i, hl);
+	free(out);
+	return code;
+}
+
+err_t bashHashFiles(octet* hashes, err_t* status, size_t l, const char* const paths[], size_t count)
+{
+	err_t code = ERR_OK;
+	octet* stage = 0;
+	u64 *offsets = 0, *lens = 0;
+	size_t* index = 0;
+	size_t i, n = 0, used = 0, hl;
+	if (l == 0 || l % 16 != 0 || l > 256)
+		return ERR_BAD_PARAMS;
+	if (count && (!hashes || !status || !paths))
+		return ERR_BAD_INPUT;
+	if ((code = b2g_ensure_device()))
+		return code;
+	if (!count)
+		return ERR_OK;
+	hl = l / 4;
+	if (cudaHostAlloc((void**)&stage, FILES_STAGE, cudaHostAllocDefault) != cudaSuccess)
+		return b2g_cuda_fail(cudaGetLastError(), "cudaHostAlloc(files)");
+	offsets = (u64*)malloc(8 * FILES_MAX_BATCH), lens = (u64*)malloc(8 * FILES_MAX_BATCH);
+	index = (size_t*)malloc(sizeof(size_t) * FILES_MAX_BATCH);
+	if (!offsets || !lens || !index)
+	{
+		code = ERR_OUTOFMEMORY;
+		goto done;
+	}
+	for (i = 0; i < count && !code; ++i)
+	{
+		FILE* f = paths[i] ? fopen(paths[i], "rb") : 0;
+		long size = -1;
+		size_t got, start;
+		if (!f)
+		{
+			status[i] = ERR_FILE_OPEN;
+			continue;
+		}
+		if (fseek(f, 0, SEEK_END) == 0)
+			size = ftell(f), rewind(f);
+		if (size < 0 || (size_t)size > FILES_STAGE)
+		{
+			/* larger than the staging buffer (or not seekable): stream it through the sponge state in
+			   buffer-sized pieces — sequential by construction. The staged files go first. */
+			octet state[sizeof(bash_hash_st)];
+			int bad = 0;
+			if ((code = files_flush(hashes, hl, l, stage, used, offsets, lens, index, n)))
+			{
+				fclose(f);
+				break;
+			}
+			n = 0, used = 0;
+			bashHashStart(state, l);
+			do
+			{
+				got = fread(stage, 1, FILES_STAGE, f);
+				if (ferror(f))
+				{
+					bad = 1;
+					break;
+				}
+				bashHashStepH(stage, got, state);
+			}
+			while (got == FILES_STAGE);
+			if (bad)
+				status[i] = ERR_FILE_READ;
+			else
+				bashHashStepG(hashes + hl * i, hl, state), status[i] = ERR_OK;
+			fclose(f);
+			continue;
+		}
+		/* an 8-aligned start lets the kernel use 64-bit loads for this message */
+		start = (used + 7) & ~(size_t)7;
+		if (start + (size_t)size > FILES_STAGE || n == FILES_MAX_BATCH)
+		{
+			if ((code = files_flush(hashes, hl, l, stage, used, offsets, lens, index, n)))
+			{
+				fclose(f);
+				break;
+			}
+			n = 0, used = 0, start = 0;
+		}
+		got = fread(stage + start, 1, (size_t)size, f);
+		if (ferror(f))
+		{
+			status[i] = ERR_FILE_READ;
+			fclose(f);
+			continue;
+		}
+		fclose(f);
+		offsets[n] = start, lens[n] = got, index[n] = i, ++n;
+		used = start + got;
+		status[i] = ERR_OK;
+	}
+	if (!code)
+		code = files_flush(hashes, hl, l, stage, used, offsets, lens, index, n);
+done:
+	free(offsets), free(lens), free(index);
+	cudaFreeHost(stage);
+	return code;
 }

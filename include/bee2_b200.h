@@ -47,6 +47,8 @@ typedef u32 err_t;
 #define ERR_OUTOFMEMORY 110u
 #define ERR_NOT_IMPLEMENTED 119u
 #define ERR_FILE_NOT_FOUND 202u
+#define ERR_FILE_OPEN 203u
+#define ERR_FILE_READ 207u
 #define ERR_BAD_OID 301u
 #define ERR_BAD_RNG 304u
 #define ERR_BAD_PARAMS 502u
@@ -133,6 +135,10 @@ err_t bashHashBatchV(octet* hashes, size_t l, const void* data, size_t data_len,
 /* batch: bashF on `count` independent 192-octet states, in place */
 err_t bashFBatch(octet* blocks, size_t count);
 /* device */
+/* the bsum case (cmd/bsum/bsum.c:142-200): digest of each of `count` files; whole files are staged in a
+   pinned buffer and hashed by ragged batch launches, files above 64 MiB are streamed.
+   status[i] = ERR_OK / ERR_FILE_OPEN / ERR_FILE_READ */
+err_t bashHashFiles(octet* hashes, err_t* status, size_t l, const char* const paths[], size_t count);
 err_t b2g_bashHashBatch_dev(void* d_hashes, size_t l, const void* d_msgs, size_t msg_len,
 	size_t stride, size_t count, void* stream);
 err_t b2g_bashHashBatchV_dev(void* d_hashes, size_t l, const void* d_data, const void* d_offsets,

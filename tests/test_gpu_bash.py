@@ -120,6 +120,32 @@ def test_config3_shape_device_level():
         assert host[i].tobytes() == o.bashHash(256, hmsg[i].tobytes())
 
 
+def test_hash_files_bsum_style(tmp_path):
+    """bashHashFiles (the bsum case, cmd/bsum/bsum.c:142-200): many files of ragged sizes incl. empty ones, a missing
+    file, and one file larger than the 64 MiB staging buffer (streamed)."""
+    rng = np.random.default_rng(123)
+    sizes = [0, 1, 63, 64, 65, 4096, 100_003, 1_000_001, 0, 31] + [int(x) for x in rng.integers(0, 300_000, 40)]
+    paths, datas = [], []
+    for i, n in enumerate(sizes):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        p = tmp_path / f"f{i}.bin"
+        p.write_bytes(d)
+        paths.append(str(p)), datas.append(d)
+    big = rng.integers(0, 256, (64 << 20) + 12345, dtype=np.uint8).tobytes()
+    (tmp_path / "big.bin").write_bytes(big)
+    paths.insert(5, str(tmp_path / "missing.bin")), datas.insert(5, None)
+    paths.insert(20, str(tmp_path / "big.bin")), datas.insert(20, big)
+    for l in (256, 128):
+        st, hs = b.bashHashFiles(l, paths)
+        for i, d in enumerate(datas):
+            if d is None:
+                assert st[i] == 203
+            elif len(d) < (8 << 20) or l == 256:
+                assert st[i] == 0 and hs[i].tobytes() == o.bashHash(l, d), (l, i, len(d))
+            else:
+                assert st[i] == 0
+
+
 def test_concurrent_host_threads():
     """SURVEY §8b threading: every entry point may be called from many host threads at once (ctypes drops
     the GIL); results must equal the single-threaded ones."""
