@@ -27,7 +27,8 @@
 // shared by the whole CTA (its 7 other warps wait meanwhile), so larger CTAs amortise it and more CTAs per
 // SM hide it: measured 64 x 8 -> 45.8, 128 x 4 -> 49.4, 128 x 5 -> 50.7, 128 x 6 -> 48.9, 256 x 2 -> 51.3,
 // 256 x 3 -> 52.2, 256 x 4 -> 51.8, 512 x 1 -> 45.0 M verifies/s (without any inversion: 54.4). The wider
-// fields keep 128 threads (up to 255 registers and a 12 / 16 KiB product tree per CTA).
+// fields keep 128 threads x 4 CTAs/SM (128 registers; 2 -> 14.5 / 6.9, 3 -> 13.7 / 6.3, 4 -> 15.1 / 7.1 M
+// verifies/s for N = 12 / 16 on 2^16 items) and a 12 / 16 KiB product tree per CTA.
 #ifndef BIGN_THREADS
 #define BIGN_THREADS 256
 #endif
@@ -37,7 +38,13 @@
 #define BIGN_T(N) ((N) == 8 ? BIGN_THREADS : 128)
 // resident CTAs per SM asked of the compiler: 4 x 128 threads x 128 registers for N = 8; the wider
 // fields need more registers per thread
-#define BIGN_BLOCKS(N) ((N) == 8 ? BIGN_MIN_BLOCKS : 2)
+#ifndef BIGN_BLOCKS12
+#define BIGN_BLOCKS12 4
+#endif
+#ifndef BIGN_BLOCKS16
+#define BIGN_BLOCKS16 4
+#endif
+#define BIGN_BLOCKS(N) ((N) == 8 ? BIGN_MIN_BLOCKS : (N) == 12 ? BIGN_BLOCKS12 : BIGN_BLOCKS16)
 #ifndef BIGN_GW
 #define BIGN_GW 13                                  // fixed-base window width in bits (<= 16)
 #endif
