@@ -65,6 +65,7 @@ struct BeltBigT
 
 struct BeltSmallT
 {
+	static constexpr int WORDS = 256;
 	const u32* tab;   // shared memory, 256 words: tab[x] = H[x]
 
 	__device__ __forceinline__ static void fill(u32* sm)
@@ -78,6 +79,28 @@ struct BeltSmallT
 		const u32 v = tab[x & 255u] | tab[(x >> 8) & 255u] << 8 | tab[(x >> 16) & 255u] << 16 |
 			tab[x >> 24] << 24;
 		return rotl32(v, 5 + 8 * T0);
+	}
+};
+
+// Four pre-rotated 1 KiB tables (the reference's H5 / H13 / H21 / H29, belt_block.c:121-195) without the
+// per-bank replication of BeltBigT: 4 KiB of shared memory, 4 LDS + 3 XOR per G-box, bank conflicts as
+// the data fall (the LSU pipe is idle in the kernels that use it: belt inside bign).
+struct BeltT4
+{
+	static constexpr int WORDS = 1024;
+	const u32* tab;   // tab[t * 256 + x] = rotl32(H[x], 5 + 8 t)
+
+	__device__ __forceinline__ static void fill(u32* sm)
+	{
+		for (u32 i = threadIdx.x; i < 1024u; i += blockDim.x)
+			sm[i] = rotl32((u32)c_beltH[i & 255u], 5 + 8 * (int)(i >> 8));
+	}
+	__device__ __forceinline__ BeltT4(const u32* sm) : tab(sm) {}
+	// G_r with r = 5 + 8*T0: byte k of x goes through table (T0 + k) mod 4
+	template <int T0> __device__ __forceinline__ u32 g(u32 x) const
+	{
+		return tab[((T0 + 0) & 3) * 256 + (x & 255u)] ^ tab[((T0 + 1) & 3) * 256 + ((x >> 8) & 255u)] ^
+			tab[((T0 + 2) & 3) * 256 + ((x >> 16) & 255u)] ^ tab[((T0 + 3) & 3) * 256 + (x >> 24)];
 	}
 };
 

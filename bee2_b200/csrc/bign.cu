@@ -94,6 +94,12 @@ template <> struct bign_c<16>
 // device: BIGN_GN(N) * BIGN_GE entries of 8 N octets (x || y) per level; entry j = 0 unused
 static std::atomic<uint4*> g_gtab[3];
 
+// S-box policy of the belt code inside the bign kernels (belt-hash, belt-WBL)
+#ifndef BIGN_SBOX
+#define BIGN_SBOX BeltT4
+#endif
+typedef BIGN_SBOX BignSbox;
+
 struct OidArg { u8 der[BIGN_MAX_OID]; u32 len; };
 struct TArg { u8 t[BIGN_MAX_T]; u32 len; };
 
@@ -236,7 +242,7 @@ template <int N> __device__ __noinline__ void pt_add_mul_base(pt<N>& acc, const 
 
 // ---------------------------------------------------------------- belt-hash(oid || a || b || extra)
 // a, b: field-sized (4N octets) little-endian limb strings; b and extra optional
-template <int N> __device__ __forceinline__ void hash_oid_ab(const BeltSmallT& S, u32 (&out)[8], const OidArg& oid,
+template <int N> __device__ __forceinline__ void hash_oid_ab(const BignSbox& S, u32 (&out)[8], const OidArg& oid,
 	const u32* a, const u32* b, const u8* extra, u32 extra_len)
 {
 	// message zero-padded to whole 32-octet blocks
@@ -381,11 +387,11 @@ bign_verify_kernel(u32* __restrict__ status, const u8* __restrict__ hashes, cons
 	const u8* __restrict__ pubkeys, u64 count, const OidArg oid, const uint4* __restrict__ gtab)
 {
 	constexpr int NO = 4 * N, H2 = N / 2;
-	__shared__ u32 tab[256];
+	__shared__ u32 tab[BignSbox::WORDS];
 	__shared__ u32 tree[BIGN_TREE_WORDS(N)];
-	BeltSmallT::fill(tab);
+	BignSbox::fill(tab);
 	__syncthreads();
-	const BeltSmallT S(tab);
+	const BignSbox S(tab);
 	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	// every thread stays until the block-wide inversion; `live` = still computing, `st` = verdict so far
 	bool live = i < count;
@@ -472,7 +478,7 @@ bign_verify_kernel(u32* __restrict__ status, const u8* __restrict__ hashes, cons
 
 // belt-WBL encryption of NB = 2, 3, 4 blocks: 2 NB rounds (belt_wbl.c:50-82, round reset :203).
 // Round: S = r_1 ^ ... ^ r_{NB-1}; r <- (r_2, ..., r_NB ^ E(S) ^ <round>, S)
-template <int NB> __device__ __forceinline__ void wbl(const BeltSmallT& S, u32 (&r)[4 * NB], const u32 (&key)[8])
+template <int NB> __device__ __forceinline__ void wbl(const BignSbox& S, u32 (&r)[4 * NB], const u32 (&key)[8])
 {
 #pragma unroll 1
 	for (u32 round = 1; round <= 2 * NB; ++round)
@@ -503,11 +509,11 @@ bign_sign2_kernel(u32* __restrict__ status, u8* __restrict__ sigs, const u8* __r
 	const uint4* __restrict__ gtab, const u8* __restrict__ nonces)
 {
 	constexpr int NO = 4 * N, H2 = N / 2;
-	__shared__ u32 tab[256];
+	__shared__ u32 tab[BignSbox::WORDS];
 	__shared__ u32 tree[BIGN_TREE_WORDS(N)];
-	BeltSmallT::fill(tab);
+	BignSbox::fill(tab);
 	__syncthreads();
-	const BeltSmallT S(tab);
+	const BignSbox S(tab);
 	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	bool live = i < count;
 	u32 st = B2G_OK;
