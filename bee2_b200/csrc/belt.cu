@@ -192,16 +192,20 @@ belt_ecb_kernel(uint4* dst, const uint4* src, const uint4* __restrict__ keys, u6
 	}
 }
 
+// S-box policy of the batch belt-hash kernel (-DBELT_HASH_SBOX=BeltSmallT for the 1 KiB single table)
+#ifndef BELT_HASH_SBOX
+#define BELT_HASH_SBOX BeltT4
+#endif
 // ---------------------------------------------------------------- belt-hash batch
 // One message per thread; messages of equal length msg_len at msgs + i*stride.
 __global__ void __launch_bounds__(256)
 belt_hash_kernel(u8* __restrict__ hashes, const u8* __restrict__ msgs, u64 msg_len, u64 stride,
 	u64 count)
 {
-	__shared__ u32 tab[256];
-	BeltSmallT::fill(tab);
+	__shared__ u32 tab[BELT_HASH_SBOX::WORDS];
+	BELT_HASH_SBOX::fill(tab);
 	__syncthreads();
-	const BeltSmallT S(tab);
+	const BELT_HASH_SBOX S(tab);
 	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= count)
 		return;
