@@ -252,8 +252,25 @@ class CpuArm:
         self.sample(path, 0, state)                 # probe (also warms caches / lazy curve)
         dt, units, desc = self.sample(path, target_s, state)
         scale = 1e9 if CFG[path]["unit"] == "GB/s" else 1.0
-        return {"value": units / dt / scale, "unit": CFG[path]["unit"], "cores": self.threads, "kind": self.kind,
-                "sample": desc + f", {dt:.2f} s wall"}
+        out = {"value": units / dt / scale, "unit": CFG[path]["unit"], "cores": self.threads, "kind": self.kind,
+               "sample": desc + f", {dt:.2f} s wall"}
+        # the single-thread figure (and the scalar BASH_64 build for bash) alongside
+        saved = self.threads, self.bash_lib, self.bash_name
+        try:
+            self.threads = 1
+            st1 = {}
+            self.sample(path, 0, st1)
+            dt1, u1, _ = self.sample(path, 1.0, st1)
+            out["value_1_thread"] = u1 / dt1 / scale
+            if path == "bash512" and self.kind == "reference" and saved[2] != "BASH_64":
+                self.threads, self.bash_lib, self.bash_name = saved[0], self.lib, "BASH_64"
+                st64 = {}
+                self.sample(path, 0, st64)
+                dt64, u64_, _ = self.sample(path, 1.5, st64)
+                out["value_bash_64"] = u64_ / dt64 / scale
+        finally:
+            self.threads, self.bash_lib, self.bash_name = saved
+        return out
 
 
 def run_reference(args, rank):
