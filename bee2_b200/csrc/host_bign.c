@@ -800,3 +800,73 @@ static const octet oid_bash512[] = {0x06, 0x09, 0x2A, 0x70, 0x00, 0x02, 0x00, 0x
 BIGN_LEVEL_WRAPPERS(bign128, 0, oid_belt_hash)
 BIGN_LEVEL_WRAPPERS(bign192, 1, oid_bash384)
 BIGN_LEVEL_WRAPPERS(bign256, 2, oid_bash512)
+
+/* ---------------------------------------------------------------- ecMulA behind the reference's ec_o
+   (include/bee2/math/ec.h:540-571, :892-901; qr.h:317-338; obj.h:53-58). The reference dispatches every
+   point operation through the vtable of `ec`; here only the DATA at the head of the two descriptions are
+   read — field size and modulus, A, B — to recognise one of the three standard bign curves, and the whole
+   multiplication runs on the device. Fields over a Crandall prime keep plain residues (zm.c:270-310), so
+   the word arrays of a 64-bit little-endian build are the octet strings the kernels take. Any other curve:
+   there is no CPU path — the call fails loudly. */
+typedef struct { size_t keep, p_count, o_count; } b2g_obj_hdr;
+typedef struct
+{
+	b2g_obj_hdr hdr;
+	const u64* mod;
+	const u64* unity;
+	const void* params;
+	size_t n, no;
+	/* function pointers follow */
+} b2g_qr_view;
+typedef struct
+{
+	b2g_obj_hdr hdr;
+	const b2g_qr_view* f;
+	const u64 *A, *B, *base, *order;
+	const void* pre;
+	size_t d;
+	u64 cofactor;
+	/* function pointers follow */
+} b2g_ec_view;
+
+static size_t ec_std_level(const void* ec_)
+{
+	const b2g_ec_view* ec = (const b2g_ec_view*)ec_;
+	bign_params std;
+	size_t i;
+	if (!ec || !ec->f || !ec->f->mod || !ec->A || !ec->B)
+		return 0;
+	for (i = 0; i < 3; ++i)
+	{
+		const size_t no = std_curves[i].l / 4;
+		if (ec->f->n != no / 8 || ec->f->no != no)
+			continue;
+		std_fill(&std, &std_curves[i]);
+		if (!memcmp(ec->f->mod, std.p, no) && !memcmp(ec->A, std.a, no) && !memcmp(ec->B, std.b, no))
+			return std_curves[i].l;
+	}
+	return 0;
+}
+
+size_t ecMulA_deep(size_t n, size_t ec_d, size_t ec_deep, size_t m)
+{
+	(void)n, (void)ec_d, (void)ec_deep, (void)m;
+	return 0;   /* no host scratch: the caller's `stack` is not used */
+}
+
+/* b <- d a, FALSE iff the result is O (ec.c:497-525); a, b: 2n words affine; d: m words, m <= n */
+bool_t ecMulA(u64 b[], const u64 a[], const void* ec, const u64 d[], size_t m, void* stack)
+{
+	const size_t l = ec_std_level(ec);
+	octet out[128];
+	int ok = 0;
+	err_t code;
+	(void)stack;
+	if (!l || !a || !b || !d || m == 0 || 8 * m > l / 4)
+		b2g_die("ecMulA (curve is not a standard bign curve, or m > n: no CPU path)", l ? ERR_BAD_INPUT : ERR_NOT_IMPLEMENTED);
+	if ((code = ecMulABatchL(l, out, &ok, (const octet*)a, (const octet*)d, 8 * m, 1)))
+		b2g_die("ecMulA", code);
+	if (ok)
+		memcpy(b, out, l / 2);
+	return ok ? 1 : 0;
+}

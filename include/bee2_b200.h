@@ -332,6 +332,12 @@ err_t ecMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d_le
 /* batch ecAddMulA with the base point (ec.c:1183-1273): b_i = d_i * a_i + k_i * G, k_i 32 octets */
 err_t ecAddMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d_len, const octet* k,
 	size_t count);
+/* drop-in: ec.h:892-901 (ec.c:497-525) for an `ec_o` built by the reference (bignEcCreate, ecpCreateJ over
+   gfpCreate) that describes one of the three standard bign curves: only the data at the head of the
+   descriptions are read (field modulus, A, B), the multiplication runs on the device; m <= n words.
+   Other curves abort() — there is no CPU path. `ec` is the reference's `const ec_o*`, `word` = u64. */
+bool_t ecMulA(u64 b[], const u64 a[], const void* ec, const u64 d[], size_t m, void* stack);
+size_t ecMulA_deep(size_t n, size_t ec_d, size_t ec_deep, size_t m);
 /* the same on the standard curve of level l = 128 / 192 / 256: points l/2 octets, d_len <= l/4,
    k_i l/4 octets */
 err_t ecMulABatchL(size_t l, octet* b, int* ok, const octet* a, const octet* d, size_t d_len, size_t count);

@@ -265,6 +265,49 @@ def test_sign_with_generator_and_level_wrappers(l):
     assert getattr(L, pre + "DH")(key, priv, pub, no) == 0 and (0, key.raw) == o.bignDH(priv, pub, no, l)
 
 
+@pytest.mark.skipif(o.ref() is None, reason="oracle/_ref/libbee2ref_64.so not built")
+@pytest.mark.parametrize("l", [128, 192, 256])
+def test_ecMulA_dropin_on_reference_ec_object(l):
+    """The drop-in ecMulA (ec.h:892-901) takes an ec_o BUILT BY THE UNMODIFIED REFERENCE (bignEcCreate) and
+    returns what the reference's own ecMulA returns on the same object: points as n-word arrays, scalars of
+    m <= n words, FALSE for the point at infinity."""
+    import ctypes as C
+    R, L = o.ref(), b.lib()
+    ec = C.c_void_p()
+    assert R.bignEcCreate(C.byref(ec), C.byref(o.ref_params(l))) == 0
+    try:
+        no, n = l // 4, l // 32
+        R.ecMulA_deep.restype = C.c_size_t
+        L.ecMulA.restype = C.c_int
+        L.ecMulA.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        R.ecMulA.restype = C.c_int
+        R.ecMulA.argtypes = L.ecMulA.argtypes
+        stack = C.create_string_buffer(1 << 20)
+        rng = np.random.default_rng(500 + l)
+        p = b.bignParamsStd(b.BIGN_CURVES[l])
+        priv = rng.integers(0, 256, (6, no), dtype=np.uint8)
+        priv[:, no - 1] &= 0x7F
+        _, pts = b.bignPubkeyCalcBatch(p, priv)
+        q = Q if l == 128 else CURVE_Q[l]
+        for i in range(6):
+            for m in (n, n // 2 + 1, 1):
+                d = rng.integers(0, 256, 8 * m, dtype=np.uint8).tobytes()
+                if i == 0 and m == n:
+                    d = q.to_bytes(no, "little")               # q A = O -> FALSE
+                if i == 1 and m == 1:
+                    d = bytes(8)                                # 0 A = O -> FALSE
+                a = pts[i].tobytes()
+                got, want = C.create_string_buffer(2 * no), C.create_string_buffer(2 * no)
+                r1 = L.ecMulA(got, a, ec, d, m, None)
+                r2 = R.ecMulA(want, a, ec, d, m, stack)
+                assert r1 == r2, (i, m)
+                if r2:
+                    assert got.raw == want.raw, (i, m)
+        assert L.ecMulA_deep(n, 3, 0, n) == 0
+    finally:
+        R.bignEcClose(ec)
+
+
 @pytest.mark.parametrize("l", [128, 256])
 def test_dh_batch_vs_oracle(l):
     """d_i Q_j = d_j Q_i (both sides of the exchange agree), keys equal the oracle's, statuses item by item."""
