@@ -755,6 +755,36 @@ bign_dh_kernel(u32* __restrict__ status, u8* __restrict__ out, const u8* __restr
 		status[i] = st;
 }
 
+// sum of k affine points (the tail of the drop-in ecAddMulA: the k products d_i a_i come from
+// ecp_mul_kernel, items with ok_in[i] == 0 are the point at infinity). One thread; k is small.
+template <int N> __global__ void ecp_sum_kernel(u8* __restrict__ out, int* __restrict__ ok_out,
+	const u8* __restrict__ pts, const int* __restrict__ ok_in, u32 k)
+{
+	constexpr int NO = 4 * N;
+	if (blockIdx.x || threadIdx.x)
+		return;
+	pt<N> R;
+	pt_set_inf<N>(R);
+#pragma unroll 1
+	for (u32 i = 0; i < k; ++i)
+	{
+		if (!ok_in[i])
+			continue;
+		fe<N> x, y;
+		fe_load<N>(x, pts + 2 * NO * i), fe_load<N>(y, pts + 2 * NO * i + NO);
+		pt_madd<N>(R, R, x, y);
+	}
+	if (pt_is_inf<N>(R))
+	{
+		ok_out[0] = 0;
+		return;
+	}
+	fe<N> x, y;
+	pt_to_affine<N>(x, y, R);
+	fe_store<N>(out, x), fe_store<N>(out + NO, y);
+	ok_out[0] = 1;
+}
+
 // ---------------------------------------------------------------- launchers (C ABI)
 // q and yG are static constants, GTAB is built lazily; only the belt S-box needs uploading
 extern "C" u32 b2g_bign_upload_tables(const u8 H[256]) { return belt_upload_H(H); }
@@ -1043,6 +1073,28 @@ extern "C" u32 b2g_bignSignBatchL_k_dev(size_t l, void* d_status, void* d_sigs, 
 	if ((uintptr_t)d_status & 3) return B2G_BAD_INPUT;
 	cudaStream_t st = (cudaStream_t)stream;
 #define CALL(N) sign2_launch<N>(d_status, d_sigs, oid, ta, d_hashes, d_privkeys, count, st, d_nonces)
+	return BIGN_DISPATCH(l, CALL);
+#undef CALL
+}
+
+template <int N> static u32 sum_launch(void* d_out, void* d_ok_out, const void* d_pts, const void* d_ok_in, size_t k,
+	cudaStream_t st)
+{
+	ecp_sum_kernel<N><<<1, 32, 0, st>>>((u8*)d_out, (int*)d_ok_out, (const u8*)d_pts, (const int*)d_ok_in, (u32)k);
+	b2g_note_launch();
+	return b2g_check_launch("ecp_sum_kernel");
+}
+
+// d_out (l/2 octets) <- sum of the k affine points d_pts[i] with d_ok_in[i] != 0; d_ok_out[0] = 0 iff the sum is O
+extern "C" u32 b2g_ecSumL_dev(size_t l, void* d_out, void* d_ok_out, const void* d_pts, const void* d_ok_in,
+	size_t k, void* stream)
+{
+	u32 e = b2g_ensure_device();
+	if (e) return e;
+	if (l != 128 && l != 192 && l != 256) return 119u;
+	if (((uintptr_t)d_ok_out & 3) || ((uintptr_t)d_ok_in & 3) || k > 0xFFFFFFFFu) return B2G_BAD_INPUT;
+	cudaStream_t st = (cudaStream_t)stream;
+#define CALL(N) sum_launch<N>(d_out, d_ok_out, d_pts, d_ok_in, k, st)
 	return BIGN_DISPATCH(l, CALL);
 #undef CALL
 }

@@ -8,6 +8,7 @@
 #include "engine.h"
 #include <string.h>
 #include <stdlib.h>
+#include <stdarg.h>
 
 #define CU(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { code = b2g_cuda_fail(e_, what); goto done; } } while (0)
 
@@ -868,5 +869,66 @@ bool_t ecMulA(u64 b[], const u64 a[], const void* ec, const u64 d[], size_t m, v
 		b2g_die("ecMulA", code);
 	if (ok)
 		memcpy(b, out, l / 2);
+	return ok ? 1 : 0;
+}
+
+/* b <- sum_{i<k} d_i a_i for the k (a_i, d_i, m_i) triples that follow k (ec.h:1176-1190, ec.c:1183-1273),
+   FALSE iff the sum is O. The k products run as one batch of ecp_mul_kernel, a one-thread kernel adds
+   them. Same curve recognition and limits as ecMulA (m_i <= n words, k <= 64). */
+bool_t ecAddMulA(u64 b[], const void* ec, void* stack, size_t k, ...)
+{
+	const size_t l = ec_std_level(ec);
+	const size_t no = l / 4;
+	octet pts[64 * 128], scal[64 * 64], out[128];
+	b2g_slot* sl;
+	void *d_a, *d_d, *d_p, *d_ok, *d_out;
+	int ok = 0;
+	err_t code;
+	size_t i;
+	va_list ap;
+	(void)stack;
+	if (!l || !b || k == 0 || k > 64)
+		b2g_die("ecAddMulA (curve is not a standard bign curve, or k > 64: no CPU path)", l ? ERR_BAD_INPUT : ERR_NOT_IMPLEMENTED);
+	memset(scal, 0, sizeof scal);
+	va_start(ap, k);
+	for (i = 0; i < k; ++i)
+	{
+		const u64* a = va_arg(ap, const u64*);
+		const u64* d = va_arg(ap, const u64*);
+		const size_t m = va_arg(ap, size_t);
+		if (!a || !d || 8 * m > no)
+		{
+			va_end(ap);
+			b2g_die("ecAddMulA (m > n)", ERR_BAD_INPUT);
+		}
+		memcpy(pts + 2 * no * i, a, 2 * no);
+		memcpy(scal + no * i, d, 8 * m);
+	}
+	va_end(ap);
+	if ((code = b2g_ensure_device()))
+		b2g_die("ecAddMulA", code);
+	b2g_lock();
+	sl = b2g_slot_get(0);
+	if ((code = stage_in(sl, 0, pts, 2 * no * k, &d_a)) || (code = stage_in(sl, 1, scal, no * k, &d_d)) ||
+		(code = b2g_slot_buf(sl, 2, 2 * no * k, &d_p)) || (code = b2g_slot_buf(sl, 3, 4 * k + 8 + 2 * no, &d_ok)))
+		goto done;
+	d_out = (octet*)d_ok + 4 * k + 8;
+	if ((code = b2g_ecMulABatchL_dev(l, d_p, d_ok, d_a, d_d, no, k, sl->stream)) ||
+		(code = b2g_ecSumL_dev(l, d_out, (octet*)d_ok + 4 * k, d_p, d_ok, k, sl->stream)))
+		goto done;
+	CU(cudaMemcpyAsync(&ok, (octet*)d_ok + 4 * k, 4, cudaMemcpyDeviceToHost, sl->stream), "D2H(ecAddMulA ok)");
+	CU(cudaMemcpyAsync(out, d_out, 2 * no, cudaMemcpyDeviceToHost, sl->stream), "D2H(ecAddMulA)");
+	/* the scalars may be secret: wipe the staged copy */
+	CU(cudaMemsetAsync(d_d, 0, no * k, sl->stream), "memset(ecAddMulA scalars)");
+	CU(cudaStreamSynchronize(sl->stream), "sync(ecAddMulA)");
+done:
+	if (code)
+		cudaStreamSynchronize(sl->stream);
+	b2g_unlock();
+	memset(scal, 0, sizeof scal);
+	if (code)
+		b2g_die("ecAddMulA", code);
+	if (ok)
+		memcpy(b, out, 2 * no);
 	return ok ? 1 : 0;
 }

@@ -338,6 +338,9 @@ err_t ecAddMulABatch(octet* b, int* ok, const octet* a, const octet* d, size_t d
    Other curves abort() — there is no CPU path. `ec` is the reference's `const ec_o*`, `word` = u64. */
 bool_t ecMulA(u64 b[], const u64 a[], const void* ec, const u64 d[], size_t m, void* stack);
 size_t ecMulA_deep(size_t n, size_t ec_d, size_t ec_deep, size_t m);
+/* drop-in: ec.h:1176-1190 (ec.c:1183-1273): b <- sum of d_i a_i over the k triples
+   (const word a_i[], const word d_i[], size_t m_i) that follow k; same recognition as ecMulA, k <= 64 */
+bool_t ecAddMulA(u64 b[], const void* ec, void* stack, size_t k, ...);
 /* the same on the standard curve of level l = 128 / 192 / 256: points l/2 octets, d_len <= l/4,
    k_i l/4 octets */
 err_t ecMulABatchL(size_t l, octet* b, int* ok, const octet* a, const octet* d, size_t d_len, size_t count);
@@ -366,6 +369,8 @@ err_t b2g_bignSignBatchL_k_dev(size_t l, void* d_status, void* d_sigs, const oct
 err_t b2g_bignDHBatchL_dev(size_t l, void* d_status, void* d_out, const void* d_privkeys,
 	const void* d_pubkeys, size_t count, void* stream);
 err_t b2g_bignPubkeyValBatchL_dev(size_t l, void* d_status, const void* d_pubkeys, size_t count, void* stream);
+err_t b2g_ecSumL_dev(size_t l, void* d_out, void* d_ok_out, const void* d_pts, const void* d_ok_in,
+	size_t k, void* stream);
 err_t b2g_ecMulABatchL_dev(size_t l, void* d_b, void* d_ok, const void* d_a, const void* d_d, size_t d_len,
 	size_t count, void* stream);
 err_t b2g_ecAddMulABatchL_dev(size_t l, void* d_b, void* d_ok, const void* d_a, const void* d_d, size_t d_len,

@@ -304,6 +304,31 @@ def test_ecMulA_dropin_on_reference_ec_object(l):
                 if r2:
                     assert got.raw == want.raw, (i, m)
         assert L.ecMulA_deep(n, 3, 0, n) == 0
+        # ecAddMulA (variadic): the verification's own call shape s1 G + s0 Q (bign_sign.c:332), a 3-term sum,
+        # a sum that cancels to O
+        L.ecAddMulA.restype = C.c_int
+        R.ecAddMulA.restype = C.c_int
+        base = bytes(no) + bytes(p.yG)[:no]
+        sz, vp = C.c_size_t, C.c_void_p
+
+        def both(terms):
+            args = []
+            keep = []
+            for a, d in terms:
+                ba, bd = C.create_string_buffer(a, 2 * no), C.create_string_buffer(d, len(d))
+                keep += [ba, bd]
+                args += [C.cast(ba, vp), C.cast(bd, vp), sz(len(d) // 8)]
+            got, want = C.create_string_buffer(2 * no), C.create_string_buffer(2 * no)
+            r1 = L.ecAddMulA(C.cast(got, vp), ec, vp(None), sz(len(terms)), *args)
+            r2 = R.ecAddMulA(C.cast(want, vp), ec, C.cast(stack, vp), sz(len(terms)), *args)
+            assert r1 == r2 and (not r2 or got.raw == want.raw)
+            return r1
+        s1 = rng.integers(0, 256, no, dtype=np.uint8).tobytes()
+        s0 = rng.integers(0, 256, no // 2, dtype=np.uint8).tobytes() + (1).to_bytes(8, "little")
+        assert both([(base, s1), (pts[2].tobytes(), s0)]) == 1
+        assert both([(pts[0].tobytes(), s1), (pts[1].tobytes(), s0), (pts[2].tobytes(), s1[:8])]) == 1
+        neg = (q - 5).to_bytes(no, "little")
+        assert both([(pts[3].tobytes(), (5).to_bytes(8, "little")), (pts[3].tobytes(), neg)]) == 0
     finally:
         R.bignEcClose(ec)
 
