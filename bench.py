@@ -53,7 +53,7 @@ CFG = {
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the bench
 # configuration, from the committed `ncu --set full` captures (profiles/r01_ncu_raw_*.csv)
 NCU_BIGN_WIDE_PER_VERIFY = 101600   # IMAD.WIDE(.X) executed per verify (profiles/r01_bign_opcode_mix.json)
-NCU_TRAFFIC = {"bign_sign2": 29.7e6 + 65.5e6, "belt_dwp": None, "belt_ecb": None, "belt_ctr": 0.13e6 + 1.0142e9, "bash512": 4.4244e9 + 14.5e6, "bign_verify": 2.4819e9 + 531.3e6}
+NCU_TRAFFIC = {"bign_sign2": 50.2e6 + 225.7e6, "belt_dwp": None, "belt_ecb": None, "belt_ctr": 0.13e6 + 1.0142e9, "bash512": 4.4244e9 + 14.5e6, "bign_verify": 6.8026e9 + 1.4227e9}
 
 
 def hbm_peak():
