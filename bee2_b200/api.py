@@ -16,7 +16,7 @@ __all__ = [
     "ERR_OK", "ERR_BAD_INPUT", "ERR_OUTOFMEMORY", "ERR_NOT_IMPLEMENTED", "ERR_FILE_NOT_FOUND",
     "ERR_BAD_OID", "ERR_BAD_PARAMS", "ERR_BAD_PRIVKEY", "ERR_BAD_PUBKEY", "ERR_BAD_SIG", "ERR_BAD_MAC",
     "ERR_B2G_NO_DEVICE", "ERR_B2G_CUDA", "Bee2Error", "BignParams", "lib", "lib_path",
-    "b2g_init", "b2g_last_error", "b2g_sm_count", "b2g_launch_count", "b2g_sync", "b2g_microbench",
+    "b2g_init", "b2g_init_devices", "b2g_device_count", "b2g_ipc_export", "b2g_ipc_open", "b2g_ipc_close", "b2g_last_error", "b2g_sm_count", "b2g_launch_count", "b2g_sync", "b2g_microbench",
     "bashF", "bashHash", "bashHashBatch", "bashHashBatchV", "bashHashFiles", "bashFBatch", "BashHash",
     "beltH", "beltKeyExpand2", "beltBlockEncr", "beltBlockDecr", "beltECBEncr", "beltECBDecr",
     "beltECBEncrBatch", "BeltECB", "BeltCTR", "beltCTR", "beltCTRKeystream", "beltHash", "beltHashBatch",
@@ -95,6 +95,9 @@ def _declare(L: C.CDLL) -> None:
         "b2g_host_alloc": (vp, [sz]), "b2g_host_free": (None, [vp]), "b2g_dev_alloc": (vp, [sz]),
         "b2g_dev_free": (None, [vp]), "b2g_memcpy_h2d": (u32, [vp, vp, sz]), "b2g_memcpy_d2h": (u32, [vp, vp, sz]),
         "b2g_sync": (u32, []), "b2g_launch_count": (u64, []), "b2g_microbench": (C.c_double, [ci, C.c_uint]),
+        "b2g_init_devices": (u32, [ci]), "b2g_device_count": (ci, []),
+        "b2g_ipc_export": (u32, [vp, vp]), "b2g_ipc_open": (u32, [vp, vp]), "b2g_ipc_close": (u32, [vp]),
+        "b2g_memcpy_async": (u32, [vp, vp, sz, ci, vp]),
         "bashF_deep": (sz, []), "bashF": (None, [vp, vp]), "bashHash_keep": (sz, []),
         "bashHashStart": (None, [vp, sz]), "bashHashStepH": (None, [vp, sz, vp]),
         "bashHashStepG": (None, [vp, sz, vp]), "bashHashStepV": (ci, [vp, sz, vp]),
@@ -205,6 +208,38 @@ _PINNED: list = []
 # ------------------------------------------------------------------ engine
 def b2g_init(device: int = -1) -> int:
     return lib().b2g_init(device)
+
+
+def b2g_init_devices(n: int = 0) -> int:
+    """In-process multi-device mode: the *Batch calls shard over devices 0..n-1 (n <= 0: all)."""
+    return lib().b2g_init_devices(n)
+
+
+def b2g_device_count() -> int:
+    return lib().b2g_device_count()
+
+
+def b2g_ipc_export(dptr: int) -> bytes:
+    """CUDA IPC handle (64 octets) of a b2g_dev_alloc'ed buffer, for a peer rank's b2g_ipc_open."""
+    h = (C.c_ubyte * 64)()
+    code = lib().b2g_ipc_export(h, dptr)
+    if code:
+        raise Bee2Error("b2g_ipc_export", code)
+    return bytes(h)
+
+
+def b2g_ipc_open(handle: bytes) -> int:
+    """Map a peer rank's buffer into this process; returns the device pointer."""
+    p = C.c_void_p()
+    hb = (C.c_ubyte * 64).from_buffer_copy(handle)
+    code = lib().b2g_ipc_open(C.byref(p), hb)
+    if code:
+        raise Bee2Error("b2g_ipc_open", code)
+    return int(p.value)
+
+
+def b2g_ipc_close(dptr: int) -> None:
+    lib().b2g_ipc_close(dptr)
 
 
 def b2g_last_error() -> str:

@@ -92,7 +92,9 @@ template <> struct bign_c<16>
 };
 
 // device: BIGN_GN(N) * BIGN_GE entries of 8 N octets (x || y) per level; entry j = 0 unused
-static std::atomic<uint4*> g_gtab[3];
+// one table per device the engine runs on (engine.c: per-device contexts) and level
+#define BIGN_MAX_DEV 16
+static std::atomic<uint4*> g_gtab[BIGN_MAX_DEV][3];
 
 // S-box policy of the belt code inside the bign kernels (belt-hash, belt-WBL)
 #ifndef BIGN_SBOX
@@ -818,7 +820,7 @@ template <int N> static u32 bign_build_gtab(cudaStream_t st, uint4** out)
 template <int N> static u32 bign_ensure_gtab(cudaStream_t st, const uint4** out)
 {
 	static std::mutex mu;
-	std::atomic<uint4*>& slot = g_gtab[N / 4 - 2];
+	std::atomic<uint4*>& slot = g_gtab[b2g_cur_dev() & (BIGN_MAX_DEV - 1)][N / 4 - 2];
 	uint4* p = slot.load(std::memory_order_acquire);
 	if (!p)
 	{

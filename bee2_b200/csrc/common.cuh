@@ -21,6 +21,7 @@ typedef uint64_t u64;
 extern "C" {
 // engine.c
 int b2g_sm_count(void);
+int b2g_cur_dev(void);     // CUDA ordinal selected by the last b2g_ensure_device() on this thread
 void b2g_note_launch(void);
 u32 b2g_check_launch(const char* what);   // cudaGetLastError -> err_t, records text
 u32 b2g_ensure_device(void);

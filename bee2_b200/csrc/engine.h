@@ -9,16 +9,25 @@
 extern "C" {
 #endif
 
-/* lazy per-process initialisation: device check, constant tables. 0 or an err_t. */
+/* selects this thread's device (see engine.c), makes it current, lazily brings the engine up on it
+   (constant tables, streams). 0 or an err_t. Every entry point starts with it. */
 u32 b2g_ensure_device(void);
 void b2g_note_launch(void);
 u32 b2g_check_launch(const char* what);
 u32 b2g_cuda_fail(cudaError_t e, const char* what);   /* records text, returns ERR_B2G_CUDA (or OOM) */
 void b2g_die(const char* fn, u32 code);              /* void drop-ins: print + abort() */
 
-/* One big lock around the host-pointer entry points (they share the workspace). */
+/* The lock of the device selected by the last b2g_ensure_device() on this thread: host-pointer
+   entry points on one device share its workspace. */
 void b2g_lock(void);
 void b2g_unlock(void);
+#define B2G_MAX_DEV 16
+int b2g_cur_dev(void);   /* CUDA ordinal selected by the last b2g_ensure_device() on this thread */
+/* Shard `count` units over the device set (b2g_init_devices): fn(arg, first, n) runs once per
+   device on its own host thread with that device selected; shares are contiguous, multiples of 256
+   units, none smaller than `grain`. One device (or a small batch): a plain call on this thread. */
+typedef u32 (*b2g_shard_fn)(void* arg, size_t first, size_t n);
+u32 b2g_fanout(size_t count, size_t grain, b2g_shard_fn fn, void* arg);
 
 /* Pipelined workspace: NSLOT slots, each a stream + growable device buffers. */
 #define B2G_NSLOT 2
@@ -32,6 +41,10 @@ typedef struct
 b2g_slot* b2g_slot_get(int i);
 /* device buffer `which` of slot `s` with at least `bytes` capacity (grown if needed) */
 u32 b2g_slot_buf(b2g_slot* s, int which, size_t bytes, void** out);
+
+/* waits for the slot's stream, then zeroes every device buffer of the slot (failure paths of the
+   entry points that stage secrets) */
+void b2g_slot_wipe(b2g_slot* s);
 
 /* kernels' device-level launchers that are not part of the public header */
 u32 b2g_belt_upload_tables(const octet H[256]);

@@ -58,7 +58,7 @@ void bashF(octet block[192], void* stack)
 		b2g_die("bashF", code);
 }
 
-err_t bashHashBatch(octet* hashes, size_t l, const void* msgs, size_t msg_len, size_t stride,
+static err_t hash_batch_1(octet* hashes, size_t l, const void* msgs, size_t msg_len, size_t stride,
 	size_t count)
 {
 	err_t code;
@@ -105,6 +105,34 @@ done:
 			cudaStreamSynchronize(b2g_slot_get((int)c)->stream);
 	b2g_unlock();
 	return code;
+}
+
+/* in-process multi-device mode: contiguous shares of the messages, one device each */
+typedef struct
+{
+	octet* hashes;
+	size_t l;
+	const octet* msgs;
+	size_t msg_len, stride;
+} hashb_args;
+static u32 hashb_shard(void* arg, size_t first, size_t n)
+{
+	const hashb_args* a = (const hashb_args*)arg;
+	return hash_batch_1(a->hashes + first * (a->l / 4), a->l, a->msgs + first * a->stride, a->msg_len, a->stride, n);
+}
+err_t bashHashBatch(octet* hashes, size_t l, const void* msgs, size_t msg_len, size_t stride,
+	size_t count)
+{
+	hashb_args a = {hashes, l, (const octet*)msgs, msg_len, stride};
+	/* shares of at least ~16 MiB of message data */
+	const size_t grain = ((size_t)16 << 20) / (msg_len ? msg_len : 1) + 256;
+	if (b2g_device_count() <= 1 || count < 2 * grain)
+		return hash_batch_1(hashes, l, msgs, msg_len, stride, count);
+	if (l == 0 || l % 16 != 0 || l > 256)
+		return ERR_BAD_PARAMS;
+	if (!hashes || (msg_len && !msgs) || stride < msg_len)
+		return ERR_BAD_INPUT;
+	return b2g_fanout(count, grain, hashb_shard, &a);
 }
 
 /* ragged batch: message i = data[offsets[i] .. offsets[i] + lens[i]) — many files in one buffer */

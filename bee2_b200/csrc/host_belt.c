@@ -197,7 +197,7 @@ err_t beltECBDecr(void* dest, const void* src, size_t count, const octet key[], 
 	return ecb_oneshot(dest, src, count, key, len, 1);
 }
 
-err_t beltECBEncrBatch(void* blocks, const octet* keys32, size_t count)
+static err_t ecb_batch_1(void* blocks, const octet* keys32, size_t count)
 {
 	err_t code = ERR_OK;
 	const size_t chunk = b2g_chunk_units(48, CHUNK_BYTES);
@@ -230,6 +230,26 @@ done:
 	return code;
 }
 
+typedef struct
+{
+	octet* blocks;
+	const octet* keys32;
+} ecbk_args;
+static u32 ecbk_shard(void* arg, size_t first, size_t n)
+{
+	const ecbk_args* a = (const ecbk_args*)arg;
+	return ecb_batch_1(a->blocks + 16 * first, a->keys32 + 32 * first, n);
+}
+err_t beltECBEncrBatch(void* blocks, const octet* keys32, size_t count)
+{
+	ecbk_args a = {(octet*)blocks, keys32};
+	if (b2g_device_count() <= 1 || count < ((size_t)1 << 20))
+		return ecb_batch_1(blocks, keys32, count);
+	if (!blocks || !keys32)
+		return ERR_BAD_INPUT;
+	return b2g_fanout(count, (size_t)1 << 19, ecbk_shard, &a);
+}
+
 /* ---------------------------------------------------------------- CTR */
 size_t beltCTR_keep(void) { return sizeof(belt_ctr_st); }
 
@@ -254,8 +274,8 @@ void beltCTRStart(void* state, const octet key[], size_t len, const octet iv[16]
 
 /* dest[0..count) <- src[0..count) ^ keystream(key, ctr0) (src == NULL: keystream only).
    If last_ks != NULL and count % 16 != 0 it receives the whole last keystream block. */
-static err_t ctr_run(octet* dest, const octet* src, size_t count, const u32 key[8], const u32 ctr0[4],
-	octet last_ks[16])
+static err_t ctr_run1(octet* dest, const octet* src, size_t count, const u32 key[8], const u32 ctr0[4],
+	octet last_ks[16], u64 first_block)
 {
 	err_t code = ERR_OK;
 	const size_t chunk = b2g_chunk_units(16, CHUNK_BYTES) * 16;   /* bytes, multiple of 16 */
@@ -280,7 +300,7 @@ static err_t ctr_run(octet* dest, const octet* src, size_t count, const u32 key[
 			CU(cudaMemcpyAsync(d, src + off, n, cudaMemcpyHostToDevice, sl->stream), "H2D(belt ctr)");
 		}
 		/* the padded tail is produced on the device buffer; only n octets go back */
-		if ((code = b2g_beltCTR_dev(d, src ? d : 0, padded, key, ctr0, off / 16, sl->stream)))
+		if ((code = b2g_beltCTR_dev(d, src ? d : 0, padded, key, ctr0, first_block + off / 16, sl->stream)))
 			goto done;
 		CU(cudaMemcpyAsync(dest + off, d, n, cudaMemcpyDeviceToHost, sl->stream), "D2H(belt ctr)");
 		if (padded != n && last_ks)
@@ -292,6 +312,32 @@ done:
 		sync_all();
 	b2g_unlock();
 	return code;
+}
+
+/* in-process multi-device mode: device g produces counter blocks [first, first + n) of the stream */
+typedef struct
+{
+	octet* dest;
+	const octet* src;
+	size_t count;
+	const u32 *key, *ctr0;
+	octet* last_ks;
+} ctr_args;
+static u32 ctr_shard(void* arg, size_t first, size_t n)
+{
+	const ctr_args* a = (const ctr_args*)arg;
+	const size_t off = 16 * first;
+	const size_t bytes = a->count - off < 16 * n ? a->count - off : 16 * n;
+	return ctr_run1(a->dest + off, a->src ? a->src + off : 0, bytes, a->key, a->ctr0,
+		off + bytes == a->count ? a->last_ks : 0, first);
+}
+static err_t ctr_run(octet* dest, const octet* src, size_t count, const u32 key[8], const u32 ctr0[4],
+	octet last_ks[16])
+{
+	ctr_args a = {dest, src, count, key, ctr0, last_ks};
+	if (b2g_device_count() <= 1 || count < ((size_t)32 << 20))
+		return ctr_run1(dest, src, count, key, ctr0, last_ks, 0);
+	return b2g_fanout((count + 15) / 16, (size_t)1 << 20, ctr_shard, &a);
 }
 
 void beltCTRStepE(void* buf, size_t count, void* state)

@@ -205,11 +205,11 @@ static size_t verify_chunk(void)
 	return (size_t)1 << 18;
 }
 
-err_t bignVerifyBatch(err_t* status, const bign_params* params, const octet oid_der[], size_t oid_len,
+static err_t verify_batch_1(err_t* status, const bign_params* params, const octet oid_der[], size_t oid_len,
 	const octet* hashes, const octet* sigs, const octet* pubkeys, size_t count)
 {
 	err_t code;
-	b2g_slot *s0 = b2g_slot_get(0), *s1 = b2g_slot_get(1);
+	b2g_slot *s0, *s1;
 	void *d_h, *d_s, *d_p, *d_st;
 	size_t no;
 	if ((code = params_check(params)))
@@ -224,6 +224,7 @@ err_t bignVerifyBatch(err_t* status, const bign_params* params, const octet oid_
 	if (!count)
 		return ERR_OK;
 	b2g_lock();
+	s0 = b2g_slot_get(0), s1 = b2g_slot_get(1);
 	/* chunks of verify_chunk() items alternate between the two workspace slots, so the H2D copy of
 	   one chunk overlaps the kernel of the previous one */
 	{
@@ -250,6 +251,36 @@ done:
 		cudaStreamSynchronize(s0->stream), cudaStreamSynchronize(s1->stream);
 	b2g_unlock();
 	return code;
+}
+
+/* in-process multi-device mode: contiguous shares of the batch, one device each */
+typedef struct
+{
+	err_t* status;
+	const bign_params* params;
+	const octet* oid_der;
+	size_t oid_len;
+	const octet *hashes, *sigs, *pubkeys;
+} verify_args;
+static u32 verify_shard(void* arg, size_t first, size_t n)
+{
+	const verify_args* a = (const verify_args*)arg;
+	const size_t no = a->params->l / 4;
+	return verify_batch_1(a->status + first, a->params, a->oid_der, a->oid_len, a->hashes + no * first,
+		a->sigs + (no + no / 2) * first, a->pubkeys + 2 * no * first, n);
+}
+err_t bignVerifyBatch(err_t* status, const bign_params* params, const octet oid_der[], size_t oid_len,
+	const octet* hashes, const octet* sigs, const octet* pubkeys, size_t count)
+{
+	verify_args a = {status, params, oid_der, oid_len, hashes, sigs, pubkeys};
+	err_t code;
+	if (b2g_device_count() <= 1 || count < 2 * 4096)
+		return verify_batch_1(status, params, oid_der, oid_len, hashes, sigs, pubkeys, count);
+	if ((code = params_check(params)))
+		return code;
+	if (!status || !hashes || !sigs || !pubkeys)
+		return ERR_BAD_INPUT;
+	return b2g_fanout(count, 4096, verify_shard, &a);
 }
 
 err_t bignVerify(const bign_params* params, const octet oid_der[], size_t oid_len,
@@ -312,15 +343,39 @@ static err_t sign2_batch(err_t* status, octet* sigs, const bign_params* params, 
 	CU(cudaStreamSynchronize(s0->stream), "sync(bign sign2)");
 done:
 	if (code)
-		cudaStreamSynchronize(s0->stream);
+		b2g_slot_wipe(s0);   /* failure path: nothing staged (keys, nonces, shared points) stays behind */
 	b2g_unlock();
 	return code;
 }
 
+typedef struct
+{
+	err_t* status;
+	octet* sigs;
+	const bign_params* params;
+	const octet* oid_der;
+	size_t oid_len;
+	const octet *hashes, *privkeys;
+} sign2_args;
+static u32 sign2_shard(void* arg, size_t first, size_t n)
+{
+	const sign2_args* a = (const sign2_args*)arg;
+	const size_t no = a->params->l / 4;
+	return sign2_batch(a->status + first, a->sigs + (no + no / 2) * first, a->params, a->oid_der, a->oid_len,
+		a->hashes + no * first, a->privkeys + no * first, n, 0, 0);
+}
 err_t bignSign2Batch(err_t* status, octet* sigs, const bign_params* params, const octet oid_der[],
 	size_t oid_len, const octet* hashes, const octet* privkeys, size_t count)
 {
-	return sign2_batch(status, sigs, params, oid_der, oid_len, hashes, privkeys, count, 0, 0);
+	sign2_args a = {status, sigs, params, oid_der, oid_len, hashes, privkeys};
+	err_t code;
+	if (b2g_device_count() <= 1 || count < 2 * 4096)
+		return sign2_batch(status, sigs, params, oid_der, oid_len, hashes, privkeys, count, 0, 0);
+	if ((code = params_check(params)))
+		return code;
+	if (!status || !sigs || !hashes || !privkeys)
+		return ERR_BAD_INPUT;
+	return b2g_fanout(count, 4096, sign2_shard, &a);
 }
 
 err_t bignSign2(octet sig[], const bign_params* params, const octet oid_der[], size_t oid_len,
@@ -336,7 +391,7 @@ err_t bignSign2(octet sig[], const bign_params* params, const octet oid_der[], s
 	return st;
 }
 
-err_t bignPubkeyCalcBatch(err_t* status, octet* pubkeys, const bign_params* params,
+static err_t pubkey_batch_1(err_t* status, octet* pubkeys, const bign_params* params,
 	const octet* privkeys, size_t count)
 {
 	err_t code;
@@ -366,9 +421,36 @@ err_t bignPubkeyCalcBatch(err_t* status, octet* pubkeys, const bign_params* para
 	CU(cudaStreamSynchronize(s0->stream), "sync(bign pubkey)");
 done:
 	if (code)
-		cudaStreamSynchronize(s0->stream);
+		b2g_slot_wipe(s0);   /* failure path: nothing staged (keys, nonces, shared points) stays behind */
 	b2g_unlock();
 	return code;
+}
+
+typedef struct
+{
+	err_t* status;
+	octet* pubkeys;
+	const bign_params* params;
+	const octet* privkeys;
+} pubkey_args;
+static u32 pubkey_shard(void* arg, size_t first, size_t n)
+{
+	const pubkey_args* a = (const pubkey_args*)arg;
+	const size_t no = a->params->l / 4;
+	return pubkey_batch_1(a->status + first, a->pubkeys + 2 * no * first, a->params, a->privkeys + no * first, n);
+}
+err_t bignPubkeyCalcBatch(err_t* status, octet* pubkeys, const bign_params* params,
+	const octet* privkeys, size_t count)
+{
+	pubkey_args a = {status, pubkeys, params, privkeys};
+	err_t code;
+	if (b2g_device_count() <= 1 || count < 2 * 4096)
+		return pubkey_batch_1(status, pubkeys, params, privkeys, count);
+	if ((code = params_check(params)))
+		return code;
+	if (!status || !pubkeys || !privkeys)
+		return ERR_BAD_INPUT;
+	return b2g_fanout(count, 4096, pubkey_shard, &a);
 }
 
 err_t bignPubkeyCalc(octet pubkey[], const bign_params* params, const octet privkey[])
@@ -415,7 +497,7 @@ err_t ecMulABatchL(size_t l, octet* b, int* ok, const octet* a, const octet* d, 
 	CU(cudaStreamSynchronize(s0->stream), "sync(ecMulA)");
 done:
 	if (code)
-		cudaStreamSynchronize(s0->stream);
+		b2g_slot_wipe(s0);   /* failure path: nothing staged (keys, nonces, shared points) stays behind */
 	b2g_unlock();
 	return code;
 }
@@ -457,7 +539,7 @@ err_t ecAddMulABatchL(size_t l, octet* b, int* ok, const octet* a, const octet* 
 	CU(cudaStreamSynchronize(s0->stream), "sync(ecAddMulA)");
 done:
 	if (code)
-		cudaStreamSynchronize(s0->stream);
+		b2g_slot_wipe(s0);   /* failure path: nothing staged (keys, nonces, shared points) stays behind */
 	b2g_unlock();
 	return code;
 }
@@ -596,7 +678,7 @@ err_t bignPubkeyValBatch(err_t* status, const bign_params* params, const octet* 
 	CU(cudaStreamSynchronize(s0->stream), "sync(bign pubkey val)");
 done:
 	if (code)
-		cudaStreamSynchronize(s0->stream);
+		b2g_slot_wipe(s0);   /* failure path: nothing staged (keys, nonces, shared points) stays behind */
 	b2g_unlock();
 	return code;
 }
@@ -654,7 +736,7 @@ err_t bignDHBatch(err_t* status, octet* keys, const bign_params* params, const o
 			memcpy(keys + key_len * i, full + 2 * no * i, key_len);
 done:
 	if (code)
-		cudaStreamSynchronize(s0->stream);
+		b2g_slot_wipe(s0);   /* failure path: nothing staged (keys, nonces, shared points) stays behind */
 	b2g_unlock();
 	if (full)
 	{
@@ -752,7 +834,7 @@ err_t bignSignBatch(err_t* status, octet* sigs, const bign_params* params, const
 	CU(cudaStreamSynchronize(s0->stream), "sync(bign sign)");
 done:
 	if (code)
-		cudaStreamSynchronize(s0->stream);
+		b2g_slot_wipe(s0);   /* failure path: nothing staged (keys, nonces, shared points) stays behind */
 	b2g_unlock();
 	memset(nonces, 0, count * no), free(nonces);
 	return code;
@@ -923,7 +1005,7 @@ bool_t ecAddMulA(u64 b[], const void* ec, void* stack, size_t k, ...)
 	CU(cudaStreamSynchronize(sl->stream), "sync(ecAddMulA)");
 done:
 	if (code)
-		cudaStreamSynchronize(sl->stream);
+		b2g_slot_wipe(sl);
 	b2g_unlock();
 	memset(scal, 0, sizeof scal);
 	if (code)

@@ -62,8 +62,18 @@ typedef u32 err_t;
 #define ERR_B2G_CUDA 9002u        /* a CUDA call failed; see b2g_last_error() */
 
 /* ======================================================================= engine */
-/* Select the CUDA device for this process (default: current device). Idempotent. */
+/* Bring the engine up on CUDA device `device` and make it current on the calling thread
+   (< 0: the thread's current device). The first device initialised is the PRIMARY one: host-pointer
+   calls from threads whose current CUDA device is not an initialised one run there. Idempotent;
+   may be called for several devices (a caller that drives each device from its own thread). */
 err_t b2g_init(int device);
+/* In-process multi-device mode: bring the engine up on devices 0..n-1 (n <= 0: all visible) and
+   shard the units of the host-pointer *Batch entry points (bashHashBatch, beltCTRKeystream,
+   beltECBEncrBatch, bignVerifyBatch, bignSign2Batch, bignPubkeyCalcBatch) over them — one host
+   thread and stream set per device, contiguous shares, results byte-identical to one device. */
+err_t b2g_init_devices(int n);
+/* Number of devices the Batch entry points shard over (1 unless b2g_init_devices was called). */
+int b2g_device_count(void);
 /* Human-readable text of the last CUDA failure on this thread ("" if none). */
 const char* b2g_last_error(void);
 /* Number of SMs of the active device (grid sizing is a multiple of it). */
@@ -77,6 +87,14 @@ void b2g_dev_free(void* p);
 err_t b2g_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes);
 err_t b2g_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes);
 err_t b2g_sync(void);
+/* One process per GPU (torchrun): map a b2g_dev_alloc'ed buffer of another rank into this process
+   (CUDA IPC, peer access over NVLink enabled on open). A `b2g_*_dev` launcher given such a pointer
+   as its output writes straight into the peer's HBM — compute and the final gather in ONE kernel. */
+err_t b2g_ipc_export(octet handle[64], void* dptr);
+err_t b2g_ipc_open(void** dptr, const octet handle[64]);
+err_t b2g_ipc_close(void* dptr);
+/* cudaMemcpyAsync on a caller's stream (to_device != 0: H2D, else D2H) */
+err_t b2g_memcpy_async(void* dst, const void* src, size_t n, int to_device, void* stream);
 /* How many kernels this library has launched in this process (for gpu_launches). */
 u64 b2g_launch_count(void);
 /* Measured issue peak of one instruction kind, lane-operations per second on the whole chip:
