@@ -133,7 +133,7 @@ def _declare(L: C.CDLL) -> None:
         "b2g_beltCHEMac_dev": (u32, [vp, vp, sz, vp, sz, vp, vp, vp, vp]),
         "b2g_beltDWPMac_dev": (u32, [vp, vp, sz, vp, sz, vp, vp, vp, vp]),
         "b2g_beltCTR_dev": (u32, [vp, vp, sz, vp, vp, u64, vp]), "b2g_beltECB_dev": (u32, [vp, vp, sz, vp, ci, vp]),
-        "b2g_beltECBEncrBatch_dev": (u32, [vp, vp, sz, vp]), "b2g_beltHashBatch_dev": (u32, [vp, vp, sz, sz, sz, vp]),
+        "b2g_beltECBEncrBatch_dev": (u32, [vp, vp, sz, vp]), "b2g_beltECBEncrBatch2_dev": (u32, [vp, vp, vp, sz, vp]), "b2g_beltHashBatch_dev": (u32, [vp, vp, sz, sz, sz, vp]),
         "bignParamsStd": (u32, [vp, C.c_char_p]), "bignVerify": (u32, [vp, vp, sz, vp, vp, vp]),
         "bignSign2": (u32, [vp, vp, vp, sz, vp, vp, vp, sz]), "bignPubkeyCalc": (u32, [vp, vp, vp]),
         "bignVerifyBatch": (u32, [vp, vp, vp, sz, vp, vp, vp, sz]),

@@ -140,7 +140,7 @@ belt_che_kernel(uint4* dst, const uint4* src, u64 nblocks, u32 tail, const BeltK
 template <bool DEC, bool MULTIKEY>
 __global__ void __launch_bounds__(BELT_THREADS, 1)
 belt_ecb_kernel(uint4* dst, const uint4* src, const uint4* __restrict__ keys, u64 nblocks,
-	const BeltKey key)
+	const BeltKey key, const bool keys32 = false)
 {
 	extern __shared__ __align__(1024) u8 sm[];
 	BeltBigT::fill(sm);
@@ -160,7 +160,13 @@ belt_ecb_kernel(uint4* dst, const uint4* src, const uint4* __restrict__ keys, u6
 				v[u] = ldg_stream(src + j);
 				if (MULTIKEY)
 				{
-					const uint4 k0 = ldg_stream(keys + 2 * j), k1 = ldg_stream(keys + 2 * j + 1);
+					// one 256-bit request per thread when the key array is 32-byte aligned: each 32-byte
+					// sector is fetched once (two 128-bit loads at stride 32 fetch every sector twice)
+					uint4 k0, k1;
+					if (keys32)
+						ldg_stream256(keys + 2 * j, k0, k1);
+					else
+						k0 = ldg_stream(keys + 2 * j), k1 = ldg_stream(keys + 2 * j + 1);
 					k[u][0] = k0.x, k[u][1] = k0.y, k[u][2] = k0.z, k[u][3] = k0.w;
 					k[u][4] = k1.x, k[u][5] = k1.y, k[u][6] = k1.z, k[u][7] = k1.w;
 				}
@@ -358,17 +364,23 @@ extern "C" u32 b2g_beltECB_dev(void* d_dest, const void* d_src, size_t nblocks, 
 	return b2g_check_launch("belt_ecb_kernel");
 }
 
-extern "C" u32 b2g_beltECBEncrBatch_dev(void* d_blocks, const void* d_keys32, size_t count, void* stream)
+// block j of d_src under key j -> block j of d_dst (d_dst may be d_src, or another device's HBM mapped
+// with b2g_ipc_open: the final gather of a sharded batch then happens inside this kernel)
+extern "C" u32 b2g_beltECBEncrBatch2_dev(void* d_dst, const void* d_src, const void* d_keys32, size_t count, void* stream)
 {
 	u32 e = b2g_ensure_device();
 	if (e) return e;
 	if (count == 0) return B2G_OK;
-	if (((uintptr_t)d_blocks & 15) || ((uintptr_t)d_keys32 & 15)) return B2G_BAD_INPUT;
+	if (((uintptr_t)d_dst & 15) || ((uintptr_t)d_src & 15) || ((uintptr_t)d_keys32 & 15)) return B2G_BAD_INPUT;
 	BeltKey k = {};
 	belt_ecb_kernel<false, true><<<belt_grid(count), BELT_THREADS, BELT_BIGT_BYTES, (cudaStream_t)stream>>>(
-		(uint4*)d_blocks, (const uint4*)d_blocks, (const uint4*)d_keys32, count, k);
+		(uint4*)d_dst, (const uint4*)d_src, (const uint4*)d_keys32, count, k, ((uintptr_t)d_keys32 & 31) == 0);
 	b2g_note_launch();
 	return b2g_check_launch("belt_ecb_kernel<multikey>");
+}
+extern "C" u32 b2g_beltECBEncrBatch_dev(void* d_blocks, const void* d_keys32, size_t count, void* stream)
+{
+	return b2g_beltECBEncrBatch2_dev(d_blocks, d_blocks, d_keys32, count, stream);
 }
 
 // ---------------------------------------------------------------- belt-hash, streaming form

@@ -287,6 +287,13 @@ template <int N> __device__ __noinline__ fe<N> block_inv(const fe<N> z, u32* sm)
 	const int tid = threadIdx.x;
 	fe<N> a, b;
 	tree_put<N>(sm, BIGN_T(N) + tid, z);
+	// a CTA may be launched with fewer than BIGN_T(N) threads (bign_shape: balanced grids for small
+	// batches), at least BIGN_T(N) / 2: the missing leaves are 1
+	if (tid + (int)blockDim.x < BIGN_T(N))
+	{
+		fe_set_u32<N>(a, 1);
+		tree_put<N>(sm, BIGN_T(N) + tid + (int)blockDim.x, a);
+	}
 	__syncthreads();
 	// up: products of the children
 #pragma unroll 1
@@ -846,7 +853,28 @@ static u32 make_oid(OidArg& o, const u8* der, size_t len)
 	return B2G_OK;
 }
 
-template <int N> static inline u32 bign_grid(size_t count) { return (u32)((count + BIGN_T(N) - 1) / BIGN_T(N)); }
+// CTA size for a batch of `count` items. Large batches: BIGN_T(N) threads (one inversion per CTA amortised
+// over the most items). Small batches (a shard of a strong-scaled job): the time is the load of the busiest
+// SM, ceil(CTAs / SMs) x threads, so try smaller CTAs too and take the smallest load, with a measured
+// penalty for the shorter amortisation (128-thread CTAs are ~6 % slower per item than 256-thread ones).
+// 2^17 items on 148 SMs: 512 CTAs of 256 put 4 CTAs = 1024 threads on some SMs (1.70x of one GPU's rate
+// at N = 2, measured), 586 CTAs of 224 put at most 896 (ideal 886).
+template <int N> static inline u32 bign_threads(size_t count)
+{
+	const u64 sms = (u64)b2g_sm_count();
+	u32 best_t = BIGN_T(N);
+	double best = 0;
+	for (u32 t = BIGN_T(N); t >= BIGN_T(N) / 2; t -= 32)
+	{
+		const u64 ctas = (count + t - 1) / t;
+		const u64 per_sm = (ctas + sms - 1) / sms;
+		const double cost = (double)(per_sm * t) * (1.0 + 0.06 * (double)(BIGN_T(N) - t) / (BIGN_T(N) / 2));
+		if (best == 0 || cost < best * 0.995)
+			best = cost, best_t = t;
+	}
+	return best_t;
+}
+template <int N> static inline u32 bign_grid(size_t count, u32 threads) { return (u32)((count + threads - 1) / threads); }
 
 template <int N> static u32 verify_launch(void* d_status, const OidArg& oid, const void* d_hashes, const void* d_sigs,
 	const void* d_pubkeys, size_t count, cudaStream_t st)
@@ -854,7 +882,7 @@ template <int N> static u32 verify_launch(void* d_status, const OidArg& oid, con
 	const uint4* gtab;
 	u32 e = bign_ensure_gtab<N>(st, &gtab);
 	if (e) return e;
-	bign_verify_kernel<N><<<bign_grid<N>(count), BIGN_T(N), 0, st>>>((u32*)d_status, (const u8*)d_hashes,
+	bign_verify_kernel<N><<<bign_grid<N>(count, bign_threads<N>(count)), bign_threads<N>(count), 0, st>>>((u32*)d_status, (const u8*)d_hashes,
 		(const u8*)d_sigs, (const u8*)d_pubkeys, count, oid, gtab);
 	b2g_note_launch();
 	return b2g_check_launch("bign_verify_kernel");
@@ -891,7 +919,7 @@ template <int N> static u32 sign2_launch(void* d_status, void* d_sigs, const Oid
 	const uint4* gtab;
 	u32 e = bign_ensure_gtab<N>(st, &gtab);
 	if (e) return e;
-	bign_sign2_kernel<N><<<bign_grid<N>(count), BIGN_T(N), 0, st>>>((u32*)d_status, (u8*)d_sigs,
+	bign_sign2_kernel<N><<<bign_grid<N>(count, bign_threads<N>(count)), bign_threads<N>(count), 0, st>>>((u32*)d_status, (u8*)d_sigs,
 		(const u8*)d_hashes, (const u8*)d_privkeys, count, oid, ta, gtab, (const u8*)d_nonces);
 	b2g_note_launch();
 	return b2g_check_launch("bign_sign2_kernel");
@@ -932,7 +960,7 @@ template <int N> static u32 pubkey_launch(void* d_status, void* d_pubkeys, const
 	const uint4* gtab;
 	u32 e = bign_ensure_gtab<N>(st, &gtab);
 	if (e) return e;
-	bign_pubkey_kernel<N><<<bign_grid<N>(count), BIGN_T(N), 0, st>>>((u32*)d_status, (u8*)d_pubkeys,
+	bign_pubkey_kernel<N><<<bign_grid<N>(count, bign_threads<N>(count)), bign_threads<N>(count), 0, st>>>((u32*)d_status, (u8*)d_pubkeys,
 		(const u8*)d_privkeys, count, gtab);
 	b2g_note_launch();
 	return b2g_check_launch("bign_pubkey_kernel");
@@ -960,7 +988,7 @@ extern "C" u32 b2g_bignPubkeyCalcBatch_dev(void* d_status, void* d_pubkeys, cons
 template <int N> static u32 mul_launch(void* d_b, void* d_ok, const void* d_a, const void* d_d, size_t d_len,
 	size_t count, cudaStream_t st)
 {
-	ecp_mul_kernel<N><<<bign_grid<N>(count), BIGN_T(N), 0, st>>>((u8*)d_b, (int*)d_ok,
+	ecp_mul_kernel<N><<<bign_grid<N>(count, bign_threads<N>(count)), bign_threads<N>(count), 0, st>>>((u8*)d_b, (int*)d_ok,
 		(const u8*)d_a, (const u8*)d_d, (u32)d_len, (const u8*)0, count, (const uint4*)0);
 	b2g_note_launch();
 	return b2g_check_launch("ecp_mul_kernel");
@@ -993,7 +1021,7 @@ template <int N> static u32 addmul_launch(void* d_b, void* d_ok, const void* d_a
 	u32 e = bign_ensure_gtab<N>(st, &gtab);
 	if (e) return e;
 	if (!d_k) return B2G_BAD_INPUT;
-	ecp_mul_kernel<N><<<bign_grid<N>(count), BIGN_T(N), 0, st>>>((u8*)d_b, (int*)d_ok, (const u8*)d_a,
+	ecp_mul_kernel<N><<<bign_grid<N>(count, bign_threads<N>(count)), bign_threads<N>(count), 0, st>>>((u8*)d_b, (int*)d_ok, (const u8*)d_a,
 		(const u8*)d_d, (u32)d_len, (const u8*)d_k, count, gtab);
 	b2g_note_launch();
 	return b2g_check_launch("ecp_mul_kernel(+G)");
@@ -1022,7 +1050,7 @@ extern "C" u32 b2g_ecAddMulABatch_dev(void* d_b, void* d_ok, const void* d_a, co
 template <int N> static u32 dh_launch(void* d_status, void* d_out, const void* d_privkeys, const void* d_pubkeys,
 	size_t count, u32 validate_only, cudaStream_t st)
 {
-	bign_dh_kernel<N><<<bign_grid<N>(count), BIGN_T(N), 0, st>>>((u32*)d_status, (u8*)d_out,
+	bign_dh_kernel<N><<<bign_grid<N>(count, bign_threads<N>(count)), bign_threads<N>(count), 0, st>>>((u32*)d_status, (u8*)d_out,
 		(const u8*)d_privkeys, (const u8*)d_pubkeys, count, validate_only);
 	b2g_note_launch();
 	return b2g_check_launch("bign_dh_kernel");

@@ -42,3 +42,10 @@ __device__ __forceinline__ void stg_stream(uint4* p, uint4 v)
 	asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
 		:: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+
+// 256-bit streaming load (LDG.E.256, new on sm_100): 32 octets per thread in one request, p 32-byte aligned
+__device__ __forceinline__ void ldg_stream256(const uint4* p, uint4& lo, uint4& hi)
+{
+	asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(p));
+}

@@ -3,7 +3,9 @@
  * tables, error mapping, pinned/device allocators and the pipelined workspace used by
  * the host-pointer entry points. No cryptographic computation happens here.
  */
+#define _GNU_SOURCE
 #include "engine.h"
+#include <dlfcn.h>
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -443,4 +445,59 @@ err_t b2g_memcpy_async(void* dst, const void* src, size_t n, int to_device, void
 	cudaError_t e = cudaMemcpyAsync(dst, src, n, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
 		(cudaStream_t)stream);
 	return e == cudaSuccess ? ERR_OK : b2g_cuda_fail(e, "cudaMemcpyAsync");
+}
+
+/* ---- overlay mode: forwarding to the stock libbee2 behind this library ---- */
+static volatile u64 g_forwards;
+static volatile long g_cpu_below = -1;     /* -1: not read from the environment yet */
+
+void* b2g_stock(const char* name)
+{
+	/* RTLD_NEXT: the next definition of `name` after THIS library in the search order, i.e. the
+	   stock libbee2 the application (also) links; NULL when there is none */
+	void* f = dlsym(RTLD_NEXT, name);
+	(void)dlerror();
+	return f;
+}
+void b2g_note_forward(void) { __sync_fetch_and_add(&g_forwards, 1); }
+u64 b2g_forward_count(void) { return g_forwards; }
+void b2g_warn_forward(const char* fn, u32 code)
+{
+	static int said;
+	b2g_note_forward();
+	if (!__sync_lock_test_and_set(&said, 1))
+		fprintf(stderr, "bee2_b200: %s cannot run on the GPU path (err %u: %s); forwarding such calls to the stock "
+			"libbee2 behind this library (said once)\n", fn, code, g_err);
+}
+void b2g_set_cpu_below(size_t bytes) { g_cpu_below = (long)bytes; }
+int b2g_route_small(size_t bytes)
+{
+	long t = g_cpu_below;
+	if (t < 0)
+	{
+		const char* e = getenv("B2G_CPU_BELOW");
+		t = e && *e ? strtol(e, 0, 0) : 0;
+		if (t < 0)
+			t = 0;
+		g_cpu_below = t;
+	}
+	return t > 0 && bytes < (size_t)t;
+}
+int b2g_has_stock(void) { return b2g_stock("bashHash") != 0; }
+
+int b2g_ct_eq(const void* a, const void* b, size_t n)
+{
+	const volatile octet* x = (const volatile octet*)a;
+	const volatile octet* y = (const volatile octet*)b;
+	octet d = 0;
+	size_t i;
+	for (i = 0; i < n; ++i)
+		d |= x[i] ^ y[i];
+	return d == 0;
+}
+void b2g_wipe(void* p, size_t n)
+{
+	volatile octet* v = (volatile octet*)p;
+	while (n--)
+		*v++ = 0;
 }

@@ -65,6 +65,45 @@ u32 b2g_beltHashStep_dev(void* d_state, const void* d_data, size_t nblocks, int 
 /* units per pipeline chunk so that one chunk moves about `target_bytes` */
 size_t b2g_chunk_units(size_t unit_bytes, size_t target_bytes);
 
+/* ---- overlay mode (SURVEY.md §8b "Packaging consequence") ----------------
+   When a stock libbee2 sits BEHIND this library in the process's symbol search order (link order
+   `-lbee2_b200 -lbee2`, or LD_PRELOAD=libbee2_b200.so), the drop-in entry points forward to it —
+   through dlsym(RTLD_NEXT, name), never to oracle/ — in three cases:
+     1. inputs the GPU path does not cover (non-standard bign_params, a generic ec_o, m > n words,
+        an OID or `t` longer than 64 octets);
+     2. payloads below the routing threshold (b2g_set_cpu_below / B2G_CPU_BELOW, default 0 = off):
+        a 13-byte bashHash or a single beltBlockEncr is latency-bound on any GPU;
+     3. a `void` drop-in whose GPU path failed (instead of abort()).
+   Without a stock library behind, 1 returns ERR_NOT_IMPLEMENTED and 3 aborts, as before. */
+/* constant-time comparison of digests / MACs (the reference's memEq is regular too, mem.c) */
+int b2g_ct_eq(const void* a, const void* b, size_t n);
+/* zero a host buffer that held key material (not optimised away) */
+void b2g_wipe(void* p, size_t n);
+void* b2g_stock(const char* name);
+int b2g_route_small(size_t bytes);
+void b2g_note_forward(void);
+/* a call handed to stock libbee2 because the GPU path could NOT run it (not by routing policy):
+   counted, and said once per process on stderr — the engine never degrades silently */
+void b2g_warn_forward(const char* fn, u32 code);
+#define B2G_STOCK_FN(name) __extension__({ static void* f_; static int tried_; \
+	if (!tried_) { f_ = b2g_stock(#name); __sync_synchronize(); tried_ = 1; } (__typeof__(&name))f_; })
+/* forward a small call: for functions returning a value / void */
+#define B2G_SMALL_R(bytes, name, ...) do { if (b2g_route_small(bytes)) { __typeof__(&name) fs_ = B2G_STOCK_FN(name); \
+	if (fs_) { b2g_note_forward(); return fs_(__VA_ARGS__); } } } while (0)
+#define B2G_SMALL_V(bytes, name, ...) do { if (b2g_route_small(bytes)) { __typeof__(&name) fs_ = B2G_STOCK_FN(name); \
+	if (fs_) { b2g_note_forward(); fs_(__VA_ARGS__); return; } } } while (0)
+/* forward unconditionally if a stock library exists (unsupported input) */
+#define B2G_STOCK_R(name, ...) do { __typeof__(&name) fs_ = B2G_STOCK_FN(name); \
+	if (fs_) { b2g_note_forward(); return fs_(__VA_ARGS__); } } while (0)
+/* the GPU path of a void drop-in failed: stock if there is one, else abort */
+#define B2G_FAIL_V(code, name, ...) do { __typeof__(&name) fs_ = B2G_STOCK_FN(name); \
+	if (fs_) { b2g_note_forward(); fs_(__VA_ARGS__); return; } b2g_die(#name, code); } while (0)
+/* first line of a void drop-in: no usable device -> the whole call goes to stock libbee2, untouched */
+#define B2G_PREFLIGHT_V(name, ...) do { const u32 pc_ = b2g_ensure_device(); if (pc_) B2G_FAIL_V(pc_, name, __VA_ARGS__); } while (0)
+#define B2G_PREFLIGHT_R(name, ...) do { const u32 pc_ = b2g_ensure_device(); if (pc_) B2G_FAIL_R(pc_, name, __VA_ARGS__); } while (0)
+#define B2G_FAIL_R(code, name, ...) do { __typeof__(&name) fs_ = B2G_STOCK_FN(name); \
+	if (fs_) { b2g_note_forward(); return fs_(__VA_ARGS__); } b2g_die(#name, code); } while (0)
+
 #ifdef __cplusplus
 }
 #endif

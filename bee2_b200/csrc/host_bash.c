@@ -52,10 +52,10 @@ done:
 
 void bashF(octet block[192], void* stack)
 {
-	err_t code = bashFBatch(block, 1);
-	(void)stack;
-	if (code)
-		b2g_die("bashF", code);
+	err_t code;
+	B2G_SMALL_V(192, bashF, block, stack);
+	if ((code = bashFBatch(block, 1)))
+		B2G_FAIL_V(code, bashF, block, stack);
 }
 
 static err_t hash_batch_1(octet* hashes, size_t l, const void* msgs, size_t msg_len, size_t stride,
@@ -181,6 +181,7 @@ err_t bashHash(octet hash[], size_t l, const void* src, size_t count)
 		return ERR_BAD_PARAMS;
 	if ((count && !src) || !hash)
 		return ERR_BAD_INPUT;
+	B2G_SMALL_R(count, bashHash, hash, l, src, count);
 	return bashHashBatch(hash, l, src, count, count, 1);
 }
 
@@ -220,9 +221,11 @@ done:
 
 void bashHashStepH(const void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(bashHashStepH, buf, count, state);
 	bash_hash_st* st = (bash_hash_st*)state;
 	const octet* p = (const octet*)buf;
 	size_t nfull;
+	const size_t pos0 = st->pos;
 	err_t code;
 	if (count < st->buf_len - st->pos)
 	{
@@ -234,35 +237,44 @@ void bashHashStepH(const void* buf, size_t count, void* state)
 	p += st->buf_len - st->pos, count -= st->buf_len - st->pos;
 	nfull = count / st->buf_len;
 	if ((code = sponge_absorb(st, p, nfull)))
-		b2g_die("bashHashStepH", code);
+	{
+		/* the device result is copied into the state only on success: s[0..pos0) is still the
+		   pending input, so the stock code (same state layout) can take the whole call over */
+		st->pos = pos0;
+		B2G_FAIL_V(code, bashHashStepH, buf, (p - (const octet*)buf) + count, state);
+	}
 	p += nfull * st->buf_len, count -= nfull * st->buf_len;
 	st->pos = count;
 	if (count)
 		memcpy(st->s, p, count);
 }
 
-static void sponge_final(bash_hash_st* st)
+static err_t sponge_final(bash_hash_st* st)
 {
-	err_t code;
 	memcpy(st->s1, st->s, 192);
 	memset(st->s1 + st->pos, 0, st->buf_len - st->pos);
 	st->s1[st->pos] = 0x40;
-	if ((code = bashFBatch(st->s1, 1)))
-		b2g_die("bashHashStepG", code);
+	return bashFBatch(st->s1, 1);
 }
 
 void bashHashStepG(octet hash[], size_t hash_len, void* state)
 {
+	B2G_PREFLIGHT_V(bashHashStepG, hash, hash_len, state);
 	bash_hash_st* st = (bash_hash_st*)state;
-	sponge_final(st);
+	err_t code;
+	if ((code = sponge_final(st)))
+		B2G_FAIL_V(code, bashHashStepG, hash, hash_len, state);   /* s is untouched: stock finishes it */
 	memmove(hash, st->s1, hash_len);
 }
 
 bool_t bashHashStepV(const octet hash[], size_t hash_len, void* state)
 {
+	B2G_PREFLIGHT_R(bashHashStepV, hash, hash_len, state);
 	bash_hash_st* st = (bash_hash_st*)state;
-	sponge_final(st);
-	return memcmp(hash, st->s1, hash_len) == 0;
+	err_t code;
+	if ((code = sponge_final(st)))
+		B2G_FAIL_R(code, bashHashStepV, hash, hash_len, state);
+	return b2g_ct_eq(hash, st->s1, hash_len);
 }
 
 /* ---------------------------------------------------------------- bash-prg (bash_prg.c:54-385) */
@@ -327,6 +339,7 @@ static void prg_commit(bash_prg_st* st, octet code)   /* bash_prg.c:92-105 */
 void bashPrgStart(void* state, size_t l, size_t d, const octet ann[], size_t ann_len, const octet key[],
 	size_t key_len)
 {
+	B2G_PREFLIGHT_V(bashPrgStart, state, l, d, ann, ann_len, key, key_len);
 	bash_prg_st* st = (bash_prg_st*)state;
 	st->pos = 1 + ann_len + key_len;
 	memset(st->s, 0, 192);
@@ -340,6 +353,7 @@ void bashPrgStart(void* state, size_t l, size_t d, const octet ann[], size_t ann
 
 void bashPrgRestart(const octet ann[], size_t ann_len, const octet key[], size_t key_len, void* state)
 {
+	B2G_PREFLIGHT_V(bashPrgRestart, ann, ann_len, key, key_len, state);
 	bash_prg_st* st = (bash_prg_st*)state;
 	size_t i;
 	if (key_len)
@@ -391,49 +405,62 @@ static void prg_step(bash_prg_st* st, octet* buf, size_t count, int mode, const 
 	st->pos = count;
 }
 
-void bashPrgAbsorbStart(void* state) { prg_commit((bash_prg_st*)state, PRG_DATA); }
+void bashPrgAbsorbStart(void* state) { 	B2G_PREFLIGHT_V(bashPrgAbsorbStart, state);
+prg_commit((bash_prg_st*)state, PRG_DATA); }
 void bashPrgAbsorbStep(const void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(bashPrgAbsorbStep, buf, count, state);
 	/* absorb never writes to buf */
 	prg_step((bash_prg_st*)state, (octet*)(size_t)buf, count, 0, "bashPrgAbsorbStep");
 }
 void bashPrgAbsorb(const void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(bashPrgAbsorb, buf, count, state);
 	bashPrgAbsorbStart(state);
 	bashPrgAbsorbStep(buf, count, state);
 }
-void bashPrgSqueezeStart(void* state) { prg_commit((bash_prg_st*)state, PRG_OUT); }
+void bashPrgSqueezeStart(void* state) { 	B2G_PREFLIGHT_V(bashPrgSqueezeStart, state);
+prg_commit((bash_prg_st*)state, PRG_OUT); }
 void bashPrgSqueezeStep(void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(bashPrgSqueezeStep, buf, count, state);
 	prg_step((bash_prg_st*)state, (octet*)buf, count, 1, "bashPrgSqueezeStep");
 }
 void bashPrgSqueeze(void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(bashPrgSqueeze, buf, count, state);
 	bashPrgSqueezeStart(state);
 	bashPrgSqueezeStep(buf, count, state);
 }
-void bashPrgEncrStart(void* state) { prg_commit((bash_prg_st*)state, PRG_TEXT); }
+void bashPrgEncrStart(void* state) { 	B2G_PREFLIGHT_V(bashPrgEncrStart, state);
+prg_commit((bash_prg_st*)state, PRG_TEXT); }
 void bashPrgEncrStep(void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(bashPrgEncrStep, buf, count, state);
 	prg_step((bash_prg_st*)state, (octet*)buf, count, 2, "bashPrgEncrStep");
 }
 void bashPrgEncr(void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(bashPrgEncr, buf, count, state);
 	bashPrgEncrStart(state);
 	bashPrgEncrStep(buf, count, state);
 }
-void bashPrgDecrStart(void* state) { prg_commit((bash_prg_st*)state, PRG_TEXT); }
+void bashPrgDecrStart(void* state) { 	B2G_PREFLIGHT_V(bashPrgDecrStart, state);
+prg_commit((bash_prg_st*)state, PRG_TEXT); }
 void bashPrgDecrStep(void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(bashPrgDecrStep, buf, count, state);
 	prg_step((bash_prg_st*)state, (octet*)buf, count, 3, "bashPrgDecrStep");
 }
 void bashPrgDecr(void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(bashPrgDecr, buf, count, state);
 	bashPrgDecrStart(state);
 	bashPrgDecrStep(buf, count, state);
 }
 void bashPrgRatchet(void* state)   /* bash_prg.c:374-385 */
 {
+	B2G_PREFLIGHT_V(bashPrgRatchet, state);
 	bash_prg_st* st = (bash_prg_st*)state;
 	size_t i;
 	memcpy(st->t, st->s, 192);

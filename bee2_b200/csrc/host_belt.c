@@ -76,38 +76,44 @@ done:
 
 void beltBlockEncr(octet block[16], const u32 key[8])
 {
-	err_t code = blocks_small(block, 1, key, 0);
-	if (code) b2g_die("beltBlockEncr", code);
+	err_t code;
+	B2G_SMALL_V(16, beltBlockEncr, block, key);
+	if ((code = blocks_small(block, 1, key, 0))) B2G_FAIL_V(code, beltBlockEncr, block, key);
 }
 void beltBlockEncr2(u32 block[4], const u32 key[8])
 {
-	err_t code = blocks_small(block, 1, key, 0);
-	if (code) b2g_die("beltBlockEncr2", code);
+	err_t code;
+	B2G_SMALL_V(16, beltBlockEncr2, block, key);
+	if ((code = blocks_small(block, 1, key, 0))) B2G_FAIL_V(code, beltBlockEncr2, block, key);
 }
 void beltBlockEncr3(u32* a, u32* b, u32* c, u32* d, const u32 key[8])
 {
 	u32 t[4];
 	err_t code;
+	B2G_SMALL_V(16, beltBlockEncr3, a, b, c, d, key);
 	t[0] = *a, t[1] = *b, t[2] = *c, t[3] = *d;
-	if ((code = blocks_small(t, 1, key, 0))) b2g_die("beltBlockEncr3", code);
+	if ((code = blocks_small(t, 1, key, 0))) B2G_FAIL_V(code, beltBlockEncr3, a, b, c, d, key);
 	*a = t[0], *b = t[1], *c = t[2], *d = t[3];
 }
 void beltBlockDecr(octet block[16], const u32 key[8])
 {
-	err_t code = blocks_small(block, 1, key, 1);
-	if (code) b2g_die("beltBlockDecr", code);
+	err_t code;
+	B2G_SMALL_V(16, beltBlockDecr, block, key);
+	if ((code = blocks_small(block, 1, key, 1))) B2G_FAIL_V(code, beltBlockDecr, block, key);
 }
 void beltBlockDecr2(u32 block[4], const u32 key[8])
 {
-	err_t code = blocks_small(block, 1, key, 1);
-	if (code) b2g_die("beltBlockDecr2", code);
+	err_t code;
+	B2G_SMALL_V(16, beltBlockDecr2, block, key);
+	if ((code = blocks_small(block, 1, key, 1))) B2G_FAIL_V(code, beltBlockDecr2, block, key);
 }
 void beltBlockDecr3(u32* a, u32* b, u32* c, u32* d, const u32 key[8])
 {
 	u32 t[4];
 	err_t code;
+	B2G_SMALL_V(16, beltBlockDecr3, a, b, c, d, key);
 	t[0] = *a, t[1] = *b, t[2] = *c, t[3] = *d;
-	if ((code = blocks_small(t, 1, key, 1))) b2g_die("beltBlockDecr3", code);
+	if ((code = blocks_small(t, 1, key, 1))) B2G_FAIL_V(code, beltBlockDecr3, a, b, c, d, key);
 	*a = t[0], *b = t[1], *c = t[2], *d = t[3];
 }
 
@@ -170,11 +176,13 @@ static err_t ecb_step(octet* buf, size_t count, const u32 key[8], int decrypt)
 
 void beltECBStepE(void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(beltECBStepE, buf, count, state);
 	err_t code = ecb_step((octet*)buf, count, ((belt_ecb_st*)state)->key, 0);
 	if (code) b2g_die("beltECBStepE", code);
 }
 void beltECBStepD(void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(beltECBStepD, buf, count, state);
 	err_t code = ecb_step((octet*)buf, count, ((belt_ecb_st*)state)->key, 1);
 	if (code) b2g_die("beltECBStepD", code);
 }
@@ -190,10 +198,12 @@ static err_t ecb_oneshot(void* dest, const void* src, size_t count, const octet 
 }
 err_t beltECBEncr(void* dest, const void* src, size_t count, const octet key[], size_t len)
 {
+	B2G_SMALL_R(count, beltECBEncr, dest, src, count, key, len);
 	return ecb_oneshot(dest, src, count, key, len, 0);
 }
 err_t beltECBDecr(void* dest, const void* src, size_t count, const octet key[], size_t len)
 {
+	B2G_SMALL_R(count, beltECBDecr, dest, src, count, key, len);
 	return ecb_oneshot(dest, src, count, key, len, 1);
 }
 
@@ -263,6 +273,7 @@ static void ctr_add(u32 ctr[4], u64 n)
 
 void beltCTRStart(void* state, const octet key[], size_t len, const octet iv[16])
 {
+	B2G_PREFLIGHT_V(beltCTRStart, state, key, len, iv);
 	belt_ctr_st* st = (belt_ctr_st*)state;
 	err_t code;
 	beltKeyExpand2(st->key, key, len);
@@ -342,6 +353,7 @@ static err_t ctr_run(octet* dest, const octet* src, size_t count, const u32 key[
 
 void beltCTRStepE(void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(beltCTRStepE, buf, count, state);
 	belt_ctr_st* st = (belt_ctr_st*)state;
 	octet* p = (octet*)buf;
 	octet last[16];
@@ -376,11 +388,13 @@ err_t beltCTR(void* dest, const void* src, size_t count, const octet key[], size
 	err_t code;
 	if (!key_len_ok(len) || (count && (!src || !dest)) || !key || !iv)
 		return ERR_BAD_INPUT;
+	B2G_SMALL_R(count, beltCTR, dest, src, count, key, len, iv);
 	beltKeyExpand2(st.key, key, len);
 	memcpy(st.ctr, iv, 16);
-	if ((code = blocks_small(st.ctr, 1, st.key, 0)))
-		return code;
-	return ctr_run((octet*)dest, (const octet*)src, count, st.key, st.ctr, 0);
+	if (!(code = blocks_small(st.ctr, 1, st.key, 0)))
+		code = ctr_run((octet*)dest, (const octet*)src, count, st.key, st.ctr, 0);
+	b2g_wipe(&st, sizeof st);
+	return code;
 }
 
 err_t beltCTRKeystream(void* dest, size_t count, const octet key[], size_t len, const octet iv[16])
@@ -444,6 +458,7 @@ err_t beltHash(octet hash[32], const void* src, size_t count)
 {
 	if ((count && !src) || !hash)
 		return ERR_BAD_INPUT;
+	B2G_SMALL_R(count, beltHash, hash, src, count);
 	return beltHashBatch(hash, src, count, count, 1);
 }
 
@@ -508,6 +523,7 @@ done:
 
 void beltHashStepH(const void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(beltHashStepH, buf, count, state);
 	belt_hash_st* st = (belt_hash_st*)state;
 	const octet* p = (const octet*)buf;
 	const octet* head = 0;
@@ -562,27 +578,31 @@ static void hash_step_g(belt_hash_st* st, const char* who)
 
 void beltHashStepG(octet hash[32], void* state)
 {
+	B2G_PREFLIGHT_V(beltHashStepG, hash, state);
 	belt_hash_st* st = (belt_hash_st*)state;
 	hash_step_g(st, "beltHashStepG");
 	memcpy(hash, st->h1, 32);
 }
 void beltHashStepG2(octet hash[], size_t hash_len, void* state)
 {
+	B2G_PREFLIGHT_V(beltHashStepG2, hash, hash_len, state);
 	belt_hash_st* st = (belt_hash_st*)state;
 	hash_step_g(st, "beltHashStepG2");
 	memcpy(hash, st->h1, hash_len < 32 ? hash_len : 32);
 }
 bool_t beltHashStepV(const octet hash[32], void* state)
 {
+	B2G_PREFLIGHT_R(beltHashStepV, hash, state);
 	belt_hash_st* st = (belt_hash_st*)state;
 	hash_step_g(st, "beltHashStepV");
-	return memcmp(hash, st->h1, 32) == 0;
+	return b2g_ct_eq(hash, st->h1, 32);
 }
 bool_t beltHashStepV2(const octet hash[], size_t hash_len, void* state)
 {
+	B2G_PREFLIGHT_R(beltHashStepV2, hash, hash_len, state);
 	belt_hash_st* st = (belt_hash_st*)state;
 	hash_step_g(st, "beltHashStepV2");
-	return memcmp(hash, st->h1, hash_len < 32 ? hash_len : 32) == 0;
+	return b2g_ct_eq(hash, st->h1, hash_len < 32 ? hash_len : 32);
 }
 
 /* ---------------------------------------------------------------- belt-DWP (belt_dwp.c:250-330) */
@@ -665,7 +685,7 @@ static err_t dwp_run(void* dest, octet mac_out[8], const void* src1, size_t coun
 			goto done;
 		CU(cudaMemcpyAsync(mac, d_small, 8, cudaMemcpyDeviceToHost, sl->stream), "D2H(dwp mac)");
 		CU(cudaStreamSynchronize(sl->stream), "sync(dwp)");
-		if (memcmp(mac, expect_mac, 8) != 0)
+		if (!b2g_ct_eq(mac, expect_mac, 8))
 		{
 			code = ERR_BAD_MAC;
 			goto done;
@@ -835,6 +855,7 @@ size_t beltDWP_keep(void) { return sizeof(belt_dwp_st); }
 
 void beltDWPStart(void* state, const octet key[], size_t len, const octet iv[16])
 {
+	B2G_PREFLIGHT_V(beltDWPStart, state, key, len, iv);
 	belt_dwp_st* st = (belt_dwp_st*)state;
 	err_t code;
 	beltCTRStart(st->ctr, key, len, iv);
@@ -846,27 +867,33 @@ void beltDWPStart(void* state, const octet key[], size_t len, const octet iv[16]
 	memset(st->len, 0, sizeof st->len);
 	st->filled = 0;
 }
-void beltDWPStepE(void* buf, size_t count, void* state) { beltCTRStepE(buf, count, state); }
-void beltDWPStepD(void* buf, size_t count, void* state) { beltCTRStepE(buf, count, state); }
+void beltDWPStepE(void* buf, size_t count, void* state) { 	B2G_PREFLIGHT_V(beltDWPStepE, buf, count, state);
+beltCTRStepE(buf, count, state); }
+void beltDWPStepD(void* buf, size_t count, void* state) { 	B2G_PREFLIGHT_V(beltDWPStepD, buf, count, state);
+beltCTRStepE(buf, count, state); }
 void beltDWPStepI(const void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(beltDWPStepI, buf, count, state);
 	aead_step_i(dwp_view((belt_dwp_st*)state), buf, count, "beltDWPStepI");
 }
 void beltDWPStepA(const void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(beltDWPStepA, buf, count, state);
 	aead_step_a(dwp_view((belt_dwp_st*)state), buf, count, "beltDWPStepA");
 }
 void beltDWPStepG(octet mac[8], void* state)
 {
+	B2G_PREFLIGHT_V(beltDWPStepG, mac, state);
 	belt_dwp_st* st = (belt_dwp_st*)state;
 	aead_step_g(dwp_view(st), "beltDWPStepG");
 	memcpy(mac, st->t1, 8);
 }
 bool_t beltDWPStepV(const octet mac[8], void* state)
 {
+	B2G_PREFLIGHT_R(beltDWPStepV, mac, state);
 	belt_dwp_st* st = (belt_dwp_st*)state;
 	aead_step_g(dwp_view(st), "beltDWPStepV");
-	return memcmp(mac, st->t1, 8) == 0;
+	return b2g_ct_eq(mac, st->t1, 8);
 }
 
 /* ---- belt-CHE: the counter is the LFSR s <- s x ^ 1 over GF(2^128) (belt_che.c:86-88, belt_lcl.c:99-108) */
@@ -918,6 +945,7 @@ size_t beltCHE_keep(void) { return sizeof(belt_che_st); }
 
 void beltCHEStart(void* state, const octet key[], size_t len, const octet iv[16])
 {
+	B2G_PREFLIGHT_V(beltCHEStart, state, key, len, iv);
 	belt_che_st* st = (belt_che_st*)state;
 	err_t code;
 	beltKeyExpand2(st->key, key, len);
@@ -934,6 +962,7 @@ void beltCHEStart(void* state, const octet key[], size_t len, const octet iv[16]
 
 void beltCHEStepE(void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(beltCHEStepE, buf, count, state);
 	belt_che_st* st = (belt_che_st*)state;
 	octet* p = (octet*)buf;
 	b2g_slot* sl;
@@ -976,26 +1005,31 @@ done:
 	if (rem)
 		st->reserved = 16 - rem;   /* block1[rem..16) = unused keystream of the last block (its data part was 0) */
 }
-void beltCHEStepD(void* buf, size_t count, void* state) { beltCHEStepE(buf, count, state); }
+void beltCHEStepD(void* buf, size_t count, void* state) { 	B2G_PREFLIGHT_V(beltCHEStepD, buf, count, state);
+beltCHEStepE(buf, count, state); }
 void beltCHEStepI(const void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(beltCHEStepI, buf, count, state);
 	aead_step_i(che_view((belt_che_st*)state), buf, count, "beltCHEStepI");
 }
 void beltCHEStepA(const void* buf, size_t count, void* state)
 {
+	B2G_PREFLIGHT_V(beltCHEStepA, buf, count, state);
 	aead_step_a(che_view((belt_che_st*)state), buf, count, "beltCHEStepA");
 }
 void beltCHEStepG(octet mac[8], void* state)
 {
+	B2G_PREFLIGHT_V(beltCHEStepG, mac, state);
 	belt_che_st* st = (belt_che_st*)state;
 	aead_step_g(che_view(st), "beltCHEStepG");
 	memcpy(mac, st->t1, 8);
 }
 bool_t beltCHEStepV(const octet mac[8], void* state)
 {
+	B2G_PREFLIGHT_R(beltCHEStepV, mac, state);
 	belt_che_st* st = (belt_che_st*)state;
 	aead_step_g(che_view(st), "beltCHEStepV");
-	return memcmp(mac, st->t1, 8) == 0;
+	return b2g_ct_eq(mac, st->t1, 8);
 }
 
 err_t beltDWPWrap(void* dest, octet mac[8], const void* src1, size_t count1, const void* src2,
@@ -1003,6 +1037,7 @@ err_t beltDWPWrap(void* dest, octet mac[8], const void* src1, size_t count1, con
 {
 	if (!mac)
 		return ERR_BAD_INPUT;
+	B2G_SMALL_R(count1 + count2, beltDWPWrap, dest, mac, src1, count1, src2, count2, key, len, iv);
 	return dwp_run(dest, mac, src1, count1, src2, count2, key, len, iv, 0, 0);
 }
 
@@ -1012,6 +1047,7 @@ err_t beltDWPUnwrap(void* dest, const void* src1, size_t count1, const void* src
 	octet unused[8];
 	if (!mac)
 		return ERR_BAD_INPUT;
+	B2G_SMALL_R(count1 + count2, beltDWPUnwrap, dest, src1, count1, src2, count2, mac, key, len, iv);
 	return dwp_run(dest, unused, src1, count1, src2, count2, key, len, iv, mac, 0);
 }
 
@@ -1020,6 +1056,7 @@ err_t beltCHEWrap(void* dest, octet mac[8], const void* src1, size_t count1, con
 {
 	if (!mac)
 		return ERR_BAD_INPUT;
+	B2G_SMALL_R(count1 + count2, beltCHEWrap, dest, mac, src1, count1, src2, count2, key, len, iv);
 	return dwp_run(dest, mac, src1, count1, src2, count2, key, len, iv, 0, 1);
 }
 
@@ -1029,5 +1066,6 @@ err_t beltCHEUnwrap(void* dest, const void* src1, size_t count1, const void* src
 	octet unused[8];
 	if (!mac)
 		return ERR_BAD_INPUT;
+	B2G_SMALL_R(count1 + count2, beltCHEUnwrap, dest, src1, count1, src2, count2, mac, key, len, iv);
 	return dwp_run(dest, unused, src1, count1, src2, count2, key, len, iv, mac, 1);
 }

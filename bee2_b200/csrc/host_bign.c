@@ -139,6 +139,13 @@ static err_t params_check(const bign_params* params)
 	return ERR_OK;
 }
 
+/* Overlay routing of the single-item drop-ins: a parameter block that is structurally valid but not one
+   of the three standard curves (the reference accepts any, bign_params.c:197-280), and — when the
+   caller asked for it (b2g_set_cpu_below) — every single-item call, go to the stock libbee2 behind us. */
+#define BIGN_ROUTE(name, ...) do { \
+	if (params && (params_check(params) == ERR_NOT_IMPLEMENTED || b2g_route_small(1))) \
+		B2G_STOCK_R(name, __VA_ARGS__); } while (0)
+
 /* DER OBJECT IDENTIFIER syntax as accepted by oidFromDER(0, der, len) != SIZE_MAX
    (oid.c:94-101, der.c:114-151, :193-232, :921-975) */
 static int oid_der_valid(const octet* der, size_t count)
@@ -200,9 +207,11 @@ static size_t verify_chunk(void)
 		if (v >= 128)
 			return (size_t)v;
 	}
-	/* measured on B200 (2^18 items, pinned buffers): 2^16 -> 35 M/s, 2^17 -> 39 M/s, 2^18 -> 41.5 M/s:
-	   the 144 B/item upload is short next to the kernel, so few large stages win */
-	return (size_t)1 << 18;
+	/* 2^16 items per stage: the upload of stage i+1 and the status download of stage i-1 run under the
+	   kernel of stage i. (Round 1 used 2^18 — no overlap at the config size — because smaller grids of
+	   256-thread CTAs lost more to wave quantisation, 35 M/s at 2^16; the launcher now sizes the CTAs of a
+	   small grid so that every SM gets the same load, bign.cu bign_threads.) */
+	return (size_t)1 << 16;
 }
 
 static err_t verify_batch_1(err_t* status, const bign_params* params, const octet oid_der[], size_t oid_len,
@@ -286,6 +295,7 @@ err_t bignVerifyBatch(err_t* status, const bign_params* params, const octet oid_
 err_t bignVerify(const bign_params* params, const octet oid_der[], size_t oid_len,
 	const octet hash[], const octet sig[], const octet pubkey[])
 {
+	BIGN_ROUTE(bignVerify, params, oid_der, oid_len, hash, sig, pubkey);
 	err_t st = ERR_BAD_SIG, code;
 	/* order of checks: params (bign_sign.c:355-356), buffers, OID (:286-290) */
 	if ((code = params_check(params)))
@@ -293,7 +303,11 @@ err_t bignVerify(const bign_params* params, const octet oid_der[], size_t oid_le
 	if (!hash || !sig || !pubkey)
 		return ERR_BAD_INPUT;
 	if ((code = bignVerifyBatch(&st, params, oid_der, oid_len, hash, sig, pubkey, 1)))
+	{
+		if (code == ERR_NOT_IMPLEMENTED)   /* an OID longer than 64 octets */
+			B2G_STOCK_R(bignVerify, params, oid_der, oid_len, hash, sig, pubkey);
 		return code;
+	}
 	return st;
 }
 
@@ -381,13 +395,18 @@ err_t bignSign2Batch(err_t* status, octet* sigs, const bign_params* params, cons
 err_t bignSign2(octet sig[], const bign_params* params, const octet oid_der[], size_t oid_len,
 	const octet hash[], const octet privkey[], const void* t, size_t t_len)
 {
+	BIGN_ROUTE(bignSign2, sig, params, oid_der, oid_len, hash, privkey, t, t_len);
 	err_t st = ERR_BAD_INPUT, code;
 	if ((code = params_check(params)))
 		return code;
 	if (!hash || !privkey || !sig)
 		return ERR_BAD_INPUT;
 	if ((code = sign2_batch(&st, sig, params, oid_der, oid_len, hash, privkey, 1, t, t ? t_len : 0)))
+	{
+		if (code == ERR_NOT_IMPLEMENTED)   /* OID or t longer than 64 octets (bign_sign.c:198-206 takes any) */
+			B2G_STOCK_R(bignSign2, sig, params, oid_der, oid_len, hash, privkey, t, t_len);
 		return code;
+	}
 	return st;
 }
 
@@ -455,6 +474,7 @@ err_t bignPubkeyCalcBatch(err_t* status, octet* pubkeys, const bign_params* para
 
 err_t bignPubkeyCalc(octet pubkey[], const bign_params* params, const octet privkey[])
 {
+	BIGN_ROUTE(bignPubkeyCalc, pubkey, params, privkey);
 	err_t st = ERR_BAD_INPUT, code;
 	octet out[128];
 	if ((code = params_check(params)))
@@ -608,6 +628,7 @@ err_t bignKeypairGenBatch(octet* privkeys, octet* pubkeys, const bign_params* pa
 
 err_t bignKeypairGen(octet privkey[], octet pubkey[], const bign_params* params, gen_i rng, void* rng_state)
 {
+	BIGN_ROUTE(bignKeypairGen, privkey, pubkey, params, rng, rng_state);
 	err_t code;
 	if ((code = params_check(params)))
 		return code;
@@ -642,6 +663,7 @@ err_t bignKeypairValBatch(err_t* status, const bign_params* params, const octet*
 
 err_t bignKeypairVal(const bign_params* params, const octet privkey[], const octet pubkey[])
 {
+	BIGN_ROUTE(bignKeypairVal, params, privkey, pubkey);
 	err_t st = ERR_BAD_INPUT, code;
 	if ((code = params_check(params)))
 		return code;
@@ -685,6 +707,7 @@ done:
 
 err_t bignPubkeyVal(const bign_params* params, const octet pubkey[])
 {
+	BIGN_ROUTE(bignPubkeyVal, params, pubkey);
 	err_t st = ERR_BAD_INPUT, code;
 	if ((code = params_check(params)))
 		return code;
@@ -748,6 +771,7 @@ done:
 
 err_t bignDH(octet key[], const bign_params* params, const octet privkey[], const octet pubkey[], size_t key_len)
 {
+	BIGN_ROUTE(bignDH, key, params, privkey, pubkey, key_len);
 	err_t st = ERR_BAD_INPUT, code;
 	if ((code = params_check(params)))
 		return code;
@@ -843,13 +867,16 @@ done:
 err_t bignSign(octet sig[], const bign_params* params, const octet oid_der[], size_t oid_len,
 	const octet hash[], const octet privkey[], gen_i rng, void* rng_state)
 {
+	BIGN_ROUTE(bignSign, sig, params, oid_der, oid_len, hash, privkey, rng, rng_state);
 	err_t st = ERR_BAD_INPUT, code;
+	if (oid_len > 64)                      /* not staged into kernel arguments: before the generator is touched */
+		B2G_STOCK_R(bignSign, sig, params, oid_der, oid_len, hash, privkey, rng, rng_state);
 	if ((code = params_check(params)))
 		return code;
 	if (!hash || !privkey || !sig)
 		return ERR_BAD_INPUT;
 	if ((code = bignSignBatch(&st, sig, params, oid_der, oid_len, hash, privkey, rng, rng_state, 1)))
-		return code;
+		return code;   /* (a too-long OID is caught before the generator is touched: see bignSignBatch) */
 	return st;
 }
 
@@ -933,7 +960,8 @@ static size_t ec_std_level(const void* ec_)
 
 size_t ecMulA_deep(size_t n, size_t ec_d, size_t ec_deep, size_t m)
 {
-	(void)n, (void)ec_d, (void)ec_deep, (void)m;
+	/* overlay mode: a call may be forwarded to stock libbee2, whose ecMulA works in the caller's stack */
+	B2G_STOCK_R(ecMulA_deep, n, ec_d, ec_deep, m);
 	return 0;   /* no host scratch: the caller's `stack` is not used */
 }
 
@@ -944,33 +972,60 @@ bool_t ecMulA(u64 b[], const u64 a[], const void* ec, const u64 d[], size_t m, v
 	octet out[128];
 	int ok = 0;
 	err_t code;
-	(void)stack;
+	/* a curve other than the three standard bign ones, or a scalar longer than the field (ec.c:497-525
+	   takes any ec_o and any m): stock libbee2 behind this library, else there is no path */
 	if (!l || !a || !b || !d || m == 0 || 8 * m > l / 4)
-		b2g_die("ecMulA (curve is not a standard bign curve, or m > n: no CPU path)", l ? ERR_BAD_INPUT : ERR_NOT_IMPLEMENTED);
+		B2G_FAIL_R(l ? ERR_BAD_INPUT : ERR_NOT_IMPLEMENTED, ecMulA, b, a, ec, d, m, stack);
+	B2G_SMALL_R(1, ecMulA, b, a, ec, d, m, stack);
 	if ((code = ecMulABatchL(l, out, &ok, (const octet*)a, (const octet*)d, 8 * m, 1)))
-		b2g_die("ecMulA", code);
+		B2G_FAIL_R(code, ecMulA, b, a, ec, d, m, stack);
 	if (ok)
 		memcpy(b, out, l / 2);
+	b2g_wipe(out, sizeof out);   /* the product may be a shared secret (bignDH, key transport) */
 	return ok ? 1 : 0;
 }
 
 /* b <- sum_{i<k} d_i a_i for the k (a_i, d_i, m_i) triples that follow k (ec.h:1176-1190, ec.c:1183-1273),
    FALSE iff the sum is O. The k products run as one batch of ecp_mul_kernel, a one-thread kernel adds
    them. Same curve recognition and limits as ecMulA (m_i <= n words, k <= 64). */
+/* the variadic call rebuilt for stock libbee2 (k <= 8 triples; the reference's own callers use 2..4) */
+static int addmul_stock(bool_t* ret, u64 b[], const void* ec, void* stack, size_t k, const u64* const a[],
+	const u64* const d[], const size_t m[])
+{
+	__typeof__(&ecAddMulA) f = B2G_STOCK_FN(ecAddMulA);
+	if (!f || k == 0 || k > 8)
+		return 0;
+	b2g_note_forward();
+#define T_(i) a[i], d[i], m[i]
+	switch (k)
+	{
+	case 1: *ret = f(b, ec, stack, k, T_(0)); break;
+	case 2: *ret = f(b, ec, stack, k, T_(0), T_(1)); break;
+	case 3: *ret = f(b, ec, stack, k, T_(0), T_(1), T_(2)); break;
+	case 4: *ret = f(b, ec, stack, k, T_(0), T_(1), T_(2), T_(3)); break;
+	case 5: *ret = f(b, ec, stack, k, T_(0), T_(1), T_(2), T_(3), T_(4)); break;
+	case 6: *ret = f(b, ec, stack, k, T_(0), T_(1), T_(2), T_(3), T_(4), T_(5)); break;
+	case 7: *ret = f(b, ec, stack, k, T_(0), T_(1), T_(2), T_(3), T_(4), T_(5), T_(6)); break;
+	default: *ret = f(b, ec, stack, k, T_(0), T_(1), T_(2), T_(3), T_(4), T_(5), T_(6), T_(7)); break;
+	}
+#undef T_
+	return 1;
+}
+
 bool_t ecAddMulA(u64 b[], const void* ec, void* stack, size_t k, ...)
 {
 	const size_t l = ec_std_level(ec);
 	const size_t no = l / 4;
 	octet pts[64 * 128], scal[64 * 64], out[128];
-	b2g_slot* sl;
+	const u64 *va[8], *vd[8];
+	size_t vm[8];
+	b2g_slot* sl = 0;
 	void *d_a, *d_d, *d_p, *d_ok, *d_out;
-	int ok = 0;
+	int ok = 0, foreign = !l || !b || k == 0 || k > 64;
+	bool_t ret = 0;
 	err_t code;
 	size_t i;
 	va_list ap;
-	(void)stack;
-	if (!l || !b || k == 0 || k > 64)
-		b2g_die("ecAddMulA (curve is not a standard bign curve, or k > 64: no CPU path)", l ? ERR_BAD_INPUT : ERR_NOT_IMPLEMENTED);
 	memset(scal, 0, sizeof scal);
 	va_start(ap, k);
 	for (i = 0; i < k; ++i)
@@ -978,17 +1033,32 @@ bool_t ecAddMulA(u64 b[], const void* ec, void* stack, size_t k, ...)
 		const u64* a = va_arg(ap, const u64*);
 		const u64* d = va_arg(ap, const u64*);
 		const size_t m = va_arg(ap, size_t);
+		if (i < 8)
+			va[i] = a, vd[i] = d, vm[i] = m;
 		if (!a || !d || 8 * m > no)
+			foreign = 1;
+		else if (!foreign && i < 64)
 		{
-			va_end(ap);
-			b2g_die("ecAddMulA (m > n)", ERR_BAD_INPUT);
+			memcpy(pts + 2 * no * i, a, 2 * no);
+			memcpy(scal + no * i, d, 8 * m);
 		}
-		memcpy(pts + 2 * no * i, a, 2 * no);
-		memcpy(scal + no * i, d, 8 * m);
 	}
 	va_end(ap);
-	if ((code = b2g_ensure_device()))
-		b2g_die("ecAddMulA", code);
+	/* another curve, a scalar longer than the field, more than 64 terms: stock libbee2, else no path */
+	if (foreign || b2g_route_small(1) || (code = b2g_ensure_device()))
+	{
+		if (addmul_stock(&ret, b, ec, stack, k, va, vd, vm))
+		{
+			b2g_wipe(scal, sizeof scal);
+			return ret;
+		}
+		if (!foreign && !b2g_ensure_device())
+			goto gpu;                  /* small-call routing asked for stock, but there is none */
+		b2g_wipe(scal, sizeof scal);
+		b2g_die("ecAddMulA (not a standard bign curve, m > n or k > 64, and no stock libbee2 behind)",
+			l ? ERR_BAD_INPUT : ERR_NOT_IMPLEMENTED);
+	}
+gpu:
 	b2g_lock();
 	sl = b2g_slot_get(0);
 	if ((code = stage_in(sl, 0, pts, 2 * no * k, &d_a)) || (code = stage_in(sl, 1, scal, no * k, &d_d)) ||
@@ -1007,10 +1077,15 @@ done:
 	if (code)
 		b2g_slot_wipe(sl);
 	b2g_unlock();
-	memset(scal, 0, sizeof scal);
+	b2g_wipe(scal, sizeof scal);
 	if (code)
+	{
+		if (addmul_stock(&ret, b, ec, stack, k, va, vd, vm))
+			return ret;
 		b2g_die("ecAddMulA", code);
+	}
 	if (ok)
 		memcpy(b, out, 2 * no);
+	b2g_wipe(out, sizeof out);
 	return ok ? 1 : 0;
 }

@@ -6,7 +6,15 @@
 One JSON line on stdout (rank 0). The headline (`metric`/`value`) is BASELINE.json configs[1]:
 belt-CTR, one key, 1 GiB of keystream per GPU per step. The other two parts of BASELINE.json's
 metric (bash-512 on 2^20 x 4 KiB messages, bign-curve256v1 verify on 2^18 signatures) are measured
-in the same run under `"paths"`, each with its own value / roofline / cpu_baseline / e2e.
+in the same run: in full under `"paths"`, and compactly (value, e2e, issue / HBM fraction, CPU
+baseline) under `config.also` and again as the LAST key `also` of the line. `--impl reference`
+times the same three paths and prints them in the same places.
+
+N > 1 additionally measures STRONG scaling of the fixed-size BASELINE configs (2^26 CTR blocks,
+2^20 messages, 2^18 signatures, 2^26 (key, block) pairs) sharded N ways, under `config.strong`:
+compute only, compute with the final gather fused into the kernel (each rank's kernel stores its
+outputs straight into rank 0's HBM over NVLink through a CUDA-IPC mapping), and compute followed by
+an NCCL gather; rank 0 checks that the gathered bytes equal its own single-GPU run of the whole batch.
 
 A step = one pass of the path over one batch. `value` is timed with CUDA events on the stream the
 kernels are launched on, inputs resident in HBM; `e2e` goes through the host-pointer C-ABI call
@@ -212,12 +220,15 @@ class CpuArm:
                 _, st, pubs = self.pubkey(priv)
                 _, st2, sigs = self.sign2(hashes, priv)
                 assert not st.any() and not st2.any()
+                bad = np.arange(0, n, 16)            # the GPU leg's corruption pattern
+                sigs[bad, bad % 48] ^= 1
                 state[key] = (hashes, sigs, pubs)
             hashes, sigs, pubs = state[key]
             dt, st = self.verify(hashes, sigs, pubs)
             state["last"] = (hashes, sigs, pubs)
-            assert not st.any()
-            units, desc = n, f"{n} valid signatures via " + ("bign128Verify" if not self.is_port else "orc_bignVerify128")
+            bad = np.arange(0, n, 16)
+            assert (st[bad] == 510).all() and int((st == 0).sum()) == n - len(bad), "cpu verify statuses off"
+            units, desc = n, f"{n} signatures (1/16 corrupted) via " + ("bign128Verify" if not self.is_port else "orc_bignVerify128")
         if dt <= 0:
             raise RuntimeError(f"cpu harness failed for {path}: {dt}")
         # the batch is capped at the config size: repeat it until the sample lasts about target_s
@@ -273,34 +284,65 @@ class CpuArm:
         return out
 
 
+def compact(r):
+    """One path's result cut down to what the driver-visible summary needs."""
+    out = {"value": r.get("value"), "unit": r.get("unit")}
+    if r.get("ms_per_step") is not None:
+        out["ms"] = round(r["ms_per_step"], 4)
+    if r.get("e2e"):
+        out["e2e"] = r["e2e"]["value"]
+    if r.get("issue_roofline"):
+        out["issue_frac"] = r["issue_roofline"].get("frac")
+        out["issue_bound"] = r["issue_roofline"].get("bound", "").split(" ")[0]
+    if r.get("roofline"):
+        out["hbm_frac"] = r["roofline"].get("frac")
+    if r.get("cpu_baseline"):
+        out["cpu"] = r["cpu_baseline"]["value"]
+        out["cpu_cores"] = r["cpu_baseline"]["cores"]
+    for k in ("impl", "sample"):
+        if r.get(k):
+            out[k] = r[k]
+    return {k: (round(v, 6) if isinstance(v, float) else v) for k, v in out.items()}
+
+
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU code on all host threads, same metric/config keys."""
+    """--impl reference: the reference's own CPU code (oracle/_ref: bashHash of the BASH_AVX512 build,
+    beltCTR, bign128Verify) on all host threads, same metric/config keys. Every path of --paths is
+    timed for `steps` bounded samples; the first one is the headline of the line."""
     if rank != 0:
         return
     arm = CpuArm()
-    path = args.paths[0]
-    cfg = CFG[path]
-    scale = 1e9 if cfg["unit"] == "GB/s" else 1.0
-    state = {}
-    arm.sample(path, 0, state)
-    per_step_s = max(0.5, min(3.0, 120.0 / max(1, args.steps + args.warmup)))
-    for _ in range(args.warmup):
-        arm.sample(path, per_step_s, state)
-    tot_t = tot_u = 0.0
-    desc = ""
-    for _ in range(args.steps):
-        dt, units, desc = arm.sample(path, per_step_s, state)
-        tot_t += dt
-        tot_u += units
-    val = tot_u / tot_t / scale
-    line = {"impl": "reference", "metric": cfg["metric"], "value": val, "unit": cfg["unit"], "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+    paths = args.paths
+    budget = 150.0 / max(1, len(paths) * (args.steps + args.warmup))
+    res = {}
+    for path in paths:
+        cfg = CFG[path]
+        scale = 1e9 if cfg["unit"] == "GB/s" else 1.0
+        state = {}
+        arm.sample(path, 0, state)
+        per_step_s = max(0.25, min(3.0, budget))
+        for _ in range(args.warmup):
+            arm.sample(path, per_step_s, state)
+        tot_t = tot_u = 0.0
+        desc = ""
+        for _ in range(args.steps):
+            dt, units, desc = arm.sample(path, per_step_s, state)
+            tot_t += dt
+            tot_u += units
+        res[path] = {"metric": cfg["metric"], "value": tot_u / tot_t / scale, "unit": cfg["unit"],
+                     "ms_per_step": 1e3 * tot_t / args.steps, "sample": desc, "impl": "reference"}
+    head = paths[0]
+    cfg, h = CFG[head], res[head]
+    also = {k: compact(v) for k, v in res.items() if k != head}
+    line = {"impl": "reference", "metric": cfg["metric"], "value": h["value"], "unit": cfg["unit"], "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": h["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
-            "config": {"workload": cfg["workload"], "reference_step": desc},
-            "cpu_baseline": {"value": val, "unit": cfg["unit"], "cores": arm.threads, "kind": arm.kind,
-                             "sample": f"{args.steps} steps: {desc}"},
-            "e2e": {"value": val, "unit": cfg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "config": {"workload": cfg["workload"], "reference_step": h["sample"], "also": also},
+            "cpu_baseline": {"value": h["value"], "unit": cfg["unit"], "cores": arm.threads, "kind": arm.kind,
+                             "sample": f"{args.steps} steps: {h['sample']}"},
+            "e2e": {"value": h["value"], "unit": cfg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "paths": {k: v for k, v in res.items() if k != head},
+            "also": {k: compact(v) for k, v in res.items()}}
     print(json.dumps(line), flush=True)
 
 
@@ -348,6 +390,46 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+# ---------------------------------------------------------------- host placement
+def numa_bind(index):
+    """Pin this rank to the CPUs of its GPU's NUMA node BEFORE any pinned buffer is allocated, so the
+    staging memory of the e2e legs is node-local (first touch). Returns what was found / done."""
+    info = {"gpu_numa_node": None, "bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                       # 00000000:1b:00.0 -> 0000:1b:00.0
+        base = f"/sys/bus/pci/devices/{bus}"
+        with open(base + "/numa_node") as f:
+            node = int(f.read().strip())
+        info["gpu_numa_node"] = node
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]
+        info["host_numa_nodes"] = len(nodes)
+        if node >= 0 and len(nodes) > 1:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpus = set()
+                for part in f.read().strip().split(","):
+                    a, _, b_ = part.partition("-")
+                    cpus.update(range(int(a), int(b_ or a) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["bound"], info["cpus"] = True, len(cpus)
+    except Exception as e:          # no sysfs / nvml in this container: nothing to bind
+        info["note"] = type(e).__name__
+    return info
+
+
+class DevBuf:
+    """A raw device pointer as a torch uint8 tensor (``torch.as_tensor(DevBuf(p, n), device=...)``)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
 # ---------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -355,11 +437,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--paths", default="belt_ctr,bash512,bign_verify,belt_ecb,belt_dwp,bign_sign2",
+    ap.add_argument("--paths", default=None,
                     help="comma list; the first one is the headline metric of the JSON line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling section (N > 1)")
     args = ap.parse_args()
+    if args.paths is None:
+        args.paths = ("belt_ctr,bash512,bign_verify" if args.impl == "reference"
+                      else "belt_ctr,bash512,bign_verify,belt_ecb,belt_dwp,bign_sign2")
     args.paths = [p for p in args.paths.split(",") if p]
     for p in args.paths:
         if p not in CFG:
@@ -397,6 +483,7 @@ def main():
     peak, peak_src = hbm_peak()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    numa = numa_bind(local_rank)
 
     def barrier():
         if world > 1:
@@ -459,8 +546,32 @@ def main():
         return {"collective": "ncclAllGather", "bytes_per_rank": int(flat.numel()), "ms": sec * 1e3,
                 "GB/s_per_rank_received": (world - 1) * flat.numel() / sec / 1e9, "own_slice_intact": ok}
 
+    def copy_roof():
+        """The e2e roof of this box: every rank moves 1 GiB between pinned host memory and its GPU at the
+        same time with plain cudaMemcpyAsync (D2H, then H2D); aggregate GB/s over the max rank time."""
+        n = 1 << 30
+        hbuf = torch.empty(n, dtype=torch.uint8).pin_memory()
+        dbuf = torch.empty(n, dtype=torch.uint8, device=dev)
+        L = b.lib()
+        out = {}
+        for name, to_dev in (("d2h", 0), ("h2d", 1)):
+            dst, src = (dbuf.data_ptr(), hbuf.data_ptr()) if to_dev else (hbuf.data_ptr(), dbuf.data_ptr())
+            best = None
+            for it in range(4):
+                barrier()
+                t0 = time.perf_counter()
+                assert L.b2g_memcpy_async(dst, src, n, to_dev, stream) == 0
+                torch.cuda.synchronize()
+                dt = shard.max_over_ranks(time.perf_counter() - t0, device=dev)
+                if it and (best is None or dt < best):
+                    best = dt
+            out[name] = world * n / best / 1e9
+        del hbuf, dbuf
+        return out
+
     results = {}
     issue = {}
+    roof = None if args.no_e2e else copy_roof()
     if rank == 0:
         for name, kind in (("lop3", 0), ("shf", 1), ("prmt", 2), ("imad", 4), ("imad_wide", 5), ("lds32", 6), ("lop3+imad_wide", 7),
                            ("lop3+imad", 8), ("lop3+ffma", 9), ("imad_hi", 10), ("lop3+lds32", 11), ("ffma", 12), ("dfma", 13), ("dfma+imad_wide", 14),
@@ -685,6 +796,138 @@ def main():
                          "note": "integer-issue bound, not HBM bound (SURVEY §8d): see issue_roofline"}
         results[path] = r
 
+
+    # ---------------------------------------------------------------- strong scaling (N > 1)
+    def strong_section():
+        """BASELINE configs 2-5 at their FIXED size, sharded `world` ways by contiguous unit ranges.
+        Three timings per path (CUDA events around each rank's work, max over ranks):
+          compute      - every rank's kernel on its slice, outputs stay local;
+          fused_gather - the same kernel stores its outputs straight into rank 0's HBM over NVLink
+                         (CUDA-IPC mapping of rank 0's buffer): compute and the final gather are ONE kernel;
+          nccl_gather  - the kernel, then one ncclAllGather of the outputs.
+        Rank 0 then runs the WHOLE batch alone and compares the gathered bytes with it."""
+        L = b.lib()
+        steps, warm = max(3, min(args.steps, 10)), 3
+        out = {}
+
+        def one(path, total, out_bytes, launch, flush, note):
+            lo, hi = shard.shard_range(total, rank, world)
+            n = hi - lo
+            nb_total = total * out_bytes
+            gptr = L.b2g_dev_alloc(nb_total) if rank == 0 else None
+            assert rank != 0 or gptr, "b2g_dev_alloc failed"
+            handle = shard.broadcast_bytes(b.b2g_ipc_export(gptr) if rank == 0 else None, 64, device=dev)
+            ipc_err = None
+            try:
+                peer = gptr if rank == 0 else b.b2g_ipc_open(handle)
+            except Exception as e:           # no CUDA IPC in this container: report it, keep the other two variants
+                peer, ipc_err = None, str(e)
+            okf = torch.tensor([0 if peer is None else 1], dtype=torch.int32, device=dev)
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            fused_ok = bool(okf.item())
+            local = torch.zeros(n * out_bytes, dtype=torch.uint8, device=dev)
+            gathered = torch.zeros(nb_total, dtype=torch.uint8, device=dev)
+            t_c, _ = timed(lambda: launch(local.data_ptr(), lo, n), steps, warm, flush)
+            t_f = None
+            if fused_ok:
+                t_f, _ = timed(lambda: launch(peer + lo * out_bytes, lo, n), steps, warm, flush)
+
+            def with_nccl():
+                launch(local.data_ptr(), lo, n)
+                dist.all_gather_into_tensor(gathered, local)
+            t_n, _ = timed(with_nccl, steps, warm, flush)
+            # the gather alone (device time, max over ranks)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_gather_into_tensor(gathered, local)
+            e1.record()
+            torch.cuda.synchronize()
+            t_g = shard.max_over_ranks(e0.elapsed_time(e1) * 1e-3, device=dev)
+            ident = None
+            if rank == 0:
+                full = torch.zeros(nb_total, dtype=torch.uint8, device=dev)
+                launch(full.data_ptr(), 0, total)
+                torch.cuda.synchronize()
+                fused = torch.as_tensor(DevBuf(gptr, nb_total), device=dev)
+                ident = {"fused_gather": bool(torch.equal(fused, full)) if fused_ok else None, "nccl_gather": bool(torch.equal(gathered, full)),
+                         "sha_free_checksum": int(full[:: max(1, nb_total >> 16)].to(torch.int64).sum().item())}
+                del full, fused
+            barrier()
+            if rank != 0 and peer is not None:
+                b.b2g_ipc_close(peer)
+            barrier()
+            if rank == 0:
+                L.b2g_dev_free(gptr)
+            cfg = CFG[path]
+            scale = (cfg["unit_bytes"] / 1e9) if cfg["unit"] == "GB/s" else 1.0
+            val = lambda t: (total * steps / t * scale) if t else None            # noqa: E731
+            one_gpu = results[path]["value"] / world if path in results else None
+            r = {"units_total": total, "units_per_gpu": n, "unit": cfg["unit"], "compute": val(t_c), "fused_gather": val(t_f),
+                 "nccl_gather": val(t_n), "ms": {"compute": 1e3 * t_c / steps, "fused_gather": 1e3 * t_f / steps if t_f else None,
+                                                 "nccl_gather": 1e3 * t_n / steps, "nccl_allgather_alone": 1e3 * t_g},
+                 "gathered_bytes": nb_total, "identical_to_single_gpu": ident, "one_gpu": one_gpu, "limiter": note}
+            if one_gpu:
+                r["vs_one_gpu"] = {k: (r[k] / one_gpu if r[k] else None) for k in ("compute", "fused_gather", "nccl_gather")}
+            if ipc_err:
+                r["ipc_error"] = ipc_err
+            out[path] = r
+            del local, gathered
+
+        if "belt_ctr" in args.paths:
+            secret = np.random.default_rng(10).integers(0, 256, 48, dtype=np.uint8).tobytes() if rank == 0 else None
+            kiv = shard.broadcast_bytes(secret, 48, device=dev)
+            st = b.BeltCTR(kiv[:32], kiv[32:])
+            key, ctr = st.key_words, st.ctr_words
+            one("belt_ctr", 1 << 26, 16,
+                lambda dst, first, n: b.beltCTR_dev(dst, 0, n * 16, key, ctr, first, stream), False,
+                "the gather: rank 0 can take 1 GiB no faster than one GPU's NVLink ingress, about as fast as one GPU "
+                "computes it (BASELINE config 2 is a 1-GPU config)")
+        if "bash512" in args.paths:
+            g = torch.Generator(device=dev).manual_seed(1)
+            msgs = torch.randint(0, 256, (1 << 20, 4096), dtype=torch.uint8, device=dev, generator=g)
+            one("bash512", 1 << 20, 64,
+                lambda dst, first, n: b.bashHashBatch_dev(dst, 256, msgs.data_ptr() + first * 4096, 4096, 4096, n, stream),
+                False, "none expected: 2^20/N messages still fill every SM; digests are 1/64 of the input")
+            del msgs
+        if "bign_verify" in args.paths:
+            units = 1 << 18
+            rng = np.random.default_rng(2)
+            priv = rng.integers(0, 256, (units, 32), dtype=np.uint8)
+            priv[:, 31] &= 0x7F
+            hashes = rng.integers(0, 256, (units, 32), dtype=np.uint8)
+            params = b.bignParamsStd()
+            st1, pubs = b.bignPubkeyCalcBatch(params, priv)
+            st2, sigs = b.bignSign2Batch(params, OID, hashes, priv)
+            assert not st1.any() and not st2.any()
+            bad = np.arange(0, units, 16)
+            sigs[bad, bad % 48] ^= 1
+            d_h, d_s, d_p = (torch.from_numpy(x).to(dev) for x in (hashes, sigs, pubs))
+            one("bign_verify", units, 4,
+                lambda dst, first, n: b.bignVerifyBatch_dev(dst, OID, d_h.data_ptr() + 32 * first, d_s.data_ptr() + 48 * first,
+                                                            d_p.data_ptr() + 64 * first, n, stream),
+                True, "wave quantisation: 2^18/N signatures = (1024/N) CTAs of 256 threads on 148 SMs x 3 CTA slots "
+                      "(N=8: 128 CTAs, under one third of a wave, two warps per scheduler)")
+            del d_h, d_s, d_p
+        if "belt_ecb" in args.paths:
+            units = 1 << 26
+            g = torch.Generator(device=dev).manual_seed(3)
+            keys = torch.randint(0, 256, (units, 32), dtype=torch.uint8, device=dev, generator=g)
+            blocks = torch.randint(0, 256, (units, 16), dtype=torch.uint8, device=dev, generator=g)
+            one("belt_ecb", units, 16,
+                lambda dst, first, n: _chk(L.b2g_beltECBEncrBatch2_dev(dst, blocks.data_ptr() + 16 * first,
+                                                                      keys.data_ptr() + 32 * first, n, stream)),
+                False, "the gather of 1 GiB into one GPU (NVLink ingress), as for belt-CTR")
+            del keys, blocks
+        return out
+
+    def _chk(code):
+        assert code == 0, code
+
+    strong = None
+    if world > 1 and not args.no_strong:
+        strong = strong_section()
+
     sampler.stop.set()
     clocks = sampler.summary()
     if rank != 0:
@@ -746,15 +989,33 @@ def main():
     head = args.paths[0]
     h = results[head]
     cfg = CFG[head]
+    if roof and h.get("e2e"):
+        # the e2e roof of this box: raw concurrent pinned copies at this N (belt/bash e2e are copy-bound)
+        for k, v in results.items():
+            e = v.get("e2e")
+            if not e:
+                continue
+            sec_per_step = world * CFG[k]["units"] * (CFG[k]["unit_bytes"] if CFG[k]["unit"] == "GB/s" else 1) / (e["value"] * (1e9 if CFG[k]["unit"] == "GB/s" else 1.0))
+            floor = world * e["h2d_bytes_per_step"] / (roof["h2d"] * 1e9) + world * e["d2h_bytes_per_step"] / (roof["d2h"] * 1e9)
+            e["copy_roof_GBs"] = roof
+            e["copy_floor_ms"] = 1e3 * floor
+            e["frac_of_copy_roof"] = floor / sec_per_step if sec_per_step > 0 else None
+    also = {k: compact(v) for k, v in results.items() if k != head}
+    config = {"workload": cfg["workload"], "l2": h["l2"], "units_per_gpu": cfg["units"],
+              "sharding": "rank r takes units [r*U,(r+1)*U); key/iv/oid broadcast from rank 0 over NCCL; no data-path collective",
+              "numa": numa, "also": also}
+    if strong is not None:
+        config["strong"] = {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk != "limiter"}
+                            for k, v in strong.items()}
     line = {"metric": cfg["metric"], "value": h["value"], "unit": cfg["unit"], "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
-            "config": {"workload": cfg["workload"], "l2": h["l2"], "units_per_gpu": cfg["units"],
-                       "sharding": "rank r takes units [r*U,(r+1)*U); key/iv/oid broadcast from rank 0 over NCCL; no data-path collective"},
+            "config": config,
             "roofline": h["roofline"], "issue_roofline": h.get("issue_roofline"),
             "cpu_baseline": h.get("cpu_baseline"), "e2e": h.get("e2e"), "gather": h.get("gather"), "gpu_launches": h["gpu_launches"],
             "clocks": clocks, "issue_peaks_Tops": issue,
-            "paths": {k: v for k, v in results.items() if k != head}}
+            "paths": {k: v for k, v in results.items() if k != head}, "strong": strong,
+            "also": {k: compact(v) for k, v in results.items()}}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

@@ -95,6 +95,15 @@ err_t b2g_ipc_open(void** dptr, const octet handle[64]);
 err_t b2g_ipc_close(void* dptr);
 /* cudaMemcpyAsync on a caller's stream (to_device != 0: H2D, else D2H) */
 err_t b2g_memcpy_async(void* dst, const void* src, size_t n, int to_device, void* stream);
+/* Overlay mode. With a stock libbee2 BEHIND this library in the symbol search order (link with
+   `-lbee2_b200 -lbee2`, or LD_PRELOAD this library into a bee2 application) the drop-in entry
+   points forward to it — dlsym(RTLD_NEXT, name) — for inputs the GPU path does not cover
+   (non-standard bign_params, a generic ec_o, scalars longer than the field, OID / t > 64 octets),
+   for one-shot calls whose payload is below `bytes` (default 0 = never; also B2G_CPU_BELOW in the
+   environment), and when the GPU path of a `void` function fails (instead of abort()). */
+void b2g_set_cpu_below(size_t bytes);
+int b2g_has_stock(void);           /* 1 if a stock libbee2 is reachable behind this library */
+u64 b2g_forward_count(void);       /* calls forwarded to it so far */
 /* How many kernels this library has launched in this process (for gpu_launches). */
 u64 b2g_launch_count(void);
 /* Measured issue peak of one instruction kind, lane-operations per second on the whole chip:
@@ -256,6 +265,8 @@ err_t b2g_beltCHEMac_dev(void* d_mac, const void* d_crit, size_t n1, const void*
 err_t b2g_beltECB_dev(void* d_dest, const void* d_src, size_t nblocks, const u32 key[8],
 	int decrypt, void* stream);
 err_t b2g_beltECBEncrBatch_dev(void* d_blocks, const void* d_keys32, size_t count, void* stream);
+/* out of place: d_dst may be another device's HBM mapped with b2g_ipc_open (gather fused into the kernel) */
+err_t b2g_beltECBEncrBatch2_dev(void* d_dst, const void* d_src, const void* d_keys32, size_t count, void* stream);
 err_t b2g_beltHashBatch_dev(void* d_hashes, const void* d_msgs, size_t msg_len, size_t stride,
 	size_t count, void* stream);
 
