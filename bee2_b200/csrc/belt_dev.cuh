@@ -63,21 +63,33 @@ struct BeltBigT
 	}
 };
 
+// The small-table policies keep the table's 32-bit SHARED-WINDOW address, not a generic pointer, and read
+// it with ld.shared: the policy object travels by value into out-of-line routines (belt_hash_words inside
+// the bign kernels), where a generic pointer made every lookup a generic LD with 64-bit address arithmetic
+// (IADD3 + IMAD.X per lookup; r02 SASS histogram: 672 LD + 504 IMAD.X per three block encryptions).
+__device__ __forceinline__ u32 belt_lds(u32 saddr)
+{
+	u32 v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+	return v;
+}
+__device__ __forceinline__ u32 belt_saddr(const void* sm) { return (u32)__cvta_generic_to_shared(sm); }
+
 struct BeltSmallT
 {
 	static constexpr int WORDS = 256;
-	const u32* tab;   // shared memory, 256 words: tab[x] = H[x]
+	u32 tab;   // shared-window byte address of 256 words: tab[x] = H[x]
 
 	__device__ __forceinline__ static void fill(u32* sm)
 	{
 		for (u32 i = threadIdx.x; i < 256u; i += blockDim.x)
 			sm[i] = c_beltH[i];
 	}
-	__device__ __forceinline__ BeltSmallT(const u32* sm) : tab(sm) {}
+	__device__ __forceinline__ BeltSmallT(const u32* sm) : tab(belt_saddr(sm)) {}
 	template <int T0> __device__ __forceinline__ u32 g(u32 x) const
 	{
-		const u32 v = tab[x & 255u] | tab[(x >> 8) & 255u] << 8 | tab[(x >> 16) & 255u] << 16 |
-			tab[x >> 24] << 24;
+		const u32 v = belt_lds(tab + ((x & 255u) << 2)) | belt_lds(tab + (((x >> 8) & 255u) << 2)) << 8 |
+			belt_lds(tab + (((x >> 16) & 255u) << 2)) << 16 | belt_lds(tab + ((x >> 24) << 2)) << 24;
 		return rotl32(v, 5 + 8 * T0);
 	}
 };
@@ -88,19 +100,21 @@ struct BeltSmallT
 struct BeltT4
 {
 	static constexpr int WORDS = 1024;
-	const u32* tab;   // tab[t * 256 + x] = rotl32(H[x], 5 + 8 t)
+	u32 tab;   // shared-window byte address of tab[t * 256 + x] = rotl32(H[x], 5 + 8 t)
 
 	__device__ __forceinline__ static void fill(u32* sm)
 	{
 		for (u32 i = threadIdx.x; i < 1024u; i += blockDim.x)
 			sm[i] = rotl32((u32)c_beltH[i & 255u], 5 + 8 * (int)(i >> 8));
 	}
-	__device__ __forceinline__ BeltT4(const u32* sm) : tab(sm) {}
+	__device__ __forceinline__ BeltT4(const u32* sm) : tab(belt_saddr(sm)) {}
 	// G_r with r = 5 + 8*T0: byte k of x goes through table (T0 + k) mod 4
 	template <int T0> __device__ __forceinline__ u32 g(u32 x) const
 	{
-		return tab[((T0 + 0) & 3) * 256 + (x & 255u)] ^ tab[((T0 + 1) & 3) * 256 + ((x >> 8) & 255u)] ^
-			tab[((T0 + 2) & 3) * 256 + ((x >> 16) & 255u)] ^ tab[((T0 + 3) & 3) * 256 + (x >> 24)];
+		return belt_lds(tab + ((T0 + 0) & 3) * 1024 + ((x & 255u) << 2)) ^
+			belt_lds(tab + ((T0 + 1) & 3) * 1024 + (((x >> 8) & 255u) << 2)) ^
+			belt_lds(tab + ((T0 + 2) & 3) * 1024 + (((x >> 16) & 255u) << 2)) ^
+			belt_lds(tab + ((T0 + 3) & 3) * 1024 + ((x >> 24) << 2));
 	}
 };
 

@@ -217,7 +217,13 @@ template <int N> __device__ __forceinline__ void load_scalar(sc<N>& k, const u8*
 
 // ---------------------------------------------------------------- fixed-base multiplication
 // acc += k * G for a 32N-bit k (little-endian limbs) through the fixed-base window table
-template <int N> __device__ __noinline__ void pt_add_mul_base(pt<N>& acc, const sc<N> ks, const uint4* __restrict__ gtab)
+// CT = true (secret scalars: the one-time key of bignSign / bignSign2, the private key of bignPubkeyCalc /
+// bignKeypairGen; the reference's bignMulBase is regular, ec.c:892-964): a zero digit does not skip the
+// addition — entry 1 of the window is added and the sum dropped by a mask — so the instruction stream does
+// not depend on the scalar. The ADDRESS of the table read still does (13 bits of the scalar select one of
+// 8192 entries of a 10 MiB table): a cache-timing channel the reference's masked wwSel scan does not have;
+// scanning 8192 entries per window is not an option here, see DESIGN.md "Secret scalars".
+template <int N, bool CT = false> __device__ __noinline__ void pt_add_mul_base(pt<N>& acc, const sc<N> ks, const uint4* __restrict__ gtab)
 {
 	const u32* k = ks.w;
 #pragma unroll 1
@@ -226,7 +232,23 @@ template <int N> __device__ __noinline__ void pt_add_mul_base(pt<N>& acc, const 
 		const int bit = BIGN_GW * i, limb = bit >> 5;
 		const u64 w = (u64)k[limb] | (limb < N - 1 ? (u64)k[limb + 1] << 32 : 0);
 		const u32 d = (u32)(w >> (bit & 31)) & (BIGN_GE - 1);
-		if (d)
+		if (CT)
+		{
+			const u32 dd = d | (u32)(d == 0);
+			const uint4* e = gtab + (size_t)(i * BIGN_GE + (int)dd) * (N / 2);
+			fe<N> x, y;
+#pragma unroll
+			for (int j = 0; j < N / 4; ++j)
+			{
+				const uint4 a = __ldg(e + j), b = __ldg(e + N / 4 + j);
+				x.v[4 * j] = a.x, x.v[4 * j + 1] = a.y, x.v[4 * j + 2] = a.z, x.v[4 * j + 3] = a.w;
+				y.v[4 * j] = b.x, y.v[4 * j + 1] = b.y, y.v[4 * j + 2] = b.z, y.v[4 * j + 3] = b.w;
+			}
+			pt<N> S;
+			pt_madd<N>(S, acc, x, y);
+			pt_select<N>(acc, S, 0u - (u32)(d != 0));
+		}
+		else if (d)
 		{
 			const uint4* e = gtab + (size_t)(i * BIGN_GE + (int)d) * (N / 2);
 			fe<N> x, y;
@@ -560,7 +582,7 @@ bign_sign2_kernel(u32* __restrict__ status, u8* __restrict__ sigs, const u8* __r
 			sc<N> ks;
 #pragma unroll
 			for (int j = 0; j < N; ++j) ks.w[j] = k[j];
-			pt_add_mul_base<N>(R, ks, gtab);
+			pt_add_mul_base<N, true>(R, ks, gtab);   // the one-time key is secret: regular form
 		}
 		if (pt_is_inf<N>(R))
 			st = B2G_BAD_PARAMS, live = false;
@@ -631,7 +653,7 @@ bign_pubkey_kernel(u32* __restrict__ status, u8* __restrict__ pubkeys, const u8*
 			sc<N> ks;
 #pragma unroll
 			for (int j = 0; j < N; ++j) ks.w[j] = d[j];
-			pt_add_mul_base<N>(R, ks, gtab);
+			pt_add_mul_base<N, true>(R, ks, gtab);   // the private key is secret: regular form
 			if (pt_is_inf<N>(R))
 				st = B2G_BAD_PARAMS, live = false;
 		}
@@ -670,12 +692,13 @@ ecp_mul_kernel(u8* __restrict__ out, int* __restrict__ ok, const u8* __restrict_
 		fe_load<N>(x, pts + 2 * NO * i), fe_load<N>(y, pts + 2 * NO * i + NO);
 		sc<N> k;
 		load_scalar<N>(k, scalars + (u64)d_len * i, d_len);
-		pt_mul_var<N>(R, k, (int)(8 * d_len), x, y);
+		// ecMulA / ecAddMulA callers may pass secret scalars (bignDH, key transport): regular forms
+		pt_mul_var<N, true>(R, k, (int)(8 * d_len), x, y);
 		if (kbase)
 		{
 			sc<N> kg;
 			load_uN<N>(kg.w, kbase + NO * i);
-			pt_add_mul_base<N>(R, kg, gtab);
+			pt_add_mul_base<N, true>(R, kg, gtab);
 		}
 		live = !pt_is_inf<N>(R);
 	}
@@ -740,7 +763,7 @@ bign_dh_kernel(u32* __restrict__ status, u8* __restrict__ out, const u8* __restr
 		}
 		if (live && !validate_only)
 		{
-			pt_mul_var<N>(R, d, 32 * N, x, y);
+			pt_mul_var<N, true>(R, d, 32 * N, x, y);   // the private key is secret: regular form
 			if (pt_is_inf<N>(R))
 				st = B2G_BAD_PARAMS, live = false;
 		}

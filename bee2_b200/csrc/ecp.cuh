@@ -176,6 +176,18 @@ template <int N> GFP_HD void pt_to_affine_x(fe<N>& x, const pt<N>& P)
 	fe_canon<N>(x);
 }
 
+// R <- m ? P : R for an all-ones / all-zero mask m, without a branch (the regular forms below)
+template <int N> GFP_HD void pt_select(pt<N>& R, const pt<N>& P, u32 m)
+{
+#pragma unroll
+	for (int k = 0; k < N; ++k)
+	{
+		R.X.v[k] ^= (R.X.v[k] ^ P.X.v[k]) & m;
+		R.Y.v[k] ^= (R.Y.v[k] ^ P.Y.v[k]) & m;
+		R.Z.v[k] ^= (R.Z.v[k] ^ P.Z.v[k]) & m;
+	}
+}
+
 // ---------------------------------------------------------------- variable-base multiplication
 // acc = k * (x, y) for a scalar of nbits bits (little-endian limbs, bits above nbits must be 0).
 // REGULAR signed 5-bit windows so that all lanes of a warp run the same doublings and additions
@@ -184,8 +196,15 @@ template <int N> GFP_HD void pt_to_affine_x(fe<N>& x, const pt<N>& P)
 //   table {1..16}(x, y) in local memory (8 doublings + 7 mixed additions);
 //   5 doublings + 1 addition per window, most significant first; nbits/5 + 1 windows, the top one
 //   always has a spare bit and absorbs the last carry.
+//
+// CT = true is the form for SECRET scalars (bignDH, ecMulA callers such as key transport; the reference's
+// ecMulA is regular on purpose, ec.c:497-525 with wwSel-style table reads, ww.c:298-310): the table entry
+// is fetched by a masked scan over all 16 entries instead of T[d], a zero digit still performs the
+// addition (with entry 1) and the result is dropped by a mask, the sign is applied by a mask. What remains
+// data-dependent are the exceptional branches of pt_add (P = +-Q, probability ~ 2^-250 for an honest
+// scalar) and the top window. CT = false (public scalars: verification) keeps the direct, cheaper form.
 #define PT_WIN 5
-template <int N> __host__ __device__ __noinline__ void pt_mul_var(pt<N>& acc, const sc<N> ks, int nbits,
+template <int N, bool CT = false> __host__ __device__ __noinline__ void pt_mul_var(pt<N>& acc, const sc<N> ks, int nbits,
 	const fe<N> x, const fe<N> y)
 {
 	const u32* k = ks.w;
@@ -236,6 +255,44 @@ template <int N> __host__ __device__ __noinline__ void pt_mul_var(pt<N>& acc, co
 		w = (w & (2 * HALF - 1)) + ((cy[i >> 5] >> (i & 31)) & 1u);
 		const bool neg = w > HALF;
 		const u32 d = neg ? 2 * HALF - w : w;
+		if (CT)
+		{
+			// Q = T[d ? d : 1] by a scan over the whole table; -Q by a mask
+			const u32 dd = d | (u32)(d == 0);
+			pt<N> Q, S;
+#pragma unroll
+			for (int k = 0; k < N; ++k) Q.X.v[k] = 0, Q.Y.v[k] = 0, Q.Z.v[k] = 0;
+#pragma unroll 1
+			for (u32 j = 1; j <= (u32)HALF; ++j)
+			{
+				const u32 m = 0u - (u32)(j == dd);
+#pragma unroll
+				for (int k = 0; k < N; ++k)
+					Q.X.v[k] |= T[j].X.v[k] & m, Q.Y.v[k] |= T[j].Y.v[k] & m, Q.Z.v[k] |= T[j].Z.v[k] & m;
+			}
+			{
+				fe<N> ny;
+				fe_neg<N>(ny, Q.Y);
+				const u32 mn = 0u - (u32)neg;
+#pragma unroll
+				for (int k = 0; k < N; ++k) Q.Y.v[k] ^= (Q.Y.v[k] ^ ny.v[k]) & mn;
+			}
+			const u32 nz = 0u - (u32)(d != 0);
+			if (first)
+			{
+				// top window: acc = d ? Q : O (Z = 0)
+				acc = Q;
+#pragma unroll
+				for (int k = 0; k < N; ++k) acc.Z.v[k] &= nz;
+				first = false;
+			}
+			else
+			{
+				pt_add<N>(S, acc, Q);
+				pt_select<N>(acc, S, nz);
+			}
+			continue;
+		}
 		if (first)
 		{
 			// the top window only selects (no doublings of O); it is never negative

@@ -459,12 +459,23 @@ void* b2g_stock(const char* name)
 	(void)dlerror();
 	return f;
 }
-void b2g_note_forward(void) { __sync_fetch_and_add(&g_forwards, 1); }
+void b2g_note_forward(const char* fn)
+{
+	static int trace = -1;
+	__sync_fetch_and_add(&g_forwards, 1);
+	if (trace < 0)
+	{
+		const char* e = getenv("B2G_TRACE_FORWARD");
+		trace = e && *e && *e != '0';
+	}
+	if (trace)
+		fprintf(stderr, "b2g-forward %s\n", fn);
+}
 u64 b2g_forward_count(void) { return g_forwards; }
 void b2g_warn_forward(const char* fn, u32 code)
 {
 	static int said;
-	b2g_note_forward();
+	b2g_note_forward(fn);
 	if (!__sync_lock_test_and_set(&said, 1))
 		fprintf(stderr, "bee2_b200: %s cannot run on the GPU path (err %u: %s); forwarding such calls to the stock "
 			"libbee2 behind this library (said once)\n", fn, code, g_err);

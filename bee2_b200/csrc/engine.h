@@ -81,7 +81,7 @@ int b2g_ct_eq(const void* a, const void* b, size_t n);
 void b2g_wipe(void* p, size_t n);
 void* b2g_stock(const char* name);
 int b2g_route_small(size_t bytes);
-void b2g_note_forward(void);
+void b2g_note_forward(const char* fn);   /* counted; B2G_TRACE_FORWARD=1 prints each name on stderr */
 /* a call handed to stock libbee2 because the GPU path could NOT run it (not by routing policy):
    counted, and said once per process on stderr — the engine never degrades silently */
 void b2g_warn_forward(const char* fn, u32 code);
@@ -89,20 +89,20 @@ void b2g_warn_forward(const char* fn, u32 code);
 	if (!tried_) { f_ = b2g_stock(#name); __sync_synchronize(); tried_ = 1; } (__typeof__(&name))f_; })
 /* forward a small call: for functions returning a value / void */
 #define B2G_SMALL_R(bytes, name, ...) do { if (b2g_route_small(bytes)) { __typeof__(&name) fs_ = B2G_STOCK_FN(name); \
-	if (fs_) { b2g_note_forward(); return fs_(__VA_ARGS__); } } } while (0)
+	if (fs_) { b2g_note_forward(#name); return fs_(__VA_ARGS__); } } } while (0)
 #define B2G_SMALL_V(bytes, name, ...) do { if (b2g_route_small(bytes)) { __typeof__(&name) fs_ = B2G_STOCK_FN(name); \
-	if (fs_) { b2g_note_forward(); fs_(__VA_ARGS__); return; } } } while (0)
+	if (fs_) { b2g_note_forward(#name); fs_(__VA_ARGS__); return; } } } while (0)
 /* forward unconditionally if a stock library exists (unsupported input) */
 #define B2G_STOCK_R(name, ...) do { __typeof__(&name) fs_ = B2G_STOCK_FN(name); \
-	if (fs_) { b2g_note_forward(); return fs_(__VA_ARGS__); } } while (0)
+	if (fs_) { b2g_note_forward(#name); return fs_(__VA_ARGS__); } } while (0)
 /* the GPU path of a void drop-in failed: stock if there is one, else abort */
 #define B2G_FAIL_V(code, name, ...) do { __typeof__(&name) fs_ = B2G_STOCK_FN(name); \
-	if (fs_) { b2g_note_forward(); fs_(__VA_ARGS__); return; } b2g_die(#name, code); } while (0)
+	if (fs_) { b2g_note_forward(#name); fs_(__VA_ARGS__); return; } b2g_die(#name, code); } while (0)
 /* first line of a void drop-in: no usable device -> the whole call goes to stock libbee2, untouched */
 #define B2G_PREFLIGHT_V(name, ...) do { const u32 pc_ = b2g_ensure_device(); if (pc_) B2G_FAIL_V(pc_, name, __VA_ARGS__); } while (0)
 #define B2G_PREFLIGHT_R(name, ...) do { const u32 pc_ = b2g_ensure_device(); if (pc_) B2G_FAIL_R(pc_, name, __VA_ARGS__); } while (0)
 #define B2G_FAIL_R(code, name, ...) do { __typeof__(&name) fs_ = B2G_STOCK_FN(name); \
-	if (fs_) { b2g_note_forward(); return fs_(__VA_ARGS__); } b2g_die(#name, code); } while (0)
+	if (fs_) { b2g_note_forward(#name); return fs_(__VA_ARGS__); } b2g_die(#name, code); } while (0)
 
 #ifdef __cplusplus
 }

@@ -995,7 +995,7 @@ static int addmul_stock(bool_t* ret, u64 b[], const void* ec, void* stack, size_
 	__typeof__(&ecAddMulA) f = B2G_STOCK_FN(ecAddMulA);
 	if (!f || k == 0 || k > 8)
 		return 0;
-	b2g_note_forward();
+	b2g_note_forward("ecAddMulA");
 #define T_(i) a[i], d[i], m[i]
 	switch (k)
 	{

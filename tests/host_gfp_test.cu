@@ -102,6 +102,17 @@ template <int N> static std::string run(const std::string& op, std::istringstrea
 		from_hex<N>(k.w, ha), from_hex<N>(x.v, hb), from_hex<N>(y.v, hc);
 		pt<N> R;
 		pt_mul_var<N>(R, k, nbits, x, y);
+		{
+			// the regular (secret-scalar) form must land on the same point, limb for limb
+			pt<N> C;
+			pt_mul_var<N, true>(C, k, nbits, x, y);
+			const bool same_inf = pt_is_inf<N>(R) == pt_is_inf<N>(C);
+			bool same = same_inf;
+			if (same && !pt_is_inf<N>(R))
+				for (int i = 0; i < N; ++i)
+					same = same && R.X.v[i] == C.X.v[i] && R.Y.v[i] == C.Y.v[i] && R.Z.v[i] == C.Z.v[i];
+			if (!same) return "ct-mismatch";
+		}
 		if (pt_is_inf<N>(R)) return "inf";
 		pt_to_affine<N>(x, y, R);
 		return to_hex(x.v, N) + " " + to_hex(y.v, N);
