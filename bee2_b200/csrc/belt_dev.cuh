@@ -99,22 +99,29 @@ struct BeltSmallT
 // the data fall (the LSU pipe is idle in the kernels that use it: belt inside bign).
 struct BeltT4
 {
-	static constexpr int WORDS = 1024;
-	u32 tab;   // shared-window byte address of tab[t * 256 + x] = rotl32(H[x], 5 + 8 t)
-
-	__device__ __forceinline__ static void fill(u32* sm)
+	// The table is a static __shared__ array of the policy itself: its shared-window address is a link-time
+	// constant, so every lookup is one LDS with an immediate base (R + imm) — no base-register add per
+	// lookup (r02 SASS: 304 IMAD.IADD per block encryption with a run-time base). Kernels still declare
+	// `__shared__ u32 tab[SB::WORDS]` and pass it around for the other policies; here it is one word.
+	static constexpr int WORDS = 1;
+	__device__ __forceinline__ static u32* table()
 	{
-		for (u32 i = threadIdx.x; i < 1024u; i += blockDim.x)
-			sm[i] = rotl32((u32)c_beltH[i & 255u], 5 + 8 * (int)(i >> 8));
+		__shared__ u32 t[1024];   // t[k * 256 + x] = rotl32(H[x], 5 + 8 k)
+		return t;
 	}
-	__device__ __forceinline__ BeltT4(const u32* sm) : tab(belt_saddr(sm)) {}
+	__device__ __forceinline__ static void fill(u32*)
+	{
+		u32* t = table();
+		for (u32 i = threadIdx.x; i < 1024u; i += blockDim.x)
+			t[i] = rotl32((u32)c_beltH[i & 255u], 5 + 8 * (int)(i >> 8));
+	}
+	__device__ __forceinline__ BeltT4(const u32*) {}
 	// G_r with r = 5 + 8*T0: byte k of x goes through table (T0 + k) mod 4
 	template <int T0> __device__ __forceinline__ u32 g(u32 x) const
 	{
-		return belt_lds(tab + ((T0 + 0) & 3) * 1024 + ((x & 255u) << 2)) ^
-			belt_lds(tab + ((T0 + 1) & 3) * 1024 + (((x >> 8) & 255u) << 2)) ^
-			belt_lds(tab + ((T0 + 2) & 3) * 1024 + (((x >> 16) & 255u) << 2)) ^
-			belt_lds(tab + ((T0 + 3) & 3) * 1024 + ((x >> 24) << 2));
+		const u32* t = table();
+		return t[((T0 + 0) & 3) * 256 + (x & 255u)] ^ t[((T0 + 1) & 3) * 256 + ((x >> 8) & 255u)] ^
+			t[((T0 + 2) & 3) * 256 + ((x >> 16) & 255u)] ^ t[((T0 + 3) & 3) * 256 + (x >> 24)];
 	}
 };
 

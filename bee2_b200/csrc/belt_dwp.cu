@@ -6,12 +6,16 @@
 // by mac = E_K(t)[0..8). Encryption itself is the belt-CTR kernel of belt.cu.
 //
 // The Horner chain is sequential in the reference; here it is a polynomial evaluation
-//     t_N = t_0 r^N  ^  sum_i B_i r^(N - i + 1)
-// cut into one contiguous chunk of K blocks per thread. Every thread runs Horner over its chunk
-// (multiplication by the fixed r through conflict-free 4-bit window tables in shared memory),
-// weights the result with r^(number of blocks after the chunk) (square-and-multiply: squarings
-// are bit spreads) and the weighted chunk values are XOR-reduced (warp shuffles + one atomicXor
-// per warp and word). A one-thread kernel encrypts the sum.
+//     t_N = t_0 r^N  ^  sum_i B_i r^(N - i)          (blocks B_0 .. B_(N-1))
+// cut into one contiguous chunk of 32 K blocks per WARP, interleaved over its lanes: lane L takes
+// blocks L, L + 32, L + 64, ... of the chunk, so the 32 lanes of a load read 512 contiguous octets
+// (round 1 gave every THREAD a contiguous chunk: 32 different 128-byte lines per load, 32 LSU
+// wavefronts instead of 4 — a fifth of that kernel's time, profiles/README.md r02). A lane runs
+// Horner in R = r^32 (multiplication by the fixed R through conflict-free 4-bit window tables in
+// shared memory), then its value is weighted with r^(1..32) (a 33-entry table of small powers), the
+// lanes are XOR-reduced by warp shuffles, the warp's value is weighted with r^(blocks after the
+// chunk) = R^q r^s (square-and-multiply in R: squarings are bit spreads) and one atomicXor per warp
+// and word adds it to the total. A one-thread kernel encrypts the sum.
 #include "belt_dev.cuh"
 #include "gf128.cuh"
 
@@ -52,7 +56,7 @@ __device__ __forceinline__ gf128 dwp_block(const DwpArgs& a, u64 i)
 	const u8* p = base + off;
 	if (off + 16 <= total && ((uintptr_t)p & 15) == 0)
 	{
-		const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+		const uint4 v = ldg_stream(reinterpret_cast<const uint4*>(p));   // a warp reads 512 contiguous octets
 		b.w[0] = v.x, b.w[1] = v.y, b.w[2] = v.z, b.w[3] = v.w;
 		return b;
 	}
@@ -91,41 +95,81 @@ __global__ void __launch_bounds__(DWP_THREADS) belt_dwp_mac_kernel(const DwpArgs
 	gf128 r;
 #pragma unroll
 	for (int i = 0; i < 4; ++i) r.w[i] = rsh[i];
-	gf_tab_build(tab, r);
+	// small powers r^0 .. r^32 (thread k computes r^k by square-and-multiply with the generic product)
+	gf128* pw = reinterpret_cast<gf128*>(rsh + 4);
+	if (threadIdx.x <= 32)
+	{
+		gf128 acc = {{1, 0, 0, 0}};
+		for (int bit = 5; bit >= 0; --bit)
+		{
+			acc = gf_sqr(acc);
+			if (threadIdx.x >> bit & 1u) acc = gf_mul(acc, r);
+		}
+		pw[threadIdx.x] = acc;
+	}
+	// tables of R = r^32
+	gf128 R = r;
+#pragma unroll
+	for (int i = 0; i < 5; ++i) R = gf_sqr(R);
+	gf_tab_build(tab, R);
 	__syncthreads();
 
-	const u64 j = (u64)blockIdx.x * DWP_THREADS + threadIdx.x;
-	const u64 b0 = j * a.K;
+	const u32 lane = threadIdx.x & 31u;
+	const u64 warp = ((u64)blockIdx.x * DWP_THREADS + threadIdx.x) >> 5;
+	const u64 b0 = warp * 32 * a.K;                    // the warp's chunk [b0, b1)
 	gf128 w = {{0, 0, 0, 0}};
 	if (b0 < a.N)
 	{
-		const u64 b1 = b0 + a.K < a.N ? b0 + a.K : a.N;
+		const u64 b1 = b0 + 32 * a.K < a.N ? b0 + 32 * a.K : a.N;
 		gf128 acc = {{0, 0, 0, 0}};
-		if (j == 0)
-		{
-			// t_0 = beltH()[0..16) (belt_dwp.c:60), or the running t of a streaming state
-			const u32* H32 = reinterpret_cast<const u32*>(c_beltH);
-#pragma unroll
-			for (int i = 0; i < 4; ++i) acc.w[i] = H32[i];
-			if (a.t0_given)
-				acc.w[0] = a.t0.x, acc.w[1] = a.t0.y, acc.w[2] = a.t0.z, acc.w[3] = a.t0.w;
-		}
+		u64 last = 0;
+		bool any = false;
 #pragma unroll 1
-		for (u64 i = b0; i < b1; ++i)
-			acc = gf_mul_tab(tab, gf_xor(acc, dwp_block(a, i)));
-		// weight: r^(blocks after this chunk)
+		for (u64 i = b0 + lane; i < b1; i += 32)
+		{
+			gf128 blk = dwp_block(a, i);
+			if (i == 0)
+			{
+				// t_0 = beltH()[0..16) (belt_dwp.c:60), or the running t of a streaming state: the chain
+				// (t ^ B_0) r ... = t_0 r^N ^ sum B_i r^(N-i), so t_0 simply joins block 0
+				const u32* H32 = reinterpret_cast<const u32*>(c_beltH);
+				gf128 t0;
+#pragma unroll
+				for (int k = 0; k < 4; ++k) t0.w[k] = H32[k];
+				if (a.t0_given)
+					t0.w[0] = a.t0.x, t0.w[1] = a.t0.y, t0.w[2] = a.t0.z, t0.w[3] = a.t0.w;
+				blk = gf_xor(blk, t0);
+			}
+			acc = any ? gf_xor(gf_mul_tab(tab, acc), blk) : blk;   // acc <- acc R ^ B
+			any = true, last = i;
+		}
+		// the lane's value counts from its last block: weight r^(b1 - last), 1 <= b1 - last <= 32
+		if (any)
+			w = gf_mul(acc, pw[b1 - last]);
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+		{
+			u32 v = w.w[k];
+#pragma unroll
+			for (int d = 16; d; d >>= 1) v ^= __shfl_xor_sync(0xFFFFFFFFu, v, d);
+			w.w[k] = v;
+		}
+		// the warp's value counts from b1: weight r^(N - b1) = R^q r^s
 		const u64 e = a.N - b1;
-		w = e ? gf_mul(acc, gf_pow_r(tab, e)) : acc;
+		if (lane == 0 && e)
+		{
+			const gf128 Rq = gf_pow_r(tab, e >> 5);
+			w = gf_mul(w, Rq);
+			if (e & 31)
+				w = gf_mul(w, pw[e & 31]);
+		}
 	}
-	// XOR-reduce over the warp, then one atomic per word
-#pragma unroll
-	for (int k = 0; k < 4; ++k)
+	if (lane == 0)
 	{
-		u32 v = w.w[k];
 #pragma unroll
-		for (int d = 16; d; d >>= 1) v ^= __shfl_xor_sync(0xFFFFFFFFu, v, d);
-		if ((threadIdx.x & 31) == 0 && v)
-			atomicXor(a.acc + k, v);
+		for (int k = 0; k < 4; ++k)
+			if (w.w[k])
+				atomicXor(a.acc + k, w.w[k]);
 	}
 }
 
@@ -194,8 +238,8 @@ static u32 dwp_mac_launch(void* d_mac, const void* d_crit, size_t n1, const void
 	u64 K = (a.N + tmax - 1) / tmax;
 	if (K < DWP_MIN_CHUNK) K = DWP_MIN_CHUNK;
 	a.K = K;
-	const u64 nthreads = (a.N + K - 1) / K;
-	const u32 grid = (u32)((nthreads + DWP_THREADS - 1) / DWP_THREADS);
+	const u64 nwarps = (a.N + 32 * K - 1) / (32 * K);   // one chunk of 32 K blocks per warp
+	const u32 grid = (u32)((nwarps * 32 + DWP_THREADS - 1) / DWP_THREADS);
 	if (cudaMemsetAsync(d_scratch, 0, 16, st) != cudaSuccess)
 		return b2g_check_launch("cudaMemsetAsync(dwp)");
 	belt_dwp_mac_kernel<<<grid, DWP_THREADS, GF_TAB_BYTES + 2048, st>>>(a);
@@ -234,8 +278,8 @@ extern "C" u32 b2g_beltPolyAbsorb_dev(void* d_t, const void* d_blocks, size_t nb
 	u64 K = (a.N + tmax - 1) / tmax;
 	if (K < DWP_MIN_CHUNK) K = DWP_MIN_CHUNK;
 	a.K = K;
-	const u64 nthreads = (a.N + K - 1) / K;
-	const u32 grid = (u32)((nthreads + DWP_THREADS - 1) / DWP_THREADS);
+	const u64 nwarps = (a.N + 32 * K - 1) / (32 * K);
+	const u32 grid = (u32)((nwarps * 32 + DWP_THREADS - 1) / DWP_THREADS);
 	if (cudaMemsetAsync(d_scratch, 0, 16, st) != cudaSuccess)
 		return b2g_check_launch("cudaMemsetAsync(poly)");
 	belt_dwp_mac_kernel<<<grid, DWP_THREADS, GF_TAB_BYTES + 2048, st>>>(a);

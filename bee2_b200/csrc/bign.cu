@@ -11,9 +11,9 @@
 // Work decomposition: ONE THREAD PER ITEM (signature / key / scalar-point pair), field
 // elements as N x u32 in registers. Scalar multiplication is REGULAR so that all lanes of a
 // warp execute the same doublings and additions in lock-step:
-//   * fixed base G: BIGN_GW-bit windows (13) over a device-resident table GTAB[GN][8192] of
-//     affine multiples j * 2^(13 i) * G (10 / 24 / 42 MiB, L2-resident; generated once per
-//     process and level by bign_gtab_kernel with the same point code) -> 20 / 30 / 40 mixed
+//   * fixed base G: 16 / 13 / 13-bit windows over a device-resident table GTAB[GN][2^w] of
+//     affine multiples j * 2^(w i) * G (67 / 24 / 42 MiB; generated once per process, device
+//     and level by bign_gtab_kernel with the same point code) -> 16 / 30 / 40 mixed
 //     additions, no doublings;
 //   * variable base Q: signed 5-bit windows, per-thread table {1..16}Q in local memory
 //     (ecp.cuh pt_mul_var) -> 5 doublings + 1 addition per window.
@@ -45,11 +45,19 @@
 #define BIGN_BLOCKS16 4
 #endif
 #define BIGN_BLOCKS(N) ((N) == 8 ? BIGN_MIN_BLOCKS : (N) == 12 ? BIGN_BLOCKS12 : BIGN_BLOCKS16)
-#ifndef BIGN_GW
-#define BIGN_GW 13                                  // fixed-base window width in bits (<= 16)
+// Fixed-base window width in bits (<= 16), per field size. N = 8: 16 bits -> 16 mixed additions from a 67 MiB
+// table (measured against 13 bits / 20 additions / 10 MiB: verify 52.7 -> 53.9 M/s, sign2 202 -> 218 M/s; the
+// random 64-byte table reads miss L2 more often — 268 MB of extra DRAM reads per 2^18 items, far from binding).
+// The wider fields keep 13 bits (24 / 42 MiB): their 16-bit tables would be 151 / 268 MiB and take ~0.5 s to build.
+#ifndef BIGN_GW8
+#define BIGN_GW8 16
 #endif
-#define BIGN_GN(N) ((32 * (N) + BIGN_GW - 1) / BIGN_GW)   // number of windows
-#define BIGN_GE (1 << BIGN_GW)                      // entries per window (entry 0 unused)
+#ifndef BIGN_GW
+#define BIGN_GW 13
+#endif
+#define BIGN_GWN(N) ((N) == 8 ? BIGN_GW8 : BIGN_GW)
+#define BIGN_GN(N) ((32 * (N) + BIGN_GWN(N) - 1) / BIGN_GWN(N))   // number of windows
+#define BIGN_GE(N) (1 << BIGN_GWN(N))               // entries per window (entry 0 unused)
 #define BIGN_MAX_OID 64
 #define BIGN_MAX_T 64
 
@@ -229,13 +237,13 @@ template <int N, bool CT = false> __device__ __noinline__ void pt_add_mul_base(p
 #pragma unroll 1
 	for (int i = 0; i < BIGN_GN(N); ++i)
 	{
-		const int bit = BIGN_GW * i, limb = bit >> 5;
+		const int bit = BIGN_GWN(N) * i, limb = bit >> 5;
 		const u64 w = (u64)k[limb] | (limb < N - 1 ? (u64)k[limb + 1] << 32 : 0);
-		const u32 d = (u32)(w >> (bit & 31)) & (BIGN_GE - 1);
+		const u32 d = (u32)(w >> (bit & 31)) & (BIGN_GE(N) - 1);
 		if (CT)
 		{
 			const u32 dd = d | (u32)(d == 0);
-			const uint4* e = gtab + (size_t)(i * BIGN_GE + (int)dd) * (N / 2);
+			const uint4* e = gtab + ((size_t)i * BIGN_GE(N) + dd) * (N / 2);
 			fe<N> x, y;
 #pragma unroll
 			for (int j = 0; j < N / 4; ++j)
@@ -250,7 +258,7 @@ template <int N, bool CT = false> __device__ __noinline__ void pt_add_mul_base(p
 		}
 		else if (d)
 		{
-			const uint4* e = gtab + (size_t)(i * BIGN_GE + (int)d) * (N / 2);
+			const uint4* e = gtab + ((size_t)i * BIGN_GE(N) + d) * (N / 2);
 			fe<N> x, y;
 #pragma unroll
 			for (int j = 0; j < N / 4; ++j)
@@ -378,13 +386,13 @@ template <int N> __device__ __forceinline__ void pt_affine_xy_zi(fe<N>& x, fe<N>
 template <int N> __global__ void __launch_bounds__(128) bign_gtab_kernel(uint4* gtab)
 {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= BIGN_GN(N) * BIGN_GE)
+	if (idx >= BIGN_GN(N) * BIGN_GE(N))
 		return;
-	const int i = idx / BIGN_GE, j = idx % BIGN_GE;
+	const int i = idx / BIGN_GE(N), j = idx % BIGN_GE(N);
 	uint4* e = gtab + (size_t)idx * (N / 2);
 	// k = j << (BIGN_GW * i); digits whose bits would pass 2^(32N) cannot occur in a 32N-bit
 	// scalar, such entries are never read
-	const int bit = BIGN_GW * i, limb = bit >> 5;
+	const int bit = BIGN_GWN(N) * i, limb = bit >> 5;
 	if (j == 0 || bit + 32 - __clz(j) > 32 * N)
 	{
 		for (int l = 0; l < N / 2; ++l) e[l] = make_uint4(0, 0, 0, 0);
@@ -824,7 +832,7 @@ extern "C" u32 b2g_bign_upload_tables(const u8 H[256]) { return belt_upload_H(H)
 template <int N> static u32 bign_build_gtab(cudaStream_t st, uint4** out)
 {
 	uint4* p = 0;
-	const size_t entries = (size_t)BIGN_GN(N) * BIGN_GE;
+	const size_t entries = (size_t)BIGN_GN(N) * BIGN_GE(N);
 	if (cudaMalloc(&p, entries * 8 * N) != cudaSuccess)
 		return b2g_check_launch("cudaMalloc(gtab)");
 	bign_gtab_kernel<N><<<(u32)((entries + 127) / 128), 128, 0, st>>>(p);

@@ -454,8 +454,27 @@ static volatile long g_cpu_below = -1;     /* -1: not read from the environment 
 void* b2g_stock(const char* name)
 {
 	/* RTLD_NEXT: the next definition of `name` after THIS library in the search order, i.e. the
-	   stock libbee2 the application (also) links; NULL when there is none */
+	   stock libbee2 the application (also) links or that this library was preloaded in front of;
+	   NULL when there is none. A process that dlopen()s this library (Python, a plugin host) has no
+	   such order: it names the stock library in B2G_STOCK_LIB and gets a private copy of it. */
+	static void* handle;
+	static int tried;
 	void* f = dlsym(RTLD_NEXT, name);
+	if (!f)
+	{
+		if (!tried)
+		{
+			const char* path = getenv("B2G_STOCK_LIB");
+			pthread_mutex_lock(&g_init_mu);
+			if (!tried && path && *path)
+				handle = dlopen(path, RTLD_NOW | RTLD_LOCAL | RTLD_DEEPBIND);
+			__sync_synchronize();
+			tried = 1;
+			pthread_mutex_unlock(&g_init_mu);
+		}
+		if (handle)
+			f = dlsym(handle, name);
+	}
 	(void)dlerror();
 	return f;
 }

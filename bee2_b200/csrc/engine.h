@@ -97,7 +97,7 @@ void b2g_warn_forward(const char* fn, u32 code);
 	if (fs_) { b2g_note_forward(#name); return fs_(__VA_ARGS__); } } while (0)
 /* the GPU path of a void drop-in failed: stock if there is one, else abort */
 #define B2G_FAIL_V(code, name, ...) do { __typeof__(&name) fs_ = B2G_STOCK_FN(name); \
-	if (fs_) { b2g_note_forward(#name); fs_(__VA_ARGS__); return; } b2g_die(#name, code); } while (0)
+	if (fs_) { b2g_warn_forward(#name, code); fs_(__VA_ARGS__); return; } b2g_die(#name, code); } while (0)
 /* first line of a void drop-in: no usable device -> the whole call goes to stock libbee2, untouched */
 #define B2G_PREFLIGHT_V(name, ...) do { const u32 pc_ = b2g_ensure_device(); if (pc_) B2G_FAIL_V(pc_, name, __VA_ARGS__); } while (0)
 #define B2G_PREFLIGHT_R(name, ...) do { const u32 pc_ = b2g_ensure_device(); if (pc_) B2G_FAIL_R(pc_, name, __VA_ARGS__); } while (0)

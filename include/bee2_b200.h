@@ -100,7 +100,8 @@ err_t b2g_memcpy_async(void* dst, const void* src, size_t n, int to_device, void
    points forward to it — dlsym(RTLD_NEXT, name) — for inputs the GPU path does not cover
    (non-standard bign_params, a generic ec_o, scalars longer than the field, OID / t > 64 octets),
    for one-shot calls whose payload is below `bytes` (default 0 = never; also B2G_CPU_BELOW in the
-   environment), and when the GPU path of a `void` function fails (instead of abort()). */
+   environment), and when the GPU path of a `void` function fails (instead of abort()). A process that
+   dlopen()s this library names the stock library in B2G_STOCK_LIB instead (loaded privately). */
 void b2g_set_cpu_below(size_t bytes);
 int b2g_has_stock(void);           /* 1 if a stock libbee2 is reachable behind this library */
 u64 b2g_forward_count(void);       /* calls forwarded to it so far */

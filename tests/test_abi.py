@@ -92,3 +92,52 @@ def test_fails_loudly_without_cuda():
         b.beltCTR(bytes(32), bytes(32), bytes(16))
     assert e.value.code == b.ERR_B2G_NO_DEVICE
     assert b.bignVerify(b.bignParamsStd(), b.OID_BELT_HASH_DER, bytes(32), bytes(48), bytes(64)) == b.ERR_B2G_NO_DEVICE
+
+
+_NO_DEVICE_OVERLAY = r"""
+import ctypes as C, os, sys
+root = sys.argv[1]
+# a dlopen()ing process has no link order: the stock library is named in B2G_STOCK_LIB (engine.c: b2g_stock);
+# binaries that LINK both libraries / preload the engine are covered on the GPU box (test_gpu_reftests.py)
+os.environ["B2G_STOCK_LIB"] = os.path.join(root, "oracle", "_ref", "libbee2ref_64.so")
+eng = C.CDLL(os.path.join(root, "bee2_b200", "libbee2_b200.so"))
+ref = C.CDLL(os.path.join(root, "oracle", "_ref", "libbee2ref_64.so"))
+eng.b2g_has_stock.restype = C.c_int
+eng.b2g_forward_count.restype = C.c_uint64
+eng.beltH.restype = C.c_void_p
+assert eng.b2g_has_stock() == 1
+H = bytes((C.c_ubyte * 256).from_address(eng.beltH()))
+# err_t entry points never degrade: no device -> ERR_B2G_NO_DEVICE, nothing forwarded
+out = (C.c_ubyte * 32)()
+eng.bashHash.restype = C.c_uint32
+assert eng.bashHash(out, C.c_size_t(128), H, C.c_size_t(13)) == 9001
+assert eng.b2g_forward_count() == 0
+# a void drop-in cannot report: with stock libbee2 behind it is handed over (round 1: abort())
+st = (C.c_uint64 * 24).from_buffer_copy(H[:192])
+eng.bashF(st, None)
+assert eng.b2g_forward_count() == 1
+ref.bashF.restype = None
+st2 = (C.c_uint64 * 24).from_buffer_copy(H[:192])
+ref.bashF(st2, None)
+assert bytes(st) == bytes(st2) and bytes(st) != H[:192]
+print("OK")
+"""
+
+
+def test_no_device_void_dropin_goes_to_stock_and_err_t_fails_loudly():
+    """CPU box: with a stock libbee2 BEHIND the engine a `void` drop-in is forwarded (and says so on stderr),
+    an `err_t` entry point still returns ERR_B2G_NO_DEVICE — no silent CPU path."""
+    import subprocess
+    import sys
+    ref = os.path.join(ROOT, "oracle", "_ref", "libbee2ref_64.so")
+    if not os.path.exists(ref):
+        pytest.skip("reference library not built")
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present: the no-device path cannot be exercised")
+    except ImportError:
+        pass
+    r = subprocess.run([sys.executable, "-c", _NO_DEVICE_OVERLAY, ROOT], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+    assert "forwarding such calls to the stock libbee2" in r.stderr
