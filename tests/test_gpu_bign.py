@@ -510,3 +510,48 @@ def test_config4_shape_vs_reference_harness():
     assert dt > 0
     assert np.array_equal(got, want)
     assert (got == 0).sum() > n // 2
+
+
+@pytest.mark.parametrize("l", [128, 192, 256])
+def test_verify_ragged_counts_staged_and_pinned(l):
+    """Odd and ragged batch sizes through every input path of the verification kernel: pageable host buffers
+    (staging copies), pinned host buffers (zero-copy, TMA bulk copies straight from host memory), device
+    buffers, and a misaligned device view (per-thread loads). At l = 192 a signature is 72 octets, so a
+    ragged last CTA with an odd item count cannot be a bulk copy (multiples of 16 octets) and reads directly."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(7 * l)
+    p, no, oid = b.bignParamsStd(b.BIGN_CURVES[l]), l // 4, o.OIDS[l]
+    nmax = 515
+    priv = rng.integers(0, 256, (nmax, no), dtype=np.uint8)
+    priv[:, no - 1] &= 0x7F
+    hashes = rng.integers(0, 256, (nmax, no), dtype=np.uint8)
+    st, pubs = b.bignPubkeyCalcBatch(p, priv)
+    st2, sigs = b.bignSign2Batch(p, oid, hashes, priv)
+    assert not st.any() and not st2.any()
+    sigs[::3, 1] ^= 4
+    want_all = np.array([o.bignVerify(hashes[i].tobytes(), sigs[i].tobytes(), pubs[i].tobytes(), oid, l)
+                         for i in range(nmax)], dtype=np.uint32)
+    assert {0, 510} <= set(int(x) for x in want_all)
+    stream = torch.cuda.current_stream().cuda_stream
+    L = b.lib()
+    ko = np.frombuffer(oid, dtype=np.uint8)
+    for n in (1, 2, 3, 31, 127, 129, 255, 257, 383, 515):
+        want = want_all[:n]
+        # pageable host buffers
+        assert np.array_equal(b.bignVerifyBatch(p, oid, hashes[:n], sigs[:n], pubs[:n]), want), (l, n, "pageable")
+        # pinned host buffers: zero-copy
+        ph, ps, pp = (torch.from_numpy(x[:n].copy()).pin_memory() for x in (hashes, sigs, pubs))
+        pst = torch.empty(n, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        got = b.bignVerifyBatch(p, oid, ph.numpy(), ps.numpy(), pp.numpy(), status=pst)
+        assert np.array_equal(got, want), (l, n, "pinned")
+        # device buffers, aligned and shifted by one octet
+        for shift in (0, 1):
+            bufs = []
+            for x in (hashes, sigs, pubs):
+                t = torch.zeros(x[:n].size + 16, dtype=torch.uint8, device="cuda")
+                t[shift:shift + x[:n].size] = torch.from_numpy(x[:n].reshape(-1)).cuda()
+                bufs.append(t)
+            dst = torch.full((n,), 77, dtype=torch.int32, device="cuda")
+            assert L.b2g_bignVerifyBatchL_dev(l, dst.data_ptr(), ko.ctypes.data, len(oid), bufs[0].data_ptr() + shift,
+                                              bufs[1].data_ptr() + shift, bufs[2].data_ptr() + shift, n, stream) == 0
+            assert np.array_equal(dst.cpu().numpy().view(np.uint32), want), (l, n, "device", shift)

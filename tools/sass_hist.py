@@ -113,7 +113,7 @@ if __name__ == "__main__":
         "bash": report("bash.o", r"bash_sponge_kernel<8, 16>|bash_f_kernel"),
         "belt": report("belt.o", r"belt_ctr_kernel|belt_ecb_kernel<false, true>"),
         "belt_dwp": report("belt_dwp.o", r"belt_dwp_mac_kernel|belt_dwp_fused"),
-        "bign": report("bign.o", r"bign_verify_kernel<8>|bign_sign2_kernel<8>"),
+        "bign": report("bign.o", r"bign_verify_kernel<8, true>|bign_sign2_kernel<8>"),
     }
     json.dump(doc, sys.stdout, indent=1)
     print()
