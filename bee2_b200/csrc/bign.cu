@@ -62,6 +62,16 @@
 #define BIGN_MAX_OID 64
 #define BIGN_MAX_T 64
 
+// The device code up to and including the verification kernel lives in a namespace chosen by the including
+// translation unit: bign.cu itself (bign_std: out-of-line field products, 3 CTAs/SM at 80 registers — the
+// issue-bound shape for full grids) and bign_lowocc.cu (bign_lowocc: the same source compiled with every
+// product inlined and 1 CTA/SM — the latency-bound shape for grids of under ~2 warps per scheduler).
+#ifndef BIGN_NS
+#define BIGN_NS bign_std
+#endif
+struct OidArg { u8 der[BIGN_MAX_OID]; u32 len; };
+struct TArg { u8 t[BIGN_MAX_T]; u32 len; };
+namespace BIGN_NS {
 // q and the y-coordinate of G = (0, yG), little-endian limbs
 // (bign_params.c:61-73 curve256v1, :110-125 curve384v1, :169-190 curve512v1)
 __constant__ u32 c_q8[8] = {0x263D6607u, 0x7E5ABF99u, 0x0DFB4DFCu, 0xD95C8ED6u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
@@ -110,9 +120,6 @@ static std::atomic<uint4*> g_gtab[BIGN_MAX_DEV][3];
 #define BIGN_SBOX BeltT4
 #endif
 typedef BIGN_SBOX BignSbox;
-
-struct OidArg { u8 der[BIGN_MAX_OID]; u32 len; };
-struct TArg { u8 t[BIGN_MAX_T]; u32 len; };
 
 // ---------------------------------------------------------------- small helpers
 // q as a register array (constant-bank operands)
@@ -556,6 +563,26 @@ bign_verify_kernel(u32* __restrict__ status, const u8* __restrict__ hashes, cons
 		status[i] = st;
 }
 
+}   // namespace BIGN_NS
+using namespace BIGN_NS;
+
+#ifdef BIGN_LOWOCC_TU
+// ---------------------------------------------------------------- bign_lowocc.cu: launcher of the inlined build
+extern "C" u32 b2g_bign_lowocc_upload_tables(const u8 H[256]) { return belt_upload_H(H); }
+extern "C" u32 b2g_bign_verify8_lowocc(void* d_status, const OidArg* oid, const void* d_hashes, const void* d_sigs,
+	const void* d_pubkeys, size_t count, const void* gtab, u32 grid, u32 threads, int staged, void* stream)
+{
+	cudaStream_t st = (cudaStream_t)stream;
+	if (staged)
+		bign_verify_kernel<8, true><<<grid, threads, 0, st>>>((u32*)d_status, (const u8*)d_hashes, (const u8*)d_sigs,
+			(const u8*)d_pubkeys, count, *oid, (const uint4*)gtab);
+	else
+		bign_verify_kernel<8, false><<<grid, threads, 0, st>>>((u32*)d_status, (const u8*)d_hashes, (const u8*)d_sigs,
+			(const u8*)d_pubkeys, count, *oid, (const uint4*)gtab);
+	b2g_note_launch();
+	return b2g_check_launch("bign_verify_kernel (low-occupancy build)");
+}
+#else
 // belt-WBL encryption of NB = 2, 3, 4 blocks: 2 NB rounds (belt_wbl.c:50-82, round reset :203).
 // Round: S = r_1 ^ ... ^ r_{NB-1}; r <- (r_2, ..., r_NB ^ E(S) ^ <round>, S)
 template <int NB> __device__ __forceinline__ void wbl(const BignSbox& S, u32 (&r)[4 * NB], const u32 (&key)[8])
@@ -868,7 +895,12 @@ template <int N> __global__ void ecp_sum_kernel(u8* __restrict__ out, int* __res
 
 // ---------------------------------------------------------------- launchers (C ABI)
 // q and yG are static constants, GTAB is built lazily; only the belt S-box needs uploading
-extern "C" u32 b2g_bign_upload_tables(const u8 H[256]) { return belt_upload_H(H); }
+extern "C" u32 b2g_bign_lowocc_upload_tables(const u8 H[256]);   // bign_lowocc.cu
+extern "C" u32 b2g_bign_upload_tables(const u8 H[256])
+{
+	const u32 e = belt_upload_H(H);
+	return e ? e : b2g_bign_lowocc_upload_tables(H);   // the second build has its own copy of the S-box
+}
 
 template <int N> static u32 bign_build_gtab(cudaStream_t st, uint4** out)
 {
@@ -948,6 +980,9 @@ template <int N> static inline u32 bign_threads(size_t count)
 }
 template <int N> static inline u32 bign_grid(size_t count, u32 threads) { return (u32)((count + threads - 1) / threads); }
 
+extern "C" u32 b2g_bign_verify8_lowocc(void* d_status, const OidArg* oid, const void* d_hashes, const void* d_sigs,
+	const void* d_pubkeys, size_t count, const void* gtab, u32 grid, u32 threads, int staged, void* stream);
+extern "C" u32 b2g_bign_lowocc_upload_tables(const u8 H[256]);
 template <int N> static u32 verify_launch(void* d_status, const OidArg& oid, const void* d_hashes, const void* d_sigs,
 	const void* d_pubkeys, size_t count, cudaStream_t st)
 {
@@ -959,6 +994,12 @@ template <int N> static u32 verify_launch(void* d_status, const OidArg& oid, con
 	static const bool no_staging = getenv("B2G_NO_STAGING") != 0;
 	const bool staged = !no_staging && (((uintptr_t)d_hashes | (uintptr_t)d_sigs | (uintptr_t)d_pubkeys) & 15) == 0;
 	const u32 threads = bign_threads<N>(count), grid = bign_grid<N>(count, threads);
+	// A small grid (a shard of a strong-scaled batch: 2^15 items = one CTA per SM, under two warps per
+	// scheduler) is latency-bound, not issue-bound: the build with every field product inlined gives the
+	// scheduler independent chains to interleave. Measured, 2^15 / 2^16 / 2^17 / 2^18 items: out-of-line
+	// products 0.978 / 1.537 / 2.650 / 4.835 ms, inlined 0.813 / 1.605 / 3.216 / 5.729 ms.
+	if (N == 8 && count <= (size_t)b2g_sm_count() * 320 && !getenv("B2G_NO_LOWOCC"))
+		return b2g_bign_verify8_lowocc(d_status, &oid, d_hashes, d_sigs, d_pubkeys, count, gtab, grid, threads, staged, st);
 	if (staged)
 		bign_verify_kernel<N, true><<<grid, threads, 0, st>>>((u32*)d_status, (const u8*)d_hashes,
 			(const u8*)d_sigs, (const u8*)d_pubkeys, count, oid, gtab);
@@ -1209,3 +1250,4 @@ extern "C" u32 b2g_ecSumL_dev(size_t l, void* d_out, void* d_ok_out, const void*
 	return BIGN_DISPATCH(l, CALL);
 #undef CALL
 }
+#endif   // !BIGN_LOWOCC_TU

@@ -23,9 +23,23 @@ def test_config2_belt_ctr_1GiB():
     ks = torch.empty(n, dtype=torch.uint8, device="cuda")
     b.beltCTR_dev(ks.data_ptr(), 0, n, key, ctr, 0, _stream())
     torch.cuda.synchronize()
-    # oracle on the head and on a window deep inside the stream (via the counter offset)
+    # the head of the stream against the port AND the unmodified reference
     head = 1 << 20
     assert ks[:head].cpu().numpy().tobytes() == o.beltCTR(bytes(head), H[128:160], H[192:208])
+    if o.ref() is not None:
+        assert ks[:head].cpu().numpy().tobytes() == o.ref_beltCTR(bytes(head), H[128:160], H[192:208])
+    # windows DEEP inside the stream (middle, last MiB, across the 2^32-block... the low counter word carries
+    # at block 2^32 - ctr0, far beyond 1 GiB, so the carry case is covered by test_gpu_belt's counter-wrap test):
+    # keystream block j is E_K(s + j + 1) with s = E_K(iv) as a 128-bit LE integer (belt_ctr.c:27-35, :55-111),
+    # computed here with the checkers' ECB on explicitly built counter blocks
+    s0 = int.from_bytes(o.beltECBEncr(H[192:208], H[128:160]), "little")
+    for first in ((n >> 5) + 12345, (n >> 4) - (1 << 12)):            # block indices: mid-stream, the last 64 KiB
+        cnt_blocks = 1 << 12
+        ctrs = b"".join(((s0 + first + j + 1) % (1 << 128)).to_bytes(16, "little") for j in range(cnt_blocks))
+        want = o.beltECBEncr(ctrs, H[128:160])
+        assert ks[16 * first:16 * (first + cnt_blocks)].cpu().numpy().tobytes() == want
+        if o.ref() is not None:
+            assert o.ref_beltECBEncr(ctrs, H[128:160]) == want
     # 8-way sharding by block offset reproduces the same stream (what N ranks compute)
     part = torch.empty(n // 8, dtype=torch.uint8, device="cuda")
     for r in (0, 3, 7):
@@ -58,7 +72,10 @@ def test_config3_bash512_2pow20_messages():
     idx = np.random.default_rng(0).integers(0, cnt, 96)
     host = out.cpu().numpy()
     for i in list(idx) + [0, cnt - 1]:
-        assert host[i].tobytes() == o.bashHash(256, msgs[int(i)].cpu().numpy().tobytes())
+        m = msgs[int(i)].cpu().numpy().tobytes()
+        assert host[i].tobytes() == o.bashHash(256, m)
+        if o.ref() is not None and i % 3 == 0:
+            assert host[i].tobytes() == o.ref_bashHash(256, m)
     # duplicates hash alike, single-bit changes do not: copy message 0 over message 1, flip a bit in 2
     msgs[1] = msgs[0]
     msgs[2, 4095] ^= 1
@@ -98,6 +115,22 @@ def test_config4_bign_verify_2pow18():
     assert np.array_equal(got, want)
     for i in rng.integers(0, n, 48):
         assert got[i] == o.bignVerify(hashes[i].tobytes(), sigs[i].tobytes(), pubs[i].tobytes())
+    # 2^15 items of the batch (every 8th: half of them corrupted, all four kinds) against the UNMODIFIED
+    # reference's bign128Verify, fanned out over the host threads by oracle/cpu_harness.c
+    if o.ref() is not None:
+        import ctypes as C
+        import os
+        sel = np.arange(0, n, 8)
+        hs, ss, ps = (np.ascontiguousarray(x[sel]) for x in (hashes, sigs, pubs))
+        harness = C.CDLL(os.path.join(o.REF_DIR, "libcpuharness.so"))
+        harness.harness_bign_verify.restype = C.c_double
+        st_ref = np.zeros(len(sel), dtype=np.uint32)
+        dt = harness.harness_bign_verify(os.path.join(o.REF_DIR, "libbee2ref_64.so").encode(), 0,
+                                         st_ref.ctypes.data_as(C.c_void_p), hs.ctypes.data_as(C.c_void_p),
+                                         ss.ctypes.data_as(C.c_void_p), ps.ctypes.data_as(C.c_void_p),
+                                         C.c_size_t(len(sel)), len(os.sched_getaffinity(0)))
+        assert dt > 0 and np.array_equal(st_ref, got[sel])
+        assert {0, 505, 510} <= set(int(x) for x in st_ref)
 
 
 def test_config5_belt_ecb_2pow26_keys():
@@ -110,7 +143,11 @@ def test_config5_belt_ecb_2pow26_keys():
     pk, pb = keys[tidx].cpu().numpy(), blocks[tidx].cpu().numpy()
     b.beltECBEncrBatch_dev(blocks.data_ptr(), keys.data_ptr(), cnt, _stream())
     torch.cuda.synchronize()
-    assert np.array_equal(blocks[tidx].cpu().numpy(), o.beltECBEncrMultiKey(pb, pk))
+    enc = blocks[tidx].cpu().numpy()
+    assert np.array_equal(enc, o.beltECBEncrMultiKey(pb, pk))
+    if o.ref() is not None:
+        for j in range(0, len(idx), 25):
+            assert enc[j].tobytes() == o.ref_beltECBEncr(pb[j].tobytes(), pk[j].tobytes())
     # same key + same block -> same ciphertext, wherever it sits in the batch
     keys[5] = keys[cnt - 7]
     blocks[5] = 7

@@ -12,7 +12,7 @@ mkdir -p $obj
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC \
   -Xcompiler -fvisibility=default -diag-suppress 20044 $extra -c -o $obj/$file.o $src/$file.cu
 objs=""
-for f in bash belt bign microbench belt_dwp engine host_bash host_belt host_bign; do
+for f in bash belt bign bign_lowocc microbench belt_dwp engine host_bash host_belt host_bign; do
   if [ $f = $file ]; then objs="$objs $obj/$f.o"; else objs="$objs $src/build/$f.o"; fi
 done
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -Xlinker -Bsymbolic \
