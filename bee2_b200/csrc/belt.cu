@@ -340,6 +340,28 @@ extern "C" u32 b2g_beltCHE_dev(void* d_dest, const void* d_src, size_t count, co
 	return b2g_check_launch("belt_che_kernel");
 }
 
+// A handful of blocks under one key (beltBlockEncr and friends, the E_K(iv) of beltCTRStart, ciphertext
+// stealing): one small CTA per 128 blocks with the 4 KiB four-table S-box instead of a 1024-thread CTA that
+// first fills the 128 KiB bank-replicated tables. Latency path, not a throughput path.
+#define BELT_SMALL_BLOCKS 4096
+template <bool DEC> __global__ void __launch_bounds__(128) belt_ecb_small_kernel(uint4* dst, const uint4* src,
+	u32 nblocks, const BeltKey key)
+{
+	__shared__ u32 tab[BeltT4::WORDS];
+	BeltT4::fill(tab);
+	__syncthreads();
+	const BeltT4 S(tab);
+	const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= nblocks)
+		return;
+	uint4 v = src[j];
+	if (DEC)
+		belt_decr(S, v.x, v.y, v.z, v.w, key.k);
+	else
+		belt_encr(S, v.x, v.y, v.z, v.w, key.k);
+	dst[j] = v;
+}
+
 extern "C" u32 b2g_beltECB_dev(void* d_dest, const void* d_src, size_t nblocks, const u32 key[8],
 	int decrypt, void* stream)
 {
@@ -350,6 +372,16 @@ extern "C" u32 b2g_beltECB_dev(void* d_dest, const void* d_src, size_t nblocks, 
 	BeltKey k;
 	for (int i = 0; i < 8; ++i) k.k[i] = key[i];
 	cudaStream_t st = (cudaStream_t)stream;
+	if (nblocks <= BELT_SMALL_BLOCKS)
+	{
+		const u32 grid = (u32)((nblocks + 127) / 128);
+		if (decrypt)
+			belt_ecb_small_kernel<true><<<grid, 128, 0, st>>>((uint4*)d_dest, (const uint4*)d_src, (u32)nblocks, k);
+		else
+			belt_ecb_small_kernel<false><<<grid, 128, 0, st>>>((uint4*)d_dest, (const uint4*)d_src, (u32)nblocks, k);
+		b2g_note_launch();
+		return b2g_check_launch("belt_ecb_small_kernel");
+	}
 	if (decrypt)
 	{
 		belt_ecb_kernel<true, false><<<belt_grid(nblocks), BELT_THREADS, BELT_BIGT_BYTES, st>>>(

@@ -1014,6 +1014,11 @@ def main():
             "roofline": h["roofline"], "issue_roofline": h.get("issue_roofline"),
             "cpu_baseline": h.get("cpu_baseline"), "e2e": h.get("e2e"), "gather": h.get("gather"), "gpu_launches": h["gpu_launches"],
             "clocks": clocks, "issue_peaks_Tops": issue,
+            # the architectural per-SM rates x 148 SMs x max SM clock, beside the measured ones
+            "issue_peaks_arch_Tops": (lambda c: {"alu (lop3/shf/prmt/iadd) 64/clk/SM": 64 * 148 * c / 1e6,
+                                                 "imad 64/clk/SM": 64 * 148 * c / 1e6, "lds32 32/clk/SM": 32 * 148 * c / 1e6,
+                                                 "imad_wide plain 64/clk/SM, carry-chained 32/clk/SM": [64 * 148 * c / 1e6, 32 * 148 * c / 1e6]})(
+                float(clocks.get("sm_max_mhz") or 1965)),
             "paths": {k: v for k, v in results.items() if k != head}, "strong": strong,
             "also": {k: compact(v) for k, v in results.items()}}
     sys.stdout.flush()

@@ -294,6 +294,10 @@ err_t bignParamsStd(bign_params* params, const char* name);
    (bign128.c:177-185, bign192.c, bign256.c), which only fix the level and the hash OID. */
 err_t bignVerify(const bign_params* params, const octet oid_der[], size_t oid_len,
 	const octet hash[], const octet sig[], const octet pubkey[]);
+/* GPU-path limits of the bign entry points (they are staged as kernel arguments): the DER of the hash OID
+   and bignSign2's optional `t` up to 64 octets each; the three standard parameter blocks. Beyond that the
+   call goes to the stock libbee2 behind this library when there is one (overlay mode, see b2g_set_cpu_below)
+   and returns ERR_NOT_IMPLEMENTED otherwise — the reference (bign_sign.c:198-206) takes any length. */
 err_t bignSign2(octet sig[], const bign_params* params, const octet oid_der[], size_t oid_len,
 	const octet hash[], const octet privkey[], const void* t, size_t t_len);
 err_t bignPubkeyCalc(octet pubkey[], const bign_params* params, const octet privkey[]);
