@@ -62,16 +62,19 @@
 #define BIGN_MAX_OID 64
 #define BIGN_MAX_T 64
 
-// The device code up to and including the verification kernel lives in a namespace chosen by the including
-// translation unit: bign.cu itself (bign_std: out-of-line field products, 3 CTAs/SM at 80 registers — the
-// issue-bound shape for full grids) and bign_lowocc.cu (bign_lowocc: the same source compiled with every
-// product inlined and 1 CTA/SM — the latency-bound shape for grids of under ~2 warps per scheduler).
-#ifndef BIGN_NS
-#define BIGN_NS bign_std
-#endif
+// The device code up to and including the verification kernel is compiled twice: by bign.cu itself
+// (out-of-line field products, 3 CTAs/SM at 80 registers — the issue-bound shape for full grids) and, inside
+// namespace bign_lowocc, by bign_lowocc.cu (the same source with every product inlined and 1 CTA/SM — the
+// latency-bound shape for grids of under ~2 warps per scheduler).
+// (Only the second build is wrapped: putting bign.cu's own copy into a namespace as well changed nothing but
+// the mangled names, yet ptxas laid the functions out differently and the full-grid kernel lost 3 % —
+// 4.979 against 4.831 ms for 2^18 items, same box, A/B — which says how close to the instruction-cache
+// edge this 166 KB kernel runs.)
 struct OidArg { u8 der[BIGN_MAX_OID]; u32 len; };
 struct TArg { u8 t[BIGN_MAX_T]; u32 len; };
-namespace BIGN_NS {
+#ifdef BIGN_LOWOCC_TU
+namespace bign_lowocc {
+#endif
 // q and the y-coordinate of G = (0, yG), little-endian limbs
 // (bign_params.c:61-73 curve256v1, :110-125 curve384v1, :169-190 curve512v1)
 __constant__ u32 c_q8[8] = {0x263D6607u, 0x7E5ABF99u, 0x0DFB4DFCu, 0xD95C8ED6u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
@@ -563,10 +566,10 @@ bign_verify_kernel(u32* __restrict__ status, const u8* __restrict__ hashes, cons
 		status[i] = st;
 }
 
-}   // namespace BIGN_NS
-using namespace BIGN_NS;
-
 #ifdef BIGN_LOWOCC_TU
+}   // namespace bign_lowocc
+using namespace bign_lowocc;
+
 // ---------------------------------------------------------------- bign_lowocc.cu: launcher of the inlined build
 extern "C" u32 b2g_bign_lowocc_upload_tables(const u8 H[256]) { return belt_upload_H(H); }
 extern "C" u32 b2g_bign_verify8_lowocc(void* d_status, const OidArg* oid, const void* d_hashes, const void* d_sigs,

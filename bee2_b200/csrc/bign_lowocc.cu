@@ -10,5 +10,4 @@
 #define FE_MUL_INLINE 1
 #define BIGN_MIN_BLOCKS 1
 #define BIGN_LOWOCC_TU 1
-#define BIGN_NS bign_lowocc
 #include "bign.cu"

@@ -14,7 +14,10 @@ sys.path.insert(0, __file__.rsplit("/", 1)[0])
 from sass_hist import classify  # noqa: E402
 
 rep, items = sys.argv[1], int(sys.argv[2])
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):            # already exported on the GPU box: ncu -i x.ncu-rep --page source --csv
+    out = open(rep).read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 kernel = rows[0][1]
 hdr = rows[1]
