@@ -612,27 +612,64 @@ template <int NB> __device__ __forceinline__ void wbl(const BignSbox& S, u32 (&r
 	}
 }
 
-// bignSign2Ec per item (bign_sign.c:140-245)
-template <int N> __global__ void __launch_bounds__(BIGN_T(N), BIGN_BLOCKS(N))
+// bignSign2Ec per item (bign_sign.c:140-245).
+// STAGED (hashes, private keys and signatures 16-byte aligned, no caller-supplied nonces): the CTA's two input
+// segments arrive by TMA bulk copies and its signatures leave by one bulk store, through the memory that holds
+// the product tree in between — with pinned host buffers bignSign2Batch then runs zero-copy, and the private
+// keys never rest in device memory.
+#define BIGN_SIGN_SMEM_BYTES(N) (BIGN_T(N) * 8 * (N) > 4 * BIGN_TREE_WORDS(N) ? BIGN_T(N) * 8 * (N) : 4 * BIGN_TREE_WORDS(N))
+template <int N, bool STAGED> __global__ void __launch_bounds__(BIGN_T(N), BIGN_BLOCKS(N))
 bign_sign2_kernel(u32* __restrict__ status, u8* __restrict__ sigs, const u8* __restrict__ hashes,
 	const u8* __restrict__ privkeys, u64 count, const OidArg oid, const TArg targ,
 	const uint4* __restrict__ gtab, const u8* __restrict__ nonces)
 {
-	constexpr int NO = 4 * N, H2 = N / 2;
+	constexpr int NO = 4 * N, H2 = N / 2, SO = NO + NO / 2;
 	__shared__ u32 tab[BignSbox::WORDS];
-	__shared__ u32 tree[BIGN_TREE_WORDS(N)];
+	__shared__ __align__(16) u8 smem[BIGN_SIGN_SMEM_BYTES(N)];
+	__shared__ u64 mbar;
+	u32* tree = reinterpret_cast<u32*>(smem);
 	BignSbox::fill(tab);
-	__syncthreads();
+	const u64 i0 = (u64)blockIdx.x * blockDim.x;
+	const u64 i = i0 + threadIdx.x;
+	const u32 n = (u32)(count - i0 < blockDim.x ? count - i0 : blockDim.x);   // items of this CTA
+	// bulk copies move multiples of 16 octets: l = 192 items are 48 / 72 octets, a ragged odd tail goes direct
+	const bool staged = STAGED && ((n * SO) & 15u) == 0;
+	const u8 *p_hash = hashes + NO * i, *p_key = privkeys + NO * i;
+	if (staged)
+	{
+		if (threadIdx.x == 0)
+			mbar_init(&mbar, 1);
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			mbar_expect_tx(&mbar, 2 * n * NO);
+			bulk_g2s(smem, hashes + NO * i0, n * NO, &mbar);
+			bulk_g2s(smem + BIGN_T(N) * NO, privkeys + NO * i0, n * NO, &mbar);
+		}
+		mbar_wait(&mbar, 0);
+		p_hash = smem + NO * threadIdx.x, p_key = smem + BIGN_T(N) * NO + NO * threadIdx.x;
+	}
+	else
+		__syncthreads();
 	const BignSbox S(tab);
-	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	bool live = i < count;
 	u32 st = B2G_OK;
 	u32 d[N], H[N], k[N];
 	pt<N> R;
 	if (live)
 	{
-		load_uN<N>(d, privkeys + NO * i);
-		load_uN<N>(H, hashes + NO * i);
+		load_uN<N>(d, p_key);
+		load_uN<N>(H, p_hash);
+	}
+	if (staged)
+	{
+		__syncthreads();   // everybody has its inputs: wipe the staged private keys, the buffer becomes the tree
+		for (u32 w = threadIdx.x; w < BIGN_T(N) * NO / 4; w += blockDim.x)
+			reinterpret_cast<u32*>(smem + BIGN_T(N) * NO)[w] = 0;
+		__syncthreads();
+	}
+	if (live)
+	{
 		// 0 < d < q else BAD_PRIVKEY (:189-194)
 		if (uN_is_zero<N>(d) || geq_q<N>(d))
 			st = B2G_BAD_PRIVKEY, live = false;
@@ -672,6 +709,8 @@ bign_sign2_kernel(u32* __restrict__ status, u8* __restrict__ sigs, const u8* __r
 	else
 		fe_set_u32<N>(z, 1);
 	const fe<N> zi = block_inv<N>(z, tree);
+	if (staged)
+		__syncthreads();   // every thread has read its leaf: the tree's memory becomes the output segment
 	if (live)
 	{
 		fe<N> rx;
@@ -701,9 +740,43 @@ bign_sign2_kernel(u32* __restrict__ status, u8* __restrict__ sigs, const u8* __r
 		modq_reduce<N>(s1, prod, N + H2 + 1);
 		modq_sub<N>(s1, k, s1);
 		modq_sub<N>(s1, s1, H);   // H as is, not reduced first (zzSubMod, :237-238)
-		u8* o = sigs + (NO + NO / 2) * i;
-		for (int j = 0; j < NO / 2; ++j) o[j] = (u8)(hv[j >> 2] >> (8 * (j & 3)));
-		for (int j = 0; j < NO; ++j) o[NO / 2 + j] = (u8)(s1[j >> 2] >> (8 * (j & 3)));
+		if (staged)
+		{
+			// the signature goes to the CTA's output segment in shared memory (the tree is done with)
+			u32* o = reinterpret_cast<u32*>(smem + SO * threadIdx.x);
+#pragma unroll
+			for (int j = 0; j < H2; ++j) o[j] = hv[j];
+#pragma unroll
+			for (int j = 0; j < N; ++j) o[H2 + j] = s1[j];
+		}
+		else
+		{
+			u8* o = sigs + SO * i;
+			for (int j = 0; j < NO / 2; ++j) o[j] = (u8)(hv[j >> 2] >> (8 * (j & 3)));
+			for (int j = 0; j < NO; ++j) o[NO / 2 + j] = (u8)(s1[j >> 2] >> (8 * (j & 3)));
+		}
+	}
+	if (staged)
+	{
+		// one bulk store for the whole CTA when every item signed; otherwise only the successful items are
+		// written, each by its own thread (a failed item must leave the caller's buffer untouched, :240-245)
+		bulk_store_fence();
+		const int all_ok = __syncthreads_and(i >= count || st == B2G_OK);
+		if (all_ok)
+		{
+			if (threadIdx.x == 0)
+			{
+				bulk_s2g(sigs + SO * i0, smem, n * SO);
+				bulk_store_wait();
+			}
+		}
+		else if (live)
+		{
+			const u32* src = reinterpret_cast<const u32*>(smem + SO * threadIdx.x);
+			u32* dst = reinterpret_cast<u32*>(sigs + SO * i);   // 4-byte aligned: the base is 16-byte aligned
+#pragma unroll
+			for (int j = 0; j < SO / 4; ++j) dst[j] = src[j];
+		}
 	}
 	if (i < count)
 		status[i] = st;
@@ -1044,8 +1117,16 @@ template <int N> static u32 sign2_launch(void* d_status, void* d_sigs, const Oid
 	const uint4* gtab;
 	u32 e = bign_ensure_gtab<N>(st, &gtab);
 	if (e) return e;
-	bign_sign2_kernel<N><<<bign_grid<N>(count, bign_threads<N>(count)), bign_threads<N>(count), 0, st>>>((u32*)d_status, (u8*)d_sigs,
-		(const u8*)d_hashes, (const u8*)d_privkeys, count, oid, ta, gtab, (const u8*)d_nonces);
+	static const bool no_staging = getenv("B2G_NO_STAGING") != 0;
+	const bool staged = !no_staging && !d_nonces &&
+		(((uintptr_t)d_hashes | (uintptr_t)d_privkeys | (uintptr_t)d_sigs) & 15) == 0;
+	const u32 threads = bign_threads<N>(count), grid = bign_grid<N>(count, threads);
+	if (staged)
+		bign_sign2_kernel<N, true><<<grid, threads, 0, st>>>((u32*)d_status, (u8*)d_sigs,
+			(const u8*)d_hashes, (const u8*)d_privkeys, count, oid, ta, gtab, (const u8*)d_nonces);
+	else
+		bign_sign2_kernel<N, false><<<grid, threads, 0, st>>>((u32*)d_status, (u8*)d_sigs,
+			(const u8*)d_hashes, (const u8*)d_privkeys, count, oid, ta, gtab, (const u8*)d_nonces);
 	b2g_note_launch();
 	return b2g_check_launch("bign_sign2_kernel");
 }

@@ -75,3 +75,15 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity)
 		"@p bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}"
 		:: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+
+// shared -> global bulk store (cp.async.bulk, bulk-group completion). All threads that wrote the source
+// call bulk_store_fence() and then synchronise; ONE thread then calls bulk_s2g() and waits in
+// bulk_store_wait() before the shared buffer is reused or the CTA exits.
+__device__ __forceinline__ void bulk_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* dst_global, const void* src_smem, u32 bytes)
+{
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+		:: "l"(dst_global), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

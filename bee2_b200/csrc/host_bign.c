@@ -360,6 +360,20 @@ static err_t sign2_batch(err_t* status, octet* sigs, const bign_params* params, 
 		return ERR_OK;
 	b2g_lock();
 	s0 = b2g_slot_get(0), s1 = b2g_slot_get(1);
+	{
+		/* all four buffers pinned: one launch straight on host memory (zero-copy; the kernel stages its inputs
+		   and its signatures with TMA bulk copies and writes a signature only where the item signed) — the
+		   private keys then never rest in device memory */
+		void *z_h = pinned_dev_ptr(hashes), *z_k = pinned_dev_ptr(privkeys), *z_sig = pinned_dev_ptr(sigs),
+			*z_st = pinned_dev_ptr(status);
+		if (z_h && z_k && z_sig && z_st && !getenv("B2G_NO_ZEROCOPY"))
+		{
+			if ((code = b2g_bignSign2BatchL_t_dev(params->l, z_st, z_sig, oid_der, oid_len, z_h, z_k, count, t, t_len, s0->stream)))
+				goto done;
+			CU(cudaStreamSynchronize(s0->stream), "sync(bign sign2, zero-copy)");
+			goto done;
+		}
+	}
 	if ((code = stage_in(s0, 0, hashes, no * count, &d_h)) || (code = stage_in(s0, 1, privkeys, no * count, &d_k)) ||
 		(code = b2g_slot_buf(s0, 2, so * count, &d_sig)) || (code = b2g_slot_buf(s1, 0, 4 * count, &d_st)))
 		goto done;

@@ -59,9 +59,9 @@ CFG = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the bench
-# configuration, from the committed `ncu --set full` captures (profiles/r01_ncu_raw_*.csv)
-NCU_BIGN_WIDE_PER_VERIFY = 101600   # IMAD.WIDE(.X) executed per verify (profiles/r01_bign_opcode_mix.json)
-NCU_TRAFFIC = {"bign_sign2": 50.2e6 + 225.7e6, "belt_dwp": None, "belt_ecb": None, "belt_ctr": 0.13e6 + 1.0142e9, "bash512": 4.4244e9 + 14.5e6, "bign_verify": 6.8026e9 + 1.4227e9}
+# configuration, from the committed `ncu --set full` captures (profiles/r02_ncu_raw_*.csv)
+NCU_BIGN_WIDE_PER_VERIFY = 98317    # IMAD.WIDE(.X) executed per verify (profiles/r02_bign_opcode_mix.json)
+NCU_TRAFFIC = {"bign_sign2": 5.2655e+08, "belt_dwp": 1.0781e+09, "belt_ecb": 4.2635e+09, "belt_ctr": 1.0139e+09, "bash512": 4.4433e+09, "bign_verify": 8.8444e+09}
 
 
 def hbm_peak():
@@ -791,7 +791,7 @@ def main():
         r["gpu_launches"] = int(launches)
         ach = algo_bytes / (total / args.steps) / 1e9
         r["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": NCU_TRAFFIC.get(path), "traffic_source": "profiles/r01_ncu_raw_*.csv (bytes per launch)",
+                         "traffic": NCU_TRAFFIC.get(path), "traffic_source": "profiles/r02_ncu_raw_*.csv (bytes per launch; belt_dwp: the tag kernel only)",
                          "algorithmic_bytes": algo_bytes, "peak_source": peak_src,
                          "note": "integer-issue bound, not HBM bound (SURVEY §8d): see issue_roofline"}
         results[path] = r

@@ -555,3 +555,68 @@ def test_verify_ragged_counts_staged_and_pinned(l):
             assert L.b2g_bignVerifyBatchL_dev(l, dst.data_ptr(), ko.ctypes.data, len(oid), bufs[0].data_ptr() + shift,
                                               bufs[1].data_ptr() + shift, bufs[2].data_ptr() + shift, n, stream) == 0
             assert np.array_equal(dst.cpu().numpy().view(np.uint32), want), (l, n, "device", shift)
+
+
+@pytest.mark.parametrize("l", [128, 192, 256])
+def test_sign2_ragged_counts_staged_and_pinned(l):
+    """Every input path of the signing kernel at odd and ragged batch sizes: pageable host buffers (staging
+    copies), pinned host buffers (zero-copy: inputs by TMA bulk copies, signatures by one bulk store per CTA),
+    device buffers aligned (staged) and shifted by one octet (direct loads). Items that fail (d = 0, d >= q)
+    must leave their signature slot untouched (bign_sign.c:189-194), also inside a CTA whose other items
+    succeed — the kernel then drops the bulk store and writes item by item."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(11 * l)
+    p, no, oid = b.bignParamsStd(b.BIGN_CURVES[l]), l // 4, o.OIDS[l]
+    so, nmax = 3 * no // 2, 515
+    priv = rng.integers(0, 256, (nmax, no), dtype=np.uint8)
+    priv[:, no - 1] &= 0x7F
+    hashes = rng.integers(0, 256, (nmax, no), dtype=np.uint8)
+    want_sig = np.zeros((nmax, so), dtype=np.uint8)
+    step = 5 if l == 128 else 40
+    checked = sorted(set(range(0, nmax, step)) | {1, 2, 30, 126, 128, 254, 256, 382, 514})
+    for i in checked:
+        rc, s = o.bignSign2(hashes[i].tobytes(), priv[i].tobytes(), None, oid, l)
+        assert rc == 0
+        want_sig[i] = A(s)
+    stream = torch.cuda.current_stream().cuda_stream
+    L = b.lib()
+    ko = np.frombuffer(oid, dtype=np.uint8)
+    for bad in ((), (0, 300)):
+        pv = priv.copy()
+        for j, i in enumerate(bad):
+            pv[i] = 0 if j == 0 else 0xFF
+        for n in (1, 2, 3, 31, 127, 129, 255, 257, 383, 515):
+            ok = [i for i in checked if i < n and i not in bad]
+            dead = [i for i in bad if i < n]
+
+            def check(st, sg, tag):
+                assert all(st[i] == 0 for i in range(n) if i not in bad), (l, n, tag)
+                assert all(st[i] == b.ERR_BAD_PRIVKEY for i in dead), (l, n, tag)
+                assert np.array_equal(sg[ok], want_sig[ok]), (l, n, tag)
+                assert all((sg[i] == 0xA5).all() for i in dead), (l, n, tag, "failed item was written")
+
+            # pageable host buffers
+            sg = np.full((n, so), 0xA5, dtype=np.uint8)
+            st, sg = b.bignSign2Batch(p, oid, hashes[:n], pv[:n], sigs=sg)
+            check(st, sg, "pageable")
+            # pinned host buffers: zero-copy
+            ph, pk = (torch.from_numpy(x[:n].copy()).pin_memory() for x in (hashes, pv))
+            psg = torch.full((n, so), 0xA5, dtype=torch.uint8).pin_memory()
+            pst = torch.empty(n, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+            st, sg = b.bignSign2Batch(p, oid, ph.numpy(), pk.numpy(), status=pst, sigs=psg.numpy())
+            check(st, sg, "pinned")
+            # device buffers, aligned and shifted by one octet
+            for shift in (0, 1):
+                bufs = []
+                for x in (hashes, pv):
+                    t = torch.zeros(x[:n].size + 16, dtype=torch.uint8, device="cuda")
+                    t[shift:shift + x[:n].size] = torch.from_numpy(x[:n].reshape(-1)).cuda()
+                    bufs.append(t)
+                dsg = torch.full((n * so + 16,), 0xA5, dtype=torch.uint8, device="cuda")
+                dst = torch.full((n,), 77, dtype=torch.int32, device="cuda")
+                assert L.b2g_bignSign2BatchL_t_dev(l, dst.data_ptr(), dsg.data_ptr() + shift, ko.ctypes.data, len(oid),
+                                                   bufs[0].data_ptr() + shift, bufs[1].data_ptr() + shift, n, None, 0,
+                                                   stream) == 0
+                sg = dsg.cpu().numpy()[shift:shift + n * so].reshape(n, so)
+                assert (dsg.cpu().numpy()[shift + n * so:] == 0xA5).all() and (dsg.cpu().numpy()[:shift] == 0xA5).all()
+                check(dst.cpu().numpy().view(np.uint32), sg, ("device", shift))
