@@ -159,56 +159,77 @@ template <int N> __device__ __forceinline__ void modq_sub(u32* r, const u32* a, 
 	for (int i = 0; i < N; ++i) r[i] = m ? u[i] : t[i];
 }
 
-// x (n limbs, n <= 2N) mod q, q = 2^(32N) - c with c < 2^(32N - 1): fold hi * c into lo until
-// hi = 0 (zzMod, bign_sign.c:234). Plain 64-bit loops in local memory; runs once per signature.
-template <int N> __device__ __noinline__ void modq_reduce(u32* r, const u32* x, int n)
+// r = x mod q for x of N + N/2 + 1 limbs — the product (s0 + 2^l) d of the signature equation (zzMod,
+// bign_sign.c:234). q = 2^(32N) - c with a short c (4 / 7 / 8 limbs on the three curves: the top half of q
+// is all ones, bign_params.c:61-66, :110-117, :169-180), so x = lo + hi 2^(32N) = lo + hi c (mod q):
+// one fold with the (N/2 + 1)-limb hi, two more with the single limb that is left, one conditional
+// subtraction. Fixed shapes, fully unrolled, everything in registers (the first version — generic loops over
+// local-memory arrays — was 15 % of the instructions of a signature).
+template <int N> struct bign_qc { static constexpr int CL = N == 8 ? 4 : N == 12 ? 7 : 8; };
+template <int N> __device__ __forceinline__ void modq_reduce(u32* r, const u32* x)
 {
-	u32 cur[2 * N], c[N], nxt[2 * N];
-	for (int i = 0; i < 2 * N; ++i) cur[i] = i < n ? x[i] : 0;
-	// c = 2^(32N) - q = -q mod 2^(32N); cl = its length in limbs
-	int cl = 0;
+	constexpr int HL = N / 2 + 1, CL = bign_qc<N>::CL, PL = HL + CL, TL = (PL > N ? PL : N) + 1;
+	u32 c[CL];
 	{
-		u64 b = 0;
-		for (int i = 0; i < N; ++i)
+		// c = -q mod 2^(32N): its limbs above CL are zero
+		u32 cy = 1;
+#pragma unroll
+		for (int i = 0; i < CL; ++i)
 		{
-			const u64 d = (u64)0 - bign_c<N>::q()[i] - b;
-			c[i] = (u32)d, b = (d >> 32) & 1;
-			if (c[i]) cl = i + 1;
+			const u64 v = (u64)(~bign_c<N>::q()[i]) + cy;
+			c[i] = (u32)v, cy = (u32)(v >> 32);
 		}
 	}
-	for (int round = 0; round < 8; ++round)
+	// P = hi * c, schoolbook: the carry of row a opens limb a + CL
+	u32 P[PL];
+#pragma unroll
+	for (int i = 0; i < PL; ++i) P[i] = 0;
+#pragma unroll
+	for (int a = 0; a < HL; ++a)
 	{
-		int hl = 0;
-		for (int i = 0; i < N; ++i)
-			if (cur[N + i]) hl = i + 1;
-		if (!hl) break;
-		for (int i = 0; i < 2 * N; ++i) nxt[i] = i < N ? cur[i] : 0;
-		for (int i = 0; i < hl; ++i)
+		u64 cy = 0;
+#pragma unroll
+		for (int b = 0; b < CL; ++b)
 		{
-			u64 carry = 0;
-			const u32 h = cur[N + i];
-			for (int j = 0; j < cl; ++j)
-			{
-				const u64 t = (u64)h * c[j] + nxt[i + j] + carry;
-				nxt[i + j] = (u32)t, carry = t >> 32;
-			}
-			for (int k = i + cl; carry && k < 2 * N; ++k)
-			{
-				const u64 t = (u64)nxt[k] + carry;
-				nxt[k] = (u32)t, carry = t >> 32;
-			}
+			const u64 v = (u64)x[N + a] * c[b] + P[a + b] + cy;
+			P[a + b] = (u32)v, cy = v >> 32;
 		}
-		for (int i = 0; i < 2 * N; ++i) cur[i] = nxt[i];
+		P[a + CL] = (u32)cy;
 	}
-	// now cur < 2^(32N); bring into [0, q)
-	for (int guard = 0; guard < 4 && geq_q<N>(cur); ++guard)
+	// t = lo + P
+	u32 t[TL];
 	{
-		u32 t[N], q[N];
+		u64 cy = 0;
+#pragma unroll
+		for (int i = 0; i < TL; ++i)
+		{
+			const u64 v = (u64)(i < N ? x[i] : 0u) + (i < PL ? P[i] : 0u) + cy;
+			t[i] = (u32)v, cy = v >> 32;
+		}
+	}
+	// what is left above 2^(32N) is a few bits in limb N (t < 2^(32N + 3)); after two more folds it is gone:
+	// t < 2^(32N) + 7c -> h <= 1 and then lo < 8c -> lo + c < 2^(32N)
+#pragma unroll
+	for (int round = 0; round < 2; ++round)
+	{
+		const u32 h = t[N];
+		u64 cy = 0;
+#pragma unroll
+		for (int i = 0; i < N; ++i)
+		{
+			const u64 v = (i < CL ? (u64)h * c[i] : 0ull) + t[i] + cy;
+			t[i] = (u32)v, cy = v >> 32;
+		}
+		t[N] = (u32)cy;
+	}
+	// t < 2^(32N) = q + c: at most one subtraction of q
+	{
+		u32 u[N], q[N];
 		load_q<N>(q);
-		(void)sub_n<N>(t, cur, q);
-		for (int i = 0; i < N; ++i) cur[i] = t[i];
+		const u32 m = sub_n<N>(u, t, q);
+#pragma unroll
+		for (int i = 0; i < N; ++i) r[i] = m ? t[i] : u[i];
 	}
-	for (int i = 0; i < N; ++i) r[i] = cur[i];
 }
 
 template <int N> __device__ __forceinline__ void load_uN(u32* r, const u8* p)
@@ -323,7 +344,8 @@ template <int N> __device__ __forceinline__ void tree_get(fe<N>& a, const u32* s
 #pragma unroll
 	for (int j = 0; j < N; ++j) a.v[j] = sm[j * (2 * BIGN_T(N)) + i];
 }
-template <int N> __device__ __noinline__ fe<N> block_inv(const fe<N> z, u32* sm)
+// CT = false: the root inversion may stop early (public inputs: verification)
+template <int N, bool CT = true> __device__ __noinline__ fe<N> block_inv(const fe<N> z, u32* sm)
 {
 	const int tid = threadIdx.x;
 	fe<N> a, b;
@@ -352,7 +374,7 @@ template <int N> __device__ __noinline__ fe<N> block_inv(const fe<N> z, u32* sm)
 	if (tid == 0)
 	{
 		tree_get<N>(a, sm, 1);
-		fe_inv<N>(a, a);
+		fe_inv<N, CT>(a, a);
 		tree_put<N>(sm, 1, a);
 	}
 #endif
@@ -442,7 +464,7 @@ template <int N> __global__ void __launch_bounds__(128) bign_gtab_kernel(uint4* 
 #define BIGN_SMEM_BYTES(N) (BIGN_STAGE_BYTES(N) > 4 * BIGN_TREE_WORDS(N) ? BIGN_STAGE_BYTES(N) : 4 * BIGN_TREE_WORDS(N))
 template <int N, bool STAGED> __global__ void __launch_bounds__(BIGN_T(N), BIGN_BLOCKS(N))
 bign_verify_kernel(u32* __restrict__ status, const u8* __restrict__ hashes, const u8* __restrict__ sigs,
-	const u8* __restrict__ pubkeys, u64 count, const OidArg oid, const uint4* __restrict__ gtab)
+	const u8* __restrict__ pubkeys, u64 count, const OidArg oid, const uint4* __restrict__ gtab, u8* __restrict__ wtab)
 {
 	constexpr int NO = 4 * N, H2 = N / 2;
 	__shared__ u32 tab[BignSbox::WORDS];
@@ -533,7 +555,10 @@ bign_verify_kernel(u32* __restrict__ status, const u8* __restrict__ hashes, cons
 			sc<N> k5;
 #pragma unroll
 			for (int k = 0; k < N; ++k) k5.w[k] = k < H2 ? s0[k] : (k == H2 ? 1u : 0u);
-			pt_mul_var<N>(R, k5, 16 * N + 1, qx, qy);
+			// the window table {1..16}Q lives in this CTA's part of the launch's scratch area (ecp.cuh win_global)
+			win_global<N> W;
+			W.base = wtab + i0 * win_global<N>::ITEM_BYTES + 32u * threadIdx.x, W.stride = 32u * blockDim.x;
+			pt_mul_var_g<N>(R, k5, 16 * N + 1, qx, qy, W);
 		}
 		{
 			sc<N> ks;
@@ -549,7 +574,7 @@ bign_verify_kernel(u32* __restrict__ status, const u8* __restrict__ hashes, cons
 		z = R.Z;
 	else
 		fe_set_u32<N>(z, 1);
-	const fe<N> zi = block_inv<N>(z, tree);
+	const fe<N> zi = block_inv<N, false>(z, tree);
 	if (live)
 	{
 		fe<N> rx;
@@ -573,15 +598,15 @@ using namespace bign_lowocc;
 // ---------------------------------------------------------------- bign_lowocc.cu: launcher of the inlined build
 extern "C" u32 b2g_bign_lowocc_upload_tables(const u8 H[256]) { return belt_upload_H(H); }
 extern "C" u32 b2g_bign_verify8_lowocc(void* d_status, const OidArg* oid, const void* d_hashes, const void* d_sigs,
-	const void* d_pubkeys, size_t count, const void* gtab, u32 grid, u32 threads, int staged, void* stream)
+	const void* d_pubkeys, size_t count, const void* gtab, void* wtab, u32 grid, u32 threads, int staged, void* stream)
 {
 	cudaStream_t st = (cudaStream_t)stream;
 	if (staged)
 		bign_verify_kernel<8, true><<<grid, threads, 0, st>>>((u32*)d_status, (const u8*)d_hashes, (const u8*)d_sigs,
-			(const u8*)d_pubkeys, count, *oid, (const uint4*)gtab);
+			(const u8*)d_pubkeys, count, *oid, (const uint4*)gtab, (u8*)wtab);
 	else
 		bign_verify_kernel<8, false><<<grid, threads, 0, st>>>((u32*)d_status, (const u8*)d_hashes, (const u8*)d_sigs,
-			(const u8*)d_pubkeys, count, *oid, (const uint4*)gtab);
+			(const u8*)d_pubkeys, count, *oid, (const uint4*)gtab, (u8*)wtab);
 	b2g_note_launch();
 	return b2g_check_launch("bign_verify_kernel (low-occupancy build)");
 }
@@ -721,23 +746,32 @@ bign_sign2_kernel(u32* __restrict__ status, u8* __restrict__ sigs, const u8* __r
 		// s1 <- (k - (s0 + 2^l) d - H) mod q (:231-238)
 		u32 prod[N + H2 + 1];
 		{
-			u32 s0w[H2 + 1];
-			for (int j = 0; j < H2; ++j) s0w[j] = hv[j];
-			s0w[H2] = 1u;
+			// prod = s0 d + d 2^l: H2 rows of products, then d added at limb H2
+#pragma unroll
 			for (int j = 0; j < N + H2 + 1; ++j) prod[j] = 0;
-			for (int a = 0; a < H2 + 1; ++a)
+#pragma unroll
+			for (int a = 0; a < H2; ++a)
 			{
 				u64 carry = 0;
+#pragma unroll
 				for (int b = 0; b < N; ++b)
 				{
-					const u64 t = (u64)s0w[a] * d[b] + prod[a + b] + carry;
+					const u64 t = (u64)hv[a] * d[b] + prod[a + b] + carry;
 					prod[a + b] = (u32)t, carry = t >> 32;
 				}
 				prod[a + N] = (u32)carry;
 			}
+			u64 carry = 0;
+#pragma unroll
+			for (int b = 0; b < N; ++b)
+			{
+				const u64 t = (u64)d[b] + prod[H2 + b] + carry;
+				prod[H2 + b] = (u32)t, carry = t >> 32;
+			}
+			prod[H2 + N] = (u32)carry;
 		}
 		u32 s1[N];
-		modq_reduce<N>(s1, prod, N + H2 + 1);
+		modq_reduce<N>(s1, prod);
 		modq_sub<N>(s1, k, s1);
 		modq_sub<N>(s1, s1, H);   // H as is, not reduced first (zzSubMod, :237-238)
 		if (staged)
@@ -1057,11 +1091,36 @@ template <int N> static inline u32 bign_threads(size_t count)
 template <int N> static inline u32 bign_grid(size_t count, u32 threads) { return (u32)((count + threads - 1) / threads); }
 
 extern "C" u32 b2g_bign_verify8_lowocc(void* d_status, const OidArg* oid, const void* d_hashes, const void* d_sigs,
-	const void* d_pubkeys, size_t count, const void* gtab, u32 grid, u32 threads, int staged, void* stream);
+	const void* d_pubkeys, size_t count, const void* gtab, void* wtab, u32 grid, u32 threads, int staged, void* stream);
 extern "C" u32 b2g_bign_lowocc_upload_tables(const u8 H[256]);
+
+// Scratch for the per-thread window tables of a verification launch (ecp.cuh win_global): stream-ordered
+// allocations from the device's default pool, which is told to keep what it has (no trip to the driver per
+// launch after the first). Concurrent launches on different streams each get their own area.
+#ifndef BIGN_WTAB_CHUNK
+#define BIGN_WTAB_CHUNK ((size_t)1 << 20)   /* items per launch at most: 1.5 / 2.5 / 3 GiB of scratch */
+#endif
+static u32 wtab_alloc(void** p, size_t bytes, cudaStream_t st)
+{
+	static std::atomic<bool> tuned[BIGN_MAX_DEV];
+	const int dev = b2g_cur_dev();
+	if (!tuned[dev & (BIGN_MAX_DEV - 1)].exchange(true))
+	{
+		cudaMemPool_t pool;
+		unsigned long long keep = ~0ull;
+		if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+			(void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		(void)cudaGetLastError();
+	}
+	if (cudaMallocAsync(p, bytes, st) != cudaSuccess)
+		return b2g_check_launch("cudaMallocAsync(bign window tables)");
+	return B2G_OK;
+}
+
 template <int N> static u32 verify_launch(void* d_status, const OidArg& oid, const void* d_hashes, const void* d_sigs,
 	const void* d_pubkeys, size_t count, cudaStream_t st)
 {
+	constexpr size_t NO = 4 * N;
 	const uint4* gtab;
 	u32 e = bign_ensure_gtab<N>(st, &gtab);
 	if (e) return e;
@@ -1069,21 +1128,39 @@ template <int N> static u32 verify_launch(void* d_status, const OidArg& oid, con
 	// of 16 and so is every CTA size); B2G_NO_STAGING=1 keeps the per-thread loads (A/B measurement)
 	static const bool no_staging = getenv("B2G_NO_STAGING") != 0;
 	const bool staged = !no_staging && (((uintptr_t)d_hashes | (uintptr_t)d_sigs | (uintptr_t)d_pubkeys) & 15) == 0;
-	const u32 threads = bign_threads<N>(count), grid = bign_grid<N>(count, threads);
-	// A small grid (a shard of a strong-scaled batch: 2^15 items = one CTA per SM, under two warps per
-	// scheduler) is latency-bound, not issue-bound: the build with every field product inlined gives the
-	// scheduler independent chains to interleave. Measured, 2^15 / 2^16 / 2^17 / 2^18 items: out-of-line
-	// products 0.978 / 1.537 / 2.650 / 4.835 ms, inlined 0.813 / 1.605 / 3.216 / 5.729 ms.
-	if (N == 8 && count <= (size_t)b2g_sm_count() * 320 && !getenv("B2G_NO_LOWOCC"))
-		return b2g_bign_verify8_lowocc(d_status, &oid, d_hashes, d_sigs, d_pubkeys, count, gtab, grid, threads, staged, st);
-	if (staged)
-		bign_verify_kernel<N, true><<<grid, threads, 0, st>>>((u32*)d_status, (const u8*)d_hashes,
-			(const u8*)d_sigs, (const u8*)d_pubkeys, count, oid, gtab);
-	else
-		bign_verify_kernel<N, false><<<grid, threads, 0, st>>>((u32*)d_status, (const u8*)d_hashes,
-			(const u8*)d_sigs, (const u8*)d_pubkeys, count, oid, gtab);
-	b2g_note_launch();
-	return b2g_check_launch("bign_verify_kernel");
+	const size_t chunk = count < BIGN_WTAB_CHUNK ? count : BIGN_WTAB_CHUNK;
+	void* wtab = 0;
+	{
+		const u32 t = bign_threads<N>(chunk);
+		if ((e = wtab_alloc(&wtab, (size_t)bign_grid<N>(chunk, t) * t * win_global<N>::ITEM_BYTES, st)))
+			return e;
+	}
+	for (size_t off = 0; off < count && !e; off += chunk)
+	{
+		const size_t n = count - off < chunk ? count - off : chunk;
+		const u32 threads = bign_threads<N>(n), grid = bign_grid<N>(n, threads);
+		u32* p_st = (u32*)d_status + off;
+		const u8 *p_h = (const u8*)d_hashes + NO * off, *p_s = (const u8*)d_sigs + (NO + NO / 2) * off,
+			*p_q = (const u8*)d_pubkeys + 2 * NO * off;
+		// A small grid (a shard of a strong-scaled batch: 2^15 items = one CTA per SM, under two warps per
+		// scheduler) is latency-bound, not issue-bound: the build with every field product inlined gives the
+		// scheduler independent chains to interleave. Measured, 2^15 / 2^16 / 2^17 / 2^18 items: out-of-line
+		// products 0.978 / 1.537 / 2.650 / 4.835 ms, inlined 0.813 / 1.605 / 3.216 / 5.729 ms.
+		if (N == 8 && n <= (size_t)b2g_sm_count() * 320 && !getenv("B2G_NO_LOWOCC"))
+		{
+			e = b2g_bign_verify8_lowocc(p_st, &oid, p_h, p_s, p_q, n, gtab, wtab, grid, threads, staged, st);
+			continue;
+		}
+		if (staged)
+			bign_verify_kernel<N, true><<<grid, threads, 0, st>>>(p_st, p_h, p_s, p_q, n, oid, gtab, (u8*)wtab);
+		else
+			bign_verify_kernel<N, false><<<grid, threads, 0, st>>>(p_st, p_h, p_s, p_q, n, oid, gtab, (u8*)wtab);
+		b2g_note_launch();
+		e = b2g_check_launch("bign_verify_kernel");
+	}
+	if (cudaFreeAsync(wtab, st) != cudaSuccess && !e)
+		e = b2g_check_launch("cudaFreeAsync(bign window tables)");
+	return e;
 }
 
 // l = 128 / 192 / 256 -> dispatch on the limb count

@@ -204,20 +204,113 @@ template <int N> GFP_HD void pt_select(pt<N>& R, const pt<N>& P, u32 m)
 // data-dependent are the exceptional branches of pt_add (P = +-Q, probability ~ 2^-250 for an honest
 // scalar) and the top window. CT = false (public scalars: verification) keeps the direct, cheaper form.
 #define PT_WIN 5
-template <int N, bool CT = false> __host__ __device__ __noinline__ void pt_mul_var(pt<N>& acc, const sc<N> ks, int nbits,
-	const fe<N> x, const fe<N> y)
+#ifndef PT_WIN_V8
+#define PT_WIN_V8 0   /* 256-bit accesses: ptxas 12.9 crashes on them inside the verification kernel */
+#endif
+
+// ---- storage of the window table T[1..16]
+// win_local: a per-thread array, i.e. LOCAL memory, which the hardware interleaves over the lanes of a warp
+// (word k of all 32 lanes shares one 128-byte line). Ideal when every lane reads the SAME entry — the masked
+// scan of the CT form — and the worst case when every lane reads its OWN entry T[d]: a warp then touches
+// ~14 different lines per word, 24 words per entry, for 3 KB of useful data: 43 KB per window and warp,
+// 8.8 GB of DRAM traffic per 2^18 verifications (ncu r01 / r02: 212 x the algorithmic bytes).
+template <int N> struct win_local
 {
-	const u32* k = ks.w;
-	constexpr int HALF = 1 << (PT_WIN - 1);
-	pt<N> T[HALF + 1];   // T[j] = j * (x, y); T[0] unused. Dynamic indexing -> local memory.
-	pt_set_affine<N>(T[1], x, y);
-#pragma unroll 1
-	for (int j = 2; j <= HALF; ++j)
+	pt<N> T[(1 << (PT_WIN - 1)) + 1];   // T[0] unused
+	GFP_HD void put(int j, const pt<N>& P) { T[j] = P; }
+	GFP_HD void get(pt<N>& P, int j) const { P = T[j]; }
+};
+// win_global: the table in a GLOBAL scratch area of the CTA, laid out for the access pattern of the direct
+// form (public scalars: verification): an entry is G granules of 32 octets; granule g of entry j of thread t
+// lies at area + ((j - 1) G + g) * 32 T + 32 t (T threads per CTA). A put is G fully coalesced 256-bit stores
+// per warp, a get of the lane's own entry is G 256-bit loads of exactly the sectors that hold it — the table
+// costs its own size in traffic (16 x 96 B written once, 25 x 96 B read per verification at N = 8).
+// A thread only ever reads what it wrote itself: no fences.
+template <int N> struct win_global
+{
+	static constexpr int G = (12 * N + 31) / 32;
+	static constexpr size_t ITEM_BYTES = (size_t)(32 * G) << (PT_WIN - 1);   // per thread
+	u8* base;      // the CTA's area + 32 * threadIdx.x
+	u32 stride;    // 32 * blockDim.x
+	GFP_HD static u32 word(const pt<N>& P, int k) { return k < N ? P.X.v[k] : k < 2 * N ? P.Y.v[k - N] : k < 3 * N ? P.Z.v[k - 2 * N] : 0u; }
+	GFP_HD static void set_word(pt<N>& P, int k, u32 w)
 	{
-		if (j & 1)
-			pt_madd<N>(T[j], T[j - 1], x, y);
-		else
-			pt_dbl<N>(T[j], T[j >> 1]);
+		if (k < N) P.X.v[k] = w;
+		else if (k < 2 * N) P.Y.v[k - N] = w;
+		else if (k < 3 * N) P.Z.v[k - 2 * N] = w;
+	}
+	GFP_HD void put(int j, const pt<N>& P) const
+	{
+		u8* e = base + (size_t)((j - 1) * G) * stride;
+#pragma unroll
+		for (int g = 0; g < G; ++g)
+		{
+#ifdef __CUDA_ARCH__
+#if PT_WIN_V8
+			asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+				:: "l"(e + (size_t)g * stride), "r"(word(P, 8 * g)), "r"(word(P, 8 * g + 1)), "r"(word(P, 8 * g + 2)),
+				"r"(word(P, 8 * g + 3)), "r"(word(P, 8 * g + 4)), "r"(word(P, 8 * g + 5)), "r"(word(P, 8 * g + 6)),
+				"r"(word(P, 8 * g + 7)) : "memory");
+#else
+#pragma unroll
+			for (int h = 0; h < 2; ++h)
+				asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};"
+					:: "l"(e + (size_t)g * stride + 16 * h), "r"(word(P, 8 * g + 4 * h)), "r"(word(P, 8 * g + 4 * h + 1)),
+					"r"(word(P, 8 * g + 4 * h + 2)), "r"(word(P, 8 * g + 4 * h + 3)) : "memory");
+#endif
+#else
+			for (int k = 0; k < 8; ++k) reinterpret_cast<u32*>(e + (size_t)g * stride)[k] = word(P, 8 * g + k);
+#endif
+		}
+	}
+	GFP_HD void get(pt<N>& P, int j) const
+	{
+		const u8* e = base + (size_t)((j - 1) * G) * stride;
+#pragma unroll
+		for (int g = 0; g < G; ++g)
+		{
+			u32 w[8];
+#ifdef __CUDA_ARCH__
+#if PT_WIN_V8
+			asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+				: "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+				: "l"(e + (size_t)g * stride) : "memory");
+#else
+#pragma unroll
+			for (int h = 0; h < 2; ++h)
+				asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+					: "=r"(w[4 * h]), "=r"(w[4 * h + 1]), "=r"(w[4 * h + 2]), "=r"(w[4 * h + 3])
+					: "l"(e + (size_t)g * stride + 16 * h) : "memory");
+#endif
+#else
+			for (int k = 0; k < 8; ++k) w[k] = reinterpret_cast<const u32*>(e + (size_t)g * stride)[k];
+#endif
+#pragma unroll
+			for (int k = 0; k < 8; ++k) set_word(P, 8 * g + k, w[k]);
+		}
+	}
+};
+
+template <int N, bool CT, class WIN> GFP_HD void pt_mul_var_w(pt<N>& acc, const u32* k, int nbits, const fe<N>& x, const fe<N>& y, WIN& T)
+{
+	constexpr int HALF = 1 << (PT_WIN - 1);
+	{
+		// T[j] = j * (x, y): 8 doublings + 7 mixed additions; an odd entry follows from the one just made
+		pt<N> cur;
+		pt_set_affine<N>(cur, x, y);
+		T.put(1, cur);
+#pragma unroll 1
+		for (int j = 2; j <= HALF; ++j)
+		{
+			if (j & 1)
+				pt_madd<N>(cur, cur, x, y);
+			else
+			{
+				T.get(cur, j >> 1);
+				pt_dbl<N>(cur, cur);
+			}
+			T.put(j, cur);
+		}
 	}
 	const int nw = nbits / PT_WIN + 1;
 	// carries of the recoding, least significant window first: bit i of cy = carry INTO window i
@@ -255,7 +348,7 @@ template <int N, bool CT = false> __host__ __device__ __noinline__ void pt_mul_v
 		w = (w & (2 * HALF - 1)) + ((cy[i >> 5] >> (i & 31)) & 1u);
 		const bool neg = w > HALF;
 		const u32 d = neg ? 2 * HALF - w : w;
-		if (CT)
+		if constexpr (CT)
 		{
 			// Q = T[d ? d : 1] by a scan over the whole table; -Q by a mask
 			const u32 dd = d | (u32)(d == 0);
@@ -268,7 +361,7 @@ template <int N, bool CT = false> __host__ __device__ __noinline__ void pt_mul_v
 				const u32 m = 0u - (u32)(j == dd);
 #pragma unroll
 				for (int k = 0; k < N; ++k)
-					Q.X.v[k] |= T[j].X.v[k] & m, Q.Y.v[k] |= T[j].Y.v[k] & m, Q.Z.v[k] |= T[j].Z.v[k] & m;
+					Q.X.v[k] |= T.T[j].X.v[k] & m, Q.Y.v[k] |= T.T[j].Y.v[k] & m, Q.Z.v[k] |= T.T[j].Z.v[k] & m;
 			}
 			{
 				fe<N> ny;
@@ -297,17 +390,32 @@ template <int N, bool CT = false> __host__ __device__ __noinline__ void pt_mul_v
 		{
 			// the top window only selects (no doublings of O); it is never negative
 			if (d)
-				acc = T[d];
+				T.get(acc, (int)d);
 			else
 				pt_set_inf<N>(acc);
 			first = false;
 		}
 		else if (d)
 		{
-			pt<N> Q = T[d];
+			pt<N> Q;
+			T.get(Q, (int)d);
 			if (neg)
 				fe_neg<N>(Q.Y, Q.Y);
 			pt_add<N>(acc, acc, Q);
 		}
 	}
+}
+
+// the out-of-line forms: table in local memory (CT = true: secret scalars; CT = false: table building) ...
+template <int N, bool CT = false> __host__ __device__ __noinline__ void pt_mul_var(pt<N>& acc, const sc<N> ks, int nbits,
+	const fe<N> x, const fe<N> y)
+{
+	win_local<N> T;
+	pt_mul_var_w<N, CT>(acc, ks.w, nbits, x, y, T);
+}
+// ... and in the caller's global scratch area (public scalars only: the verification kernel)
+template <int N> __host__ __device__ __noinline__ void pt_mul_var_g(pt<N>& acc, const sc<N> ks, int nbits,
+	const fe<N> x, const fe<N> y, win_global<N> T)
+{
+	pt_mul_var_w<N, false>(acc, ks.w, nbits, x, y, T);
 }

@@ -25,6 +25,7 @@
 // ripples further in a rare branch (probability ~ c / 2^32 per operation).
 #pragma once
 #include "gfp_asm.cuh"
+#include "gfp_inv.cuh"
 
 template <int N> struct fe { u32 v[N]; };
 
@@ -295,7 +296,7 @@ template <int N> GFP_HD void fe_sqr_n(fe<N>& r, const fe<N>& a, int n)
 // p - 2 = 2^(32N) - (c + 2): the top 32N - 16 bits are ones, the low 16 bits are
 // 0x10000 - (c + 2) = 0xFF41 / 0xFEC1 / 0xFDC5. An addition chain on runs of ones builds
 // a^(2^(32N-16) - 1), then the low 16 bits are appended bit by bit.
-template <int N> __host__ __device__ __noinline__ fe<N> fe_inv_fn(const fe<N> a)
+template <int N> __host__ __device__ __noinline__ fe<N> fe_inv_fermat_fn(const fe<N> a)
 {
 	fe<N> x2, x4, x8, x16, x32, x48, x64, x128, t;
 	fe_sqr<N>(t, a), fe_mul<N>(x2, t, a);                  // 2^2 - 1
@@ -336,7 +337,21 @@ template <int N> __host__ __device__ __noinline__ fe<N> fe_inv_fn(const fe<N> a)
 	}
 	return t;
 }
-template <int N> GFP_HD void fe_inv(fe<N>& r, const fe<N>& a) { r = fe_inv_fn<N>(a); }
+// r = 1/a (0 -> 0), canonical. The kernels use the division-step form (gfp_inv.cuh: a third of the power's
+// instructions and short dependent chains — it runs on one thread per CTA while the others wait); the power
+// stays as the cross-check of the host tests. CT = true: fixed step count (secret-dependent inputs).
+template <int N, bool CT> __host__ __device__ __noinline__ fe<N> fe_inv_fn(const fe<N> a)
+{
+	fe<N> r, c = a;
+	fe_canon<N>(c);   // the other weak form of 0 (p itself) must also give 0
+	inv_safegcd<N, CT>(r.v, c.v, fe_param<N>::C);
+	return r;
+}
+#ifdef FE_INV_FERMAT   /* A/B measurement only */
+template <int N, bool CT = true> GFP_HD void fe_inv(fe<N>& r, const fe<N>& a) { r = fe_inv_fermat_fn<N>(a); }
+#else
+template <int N, bool CT = true> GFP_HD void fe_inv(fe<N>& r, const fe<N>& a) { r = fe_inv_fn<N, CT>(a); }
+#endif
 
 // little-endian octets <-> limbs (unaligned-safe)
 template <int N> GFP_HD void fe_load(fe<N>& r, const u8* p)

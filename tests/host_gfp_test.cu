@@ -47,7 +47,15 @@ template <int N> static std::string run(const std::string& op, std::istringstrea
 		in >> ha;
 		from_hex<N>(a.v, ha);
 		if (op == "sqr") fe_sqr<N>(r, a);
-		else if (op == "inv") fe_inv<N>(r, a);
+		else if (op == "inv")
+		{
+			// the division-step form (fixed step count and early exit) and the power a^(p-2) must agree
+			fe<N> r2, r3;
+			fe_inv<N, true>(r, a), fe_inv<N, false>(r2, a);
+			r3 = fe_inv_fermat_fn<N>(a), fe_canon<N>(r3);
+			for (int i = 0; i < N; ++i)
+				if (r.v[i] != r2.v[i] || r.v[i] != r3.v[i]) return "inv-mismatch";
+		}
 		else if (op == "shl1") fe_shl<1, N>(r, a);
 		else if (op == "shl2") fe_shl<2, N>(r, a);
 		else if (op == "shl3") fe_shl<3, N>(r, a);

@@ -90,9 +90,9 @@ def test_field_ops(exe, n):
             lines.append(f"shl{k} {n} {a:x}"), want.append(("mod", (a << k) % p))
         lines.append(f"canon {n} {a:x}"), want.append(("raw", a % p if a < 2 * p else None))
         lines.append(f"iszero {n} {a:x}"), want.append(("raw", 1 if a % p == 0 else 0))
-    for a in vals[:30]:
-        if a % p:
-            lines.append(f"inv {n} {a:x}"), want.append(("mod", pow(a, -1, p)))
+    for a in vals + [rng.getrandbits(32 * n) for _ in range(200)]:
+        # canonical result (gfp_inv.cuh); 0 and p (the other weak form of 0) invert to 0
+        lines.append(f"inv {n} {a:x}"), want.append(("raw", pow(a, -1, p) if a % p else 0))
     got = run(exe, lines)
     for line, g, (kind, w) in zip(lines, got, want):
         v = int(g, 16)
