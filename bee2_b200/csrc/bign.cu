@@ -309,17 +309,39 @@ template <int N, bool CT = false> __device__ __noinline__ void pt_add_mul_base(p
 template <int N> __device__ __forceinline__ void hash_oid_ab(const BignSbox& S, u32 (&out)[8], const OidArg& oid,
 	const u32* a, const u32* b, const u8* extra, u32 extra_len)
 {
-	// message zero-padded to whole 32-octet blocks
+	// message zero-padded to whole 32-octet blocks, assembled word-wise: the DER string (zero-padded by
+	// make_oid) is copied as words, everything after it is shifted in by the octet phase of its position
 	u32 msg[(BIGN_MAX_OID + 8 * N + BIGN_MAX_T + 31) / 32 * 8];
-	u8* m8 = reinterpret_cast<u8*>(msg);
 	const int nw = (int)(sizeof(msg) / 4);
-	for (int i = 0; i < nw; ++i) msg[i] = 0;
-	u32 pos = 0;
-	for (u32 i = 0; i < oid.len; ++i) m8[pos++] = oid.der[i];
-	for (u32 i = 0; i < 4 * N; ++i) m8[pos++] = (u8)(a[i >> 2] >> (8 * (i & 3)));
+#pragma unroll
+	for (int i = 0; i < nw; ++i) msg[i] = i < BIGN_MAX_OID / 4 ? reinterpret_cast<const u32*>(oid.der)[i] : 0u;
+	u32 pos = oid.len;
+	const u32 sh = 8 * (pos & 3);
+	const auto append = [&](const u32* w, int nwords)
+	{
+		const u32 i0 = pos >> 2;
+		if (sh == 0)
+		{
+			for (int j = 0; j < nwords; ++j) msg[i0 + j] = w[j];
+		}
+		else
+		{
+			u32 lo = msg[i0];
+			for (int j = 0; j < nwords; ++j)
+				msg[i0 + j] = lo | (w[j] << sh), lo = w[j] >> (32 - sh);
+			msg[i0 + nwords] = lo;
+		}
+		pos += 4 * nwords;
+	};
+	append(a, N);
 	if (b)
-		for (u32 i = 0; i < 4 * N; ++i) m8[pos++] = (u8)(b[i >> 2] >> (8 * (i & 3)));
-	for (u32 i = 0; i < extra_len; ++i) m8[pos++] = extra[i];
+		append(b, N);
+	if (extra_len)
+	{
+		// t is zero-padded to BIGN_MAX_T octets (TArg): whole words may be appended, the length counts octets
+		append(reinterpret_cast<const u32*>(extra), (int)((extra_len + 3) >> 2));
+		pos = pos - 4 * ((extra_len + 3) >> 2) + extra_len;
+	}
 	const belt_digest dg = belt_hash_words(S, msg, pos);
 #pragma unroll
 	for (int i = 0; i < 8; ++i) out[i] = dg.w[i];
