@@ -45,21 +45,27 @@ template <int N, bool INL> PT_OP void pt_dbl_t(pt<N>& R, const pt<N>& P)
 {
 #define PM(r, a, b) (INL ? fe_mul_i<N>(r, a, b) : fe_mul<N>(r, a, b))
 #define PS(r, a) (INL ? fe_sqr_i<N>(r, a) : fe_sqr<N>(r, a))
+	// Order of evaluation = order of the calls (ptxas does not move them): chosen so that few values are
+	// alive across each call — Z3 first (Y and Z die), then alpha (delta dies), beta (X dies), ... — because
+	// whatever is alive across a call beyond the callee-saved registers is spilled around it.
+	// R may alias P: a coordinate of R is written only after the last read of that coordinate of P.
 	fe<N> delta, gamma, beta, alpha, t, u;
 	PS(delta, P.Z);
 	PS(gamma, P.Y);
-	PM(beta, P.X, gamma);
-	fe_sub<N>(t, P.X, delta), fe_add<N>(u, P.X, delta);
-	PM(alpha, t, u);
-	fe_dbl<N>(t, alpha), fe_add<N>(alpha, alpha, t);              // 3 (X - Z^2)(X + Z^2)
 	fe_add<N>(t, P.Y, P.Z), PS(t, t);
-	fe_sub<N>(t, t, gamma), fe_sub<N>(R.Z, t, delta);             // Z3 = (Y + Z)^2 - Y^2 - Z^2
+	fe_sub<N>(t, t, gamma), fe_sub<N>(t, t, delta);               // Z3 = (Y + Z)^2 - Y^2 - Z^2
+	fe_sub<N>(u, P.X, delta), fe_add<N>(delta, P.X, delta);
+	R.Z = t;
+	PM(alpha, u, delta);
+	fe_dbl<N>(t, alpha), fe_add<N>(alpha, alpha, t);              // 3 (X - Z^2)(X + Z^2)
+	PM(beta, P.X, gamma);
 	fe_shl<2, N>(beta, beta);                                     // 4 beta
-	PS(t, alpha);
-	fe_sub<N>(t, t, beta), fe_sub<N>(R.X, t, beta);               // X3 = alpha^2 - 8 beta
 	PS(gamma, gamma);
 	fe_shl<3, N>(gamma, gamma);                                   // 8 gamma^2
-	fe_sub<N>(t, beta, R.X), PM(t, alpha, t);
+	PS(t, alpha);
+	fe_sub<N>(t, t, beta), fe_sub<N>(t, t, beta);                 // X3 = alpha^2 - 8 beta
+	R.X = t;
+	fe_sub<N>(t, beta, t), PM(t, alpha, t);
 	fe_sub<N>(R.Y, t, gamma);                                     // Y3 = alpha (4 beta - X3) - 8 gamma^2
 #undef PM
 #undef PS

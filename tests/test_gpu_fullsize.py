@@ -155,3 +155,28 @@ def test_config5_belt_ecb_2pow26_keys():
     b.beltECBEncrBatch_dev(blocks.data_ptr(), keys.data_ptr(), cnt, _stream())
     torch.cuda.synchronize()
     assert torch.equal(blocks[5], blocks[cnt - 7])
+
+
+def test_bign_verify_beyond_one_launch_chunk():
+    """More items than one verification launch takes (bign.cu BIGN_WTAB_CHUNK = 2^20: the per-thread window
+    tables live in a stream-ordered scratch area sized per launch): 2^20 + 777 items are verified in two
+    launches; the batch is 2^12 distinct (hash, signature, key) triples, one in nine corrupted and each checked
+    against the oracle or the unmodified reference, tiled over the whole count."""
+    base, n = 1 << 12, (1 << 20) + 777
+    rng = np.random.default_rng(20)
+    p = b.bignParamsStd()
+    priv = rng.integers(0, 256, (base, 32), dtype=np.uint8)
+    priv[:, 31] &= 0x7F
+    hashes = rng.integers(0, 256, (base, 32), dtype=np.uint8)
+    st, pubs = b.bignPubkeyCalcBatch(p, priv)
+    st2, sigs = b.bignSign2Batch(p, b.OID_BELT_HASH_DER, hashes, priv)
+    assert not st.any() and not st2.any()
+    sigs[::9, 5] ^= 0x20
+    want = b.bignVerifyBatch(p, b.OID_BELT_HASH_DER, hashes, sigs, pubs)
+    for i in range(0, base, 64):
+        assert want[i] == o.bignVerify(hashes[i].tobytes(), sigs[i].tobytes(), pubs[i].tobytes())
+    assert (want[::9] == 510).all() and int((want == 0).sum()) == base - len(range(0, base, 9))
+    reps = (n + base - 1) // base
+    big = [np.ascontiguousarray(np.tile(x, (reps, 1))[:n]) for x in (hashes, sigs, pubs)]
+    got = b.bignVerifyBatch(p, b.OID_BELT_HASH_DER, *big)
+    assert np.array_equal(got, np.tile(want, reps)[:n])
