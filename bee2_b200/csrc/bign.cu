@@ -1098,6 +1098,13 @@ static u32 make_oid(OidArg& o, const u8* der, size_t len)
 template <int N> static inline u32 bign_threads(size_t count)
 {
 	const u64 sms = (u64)b2g_sm_count();
+	{
+		// measurement switch: a fixed CTA size (a multiple of 32 in [BIGN_T / 2, BIGN_T])
+		static const char* fix = getenv("B2G_BIGN_THREADS");
+		const u32 t = fix ? (u32)atoi(fix) : 0;
+		if (t >= BIGN_T(N) / 2 && t <= BIGN_T(N) && t % 32 == 0)
+			return t;
+	}
 	u32 best_t = BIGN_T(N);
 	double best = 0;
 	for (u32 t = BIGN_T(N); t >= BIGN_T(N) / 2; t -= 32)
@@ -1151,12 +1158,10 @@ template <int N> static u32 verify_launch(void* d_status, const OidArg& oid, con
 	static const bool no_staging = getenv("B2G_NO_STAGING") != 0;
 	const bool staged = !no_staging && (((uintptr_t)d_hashes | (uintptr_t)d_sigs | (uintptr_t)d_pubkeys) & 15) == 0;
 	const size_t chunk = count < BIGN_WTAB_CHUNK ? count : BIGN_WTAB_CHUNK;
+	// every launch covers at most chunk items rounded up to whole CTAs of at most BIGN_T(N) threads
 	void* wtab = 0;
-	{
-		const u32 t = bign_threads<N>(chunk);
-		if ((e = wtab_alloc(&wtab, (size_t)bign_grid<N>(chunk, t) * t * win_global<N>::ITEM_BYTES, st)))
-			return e;
-	}
+	if ((e = wtab_alloc(&wtab, (chunk + BIGN_T(N)) * win_global<N>::ITEM_BYTES, st)))
+		return e;
 	for (size_t off = 0; off < count && !e; off += chunk)
 	{
 		const size_t n = count - off < chunk ? count - off : chunk;

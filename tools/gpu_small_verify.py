@@ -11,7 +11,8 @@ import bee2_b200 as b
 assert b.b2g_init(0) == 0
 stream = torch.cuda.current_stream().cuda_stream
 OID = bytes.fromhex("06092A7000020022651F51")
-nmax = 1 << 18
+sizes = [int(a) for a in sys.argv[1:]] or [1 << 15, 1 << 16, 1 << 17, 1 << 18]
+nmax = max(sizes + [1 << 18])
 rng = np.random.default_rng(2)
 priv = rng.integers(0, 256, (nmax, 32), dtype=np.uint8)
 priv[:, 31] &= 0x7F
@@ -25,7 +26,7 @@ d_h, d_s, d_p = (torch.from_numpy(x).cuda() for x in (hashes, sigs, pubs))
 d_st = torch.empty(nmax, dtype=torch.int32, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 out = []
-for n in [int(a) for a in sys.argv[1:]] or [1 << 15, 1 << 16, 1 << 17, 1 << 18]:
+for n in sizes:
     fn = lambda: b.bignVerifyBatch_dev(d_st.data_ptr(), OID, d_h.data_ptr(), d_s.data_ptr(), d_p.data_ptr(), n, stream)  # noqa: E731
     for _ in range(3):
         fn()
