@@ -46,6 +46,11 @@
 #define BIGN_BLOCKS16 4
 #endif
 #define BIGN_BLOCKS(N) ((N) == 8 ? BIGN_MIN_BLOCKS : (N) == 12 ? BIGN_BLOCKS12 : BIGN_BLOCKS16)
+// the signing kernel's own occupancy request (measured at l = 128: 3 CTAs/SM 242 M/s, 4 -> 229, 2 -> see DESIGN §4.3.1)
+#ifndef BIGN_SIGN_BLOCKS8
+#define BIGN_SIGN_BLOCKS8 BIGN_MIN_BLOCKS
+#endif
+#define BIGN_SIGN_BLOCKS(N) ((N) == 8 ? BIGN_SIGN_BLOCKS8 : BIGN_BLOCKS(N))
 // Fixed-base window width in bits (<= 16), per field size. N = 8: 16 bits -> 16 mixed additions from a 67 MiB
 // table (measured against 13 bits / 20 additions / 10 MiB: verify 52.7 -> 53.9 M/s, sign2 202 -> 218 M/s; the
 // random 64-byte table reads miss L2 more often — 268 MB of extra DRAM reads per 2^18 items, far from binding).
@@ -665,7 +670,7 @@ template <int NB> __device__ __forceinline__ void wbl(const BignSbox& S, u32 (&r
 // the product tree in between — with pinned host buffers bignSign2Batch then runs zero-copy, and the private
 // keys never rest in device memory.
 #define BIGN_SIGN_SMEM_BYTES(N) (BIGN_T(N) * 8 * (N) > 4 * BIGN_TREE_WORDS(N) ? BIGN_T(N) * 8 * (N) : 4 * BIGN_TREE_WORDS(N))
-template <int N, bool STAGED> __global__ void __launch_bounds__(BIGN_T(N), BIGN_BLOCKS(N))
+template <int N, bool STAGED> __global__ void __launch_bounds__(BIGN_T(N), BIGN_SIGN_BLOCKS(N))
 bign_sign2_kernel(u32* __restrict__ status, u8* __restrict__ sigs, const u8* __restrict__ hashes,
 	const u8* __restrict__ privkeys, u64 count, const OidArg oid, const TArg targ,
 	const uint4* __restrict__ gtab, const u8* __restrict__ nonces)
