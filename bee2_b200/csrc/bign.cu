@@ -495,7 +495,8 @@ bign_verify_kernel(u32* __restrict__ status, const u8* __restrict__ hashes, cons
 {
 	constexpr int NO = 4 * N, H2 = N / 2;
 	__shared__ u32 tab[BignSbox::WORDS];
-	__shared__ __align__(16) u8 smem[BIGN_SMEM_BYTES(N)];
+	// (the direct-load build only holds the tree: 16 KB instead of 36 KB per CTA leaves more of the SM's 256 KB to L1)
+	__shared__ __align__(16) u8 smem[STAGED ? BIGN_SMEM_BYTES(N) : 4 * BIGN_TREE_WORDS(N)];
 	__shared__ u64 mbar;
 	u32* tree = reinterpret_cast<u32*>(smem);
 	BignSbox::fill(tab);
@@ -506,7 +507,9 @@ bign_verify_kernel(u32* __restrict__ status, const u8* __restrict__ hashes, cons
 	// at l = 192 (72 octets per item, odd n) is not one — that CTA reads its items directly
 	const u32 n = (u32)(count - i0 < blockDim.x ? count - i0 : blockDim.x);
 	const bool staged = STAGED && ((n * (NO + NO / 2)) & 15u) == 0;
-	if (staged)
+	if constexpr (!STAGED)
+		__syncthreads();
+	else if (staged)
 	{
 		u8* s_hash = smem;
 		u8* s_sig = smem + BIGN_T(N) * NO;
@@ -583,9 +586,13 @@ bign_verify_kernel(u32* __restrict__ status, const u8* __restrict__ hashes, cons
 #pragma unroll
 			for (int k = 0; k < N; ++k) k5.w[k] = k < H2 ? s0[k] : (k == H2 ? 1u : 0u);
 			// the window table {1..16}Q lives in this CTA's part of the launch's scratch area (ecp.cuh win_global)
+#ifdef BIGN_WTAB_LOCAL   /* A/B measurement only: the round-1 form, table in local memory */
+			pt_mul_var<N>(R, k5, 16 * N + 1, qx, qy);
+#else
 			win_global<N> W;
 			W.base = wtab + i0 * win_global<N>::ITEM_BYTES + 32u * threadIdx.x, W.stride = 32u * blockDim.x;
 			pt_mul_var_g<N>(R, k5, 16 * N + 1, qx, qy, W);
+#endif
 		}
 		{
 			sc<N> ks;
@@ -1160,8 +1167,18 @@ template <int N> static u32 verify_launch(void* d_status, const OidArg& oid, con
 	if (e) return e;
 	// TMA staging needs 16-byte aligned segments (every CTA's first item then is: item sizes are multiples
 	// of 16 and so is every CTA size); B2G_NO_STAGING=1 keeps the per-thread loads (A/B measurement)
-	static const bool no_staging = getenv("B2G_NO_STAGING") != 0;
-	const bool staged = !no_staging && (((uintptr_t)d_hashes | (uintptr_t)d_sigs | (uintptr_t)d_pubkeys) & 15) == 0;
+	// Staging pays where the inputs are (pinned) HOST memory — the zero-copy path of bignVerifyBatch: 46.0 -> 51.3 M/s.
+	// For inputs resident in HBM it gains nothing at l = 128 (56.7 against 56.9 M/s) and costs at the wider fields
+	// (l = 192: 15.2 against 15.7, l = 256: 6.3 against 7.2 M/s): its 36 KB buffer per CTA, against 16 KB for the
+	// tree alone, is taken from the L1 that serves the call frames. B2G_FORCE_STAGING=1 stages device inputs too.
+	static const bool no_staging = getenv("B2G_NO_STAGING") != 0, force_staging = getenv("B2G_FORCE_STAGING") != 0;
+	bool staged = !no_staging && (((uintptr_t)d_hashes | (uintptr_t)d_sigs | (uintptr_t)d_pubkeys) & 15) == 0;
+	if (staged && !force_staging)
+	{
+		cudaPointerAttributes pa;
+		staged = cudaPointerGetAttributes(&pa, d_hashes) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+		(void)cudaGetLastError();
+	}
 	const size_t chunk = count < BIGN_WTAB_CHUNK ? count : BIGN_WTAB_CHUNK;
 	// every launch covers at most chunk items rounded up to whole CTAs of at most BIGN_T(N) threads
 	void* wtab = 0;

@@ -50,6 +50,24 @@ template <int N, bool INL> PT_OP void pt_dbl_t(pt<N>& R, const pt<N>& P)
 	// whatever is alive across a call beyond the callee-saved registers is spilled around it.
 	// R may alias P: a coordinate of R is written only after the last read of that coordinate of P.
 	fe<N> delta, gamma, beta, alpha, t, u;
+#ifdef PT_DBL_ORDER_R1   /* A/B measurement only: the order of round 1 (all four squares and products first) */
+	PS(delta, P.Z);
+	PS(gamma, P.Y);
+	PM(beta, P.X, gamma);
+	fe_sub<N>(t, P.X, delta), fe_add<N>(u, P.X, delta);
+	PM(alpha, t, u);
+	fe_dbl<N>(t, alpha), fe_add<N>(alpha, alpha, t);
+	fe_add<N>(t, P.Y, P.Z), PS(t, t);
+	fe_sub<N>(t, t, gamma), fe_sub<N>(R.Z, t, delta);
+	fe_shl<2, N>(beta, beta);
+	PS(t, alpha);
+	fe_sub<N>(t, t, beta), fe_sub<N>(R.X, t, beta);
+	PS(gamma, gamma);
+	fe_shl<3, N>(gamma, gamma);
+	fe_sub<N>(t, beta, R.X), PM(t, alpha, t);
+	fe_sub<N>(R.Y, t, gamma);
+	return;
+#endif
 	PS(delta, P.Z);
 	PS(gamma, P.Y);
 	fe_add<N>(t, P.Y, P.Z), PS(t, t);

@@ -620,3 +620,49 @@ def test_sign2_ragged_counts_staged_and_pinned(l):
                 sg = dsg.cpu().numpy()[shift:shift + n * so].reshape(n, so)
                 assert (dsg.cpu().numpy()[shift + n * so:] == 0xA5).all() and (dsg.cpu().numpy()[:shift] == 0xA5).all()
                 check(dst.cpu().numpy().view(np.uint32), sg, ("device", shift))
+
+
+def test_verify_forced_staging_on_device_buffers():
+    """The launcher stages (TMA bulk copies) only inputs that lie in host memory; B2G_FORCE_STAGING=1 makes it
+    stage device-resident inputs too (the switch is read once per process, hence the subprocess). Both
+    builds of the kernel must give the statuses of the default path on ragged sizes."""
+    import subprocess
+    import sys
+    script = r'''
+import numpy as np, torch, sys
+sys.path.insert(0, "tests")
+import bee2_b200 as b, _oracle as o
+rng = np.random.default_rng(5)
+out = []
+for l in (128, 192, 256):
+    p, no, oid = b.bignParamsStd(b.BIGN_CURVES[l]), l // 4, o.OIDS[l]
+    n = 700
+    priv = rng.integers(0, 256, (n, no), dtype=np.uint8); priv[:, no - 1] &= 0x7F
+    hashes = rng.integers(0, 256, (n, no), dtype=np.uint8)
+    st, pubs = b.bignPubkeyCalcBatch(p, priv)
+    st2, sigs = b.bignSign2Batch(p, oid, hashes, priv)
+    assert not st.any() and not st2.any()
+    sigs[::3, 1] ^= 4
+    ko = np.frombuffer(oid, dtype=np.uint8)
+    stream = torch.cuda.current_stream().cuda_stream
+    for m in (1, 255, 256, 257, 700):
+        d = [torch.from_numpy(x[:m].copy()).cuda() for x in (hashes, sigs, pubs)]
+        dst = torch.full((m,), 77, dtype=torch.int32, device="cuda")
+        assert b.lib().b2g_bignVerifyBatchL_dev(l, dst.data_ptr(), ko.ctypes.data, len(oid), d[0].data_ptr(), d[1].data_ptr(),
+                                                d[2].data_ptr(), m, stream) == 0
+        out.append(dst.cpu().numpy().view(np.uint32).tobytes().hex())
+print("\n".join(out))
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    runs = []
+    for force in ("", "1"):
+        env = dict(os.environ)
+        env.pop("B2G_FORCE_STAGING", None)
+        if force:
+            env["B2G_FORCE_STAGING"] = force
+        r = subprocess.run([sys.executable, "-c", script], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        runs.append(r.stdout.split())
+    assert runs[0] == runs[1] and len(runs[0]) == 15
+    first = np.frombuffer(bytes.fromhex(runs[0][4]), dtype=np.uint32)      # l = 128, 700 items
+    assert (first[::3] == 510).all() and (np.delete(first, np.arange(0, 700, 3)) == 0).all()
