@@ -489,7 +489,17 @@ template <int N> __global__ void __launch_bounds__(128) bign_gtab_kernel(uint4* 
 // The staging buffer is the memory of the product tree, which is only used after the inputs are in registers.
 #define BIGN_STAGE_BYTES(N) (BIGN_T(N) * 18 * (N))   /* 4.5 no octets per item */
 #define BIGN_SMEM_BYTES(N) (BIGN_STAGE_BYTES(N) > 4 * BIGN_TREE_WORDS(N) ? BIGN_STAGE_BYTES(N) : 4 * BIGN_TREE_WORDS(N))
-template <int N, bool STAGED> __global__ void __launch_bounds__(BIGN_T(N), BIGN_BLOCKS(N))
+// (BIGN_VERIFY_T8 / BIGN_VERIFY_B8: launch bounds of the l = 128 verification kernel alone, for occupancy
+// experiments — e.g. 224 threads x 4 CTAs = 72 registers, to be launched with B2G_BIGN_THREADS=224)
+#ifndef BIGN_VERIFY_T8
+#define BIGN_VERIFY_T8 BIGN_T(8)
+#endif
+#ifndef BIGN_VERIFY_B8
+#define BIGN_VERIFY_B8 BIGN_BLOCKS(8)
+#endif
+template <int N> struct bign_verify_lb { static constexpr int T = BIGN_T(N), B = BIGN_BLOCKS(N); };
+template <> struct bign_verify_lb<8> { static constexpr int T = BIGN_VERIFY_T8, B = BIGN_VERIFY_B8; };
+template <int N, bool STAGED> __global__ void __launch_bounds__(bign_verify_lb<N>::T, bign_verify_lb<N>::B)
 bign_verify_kernel(u32* __restrict__ status, const u8* __restrict__ hashes, const u8* __restrict__ sigs,
 	const u8* __restrict__ pubkeys, u64 count, const OidArg oid, const uint4* __restrict__ gtab, u8* __restrict__ wtab)
 {
