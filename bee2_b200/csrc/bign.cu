@@ -354,11 +354,16 @@ template <int N> __device__ __forceinline__ void hash_oid_ab(const BignSbox& S, 
 
 // ---------------------------------------------------------------- block-wide inversion
 // Montgomery's simultaneous inversion as a product tree in shared memory: every thread of the CTA
-// hands in one z != 0 (1 if it has nothing to invert) and gets 1/z back, for ONE field inversion
-// per CTA (thread 0, ~270 squarings) plus 2 log2(CTA size) products per thread — instead of
-// one inversion per thread, which was 12 % of a verification and half of a signature.
-// Node i has children 2i and 2i+1, leaves at T + tid (T = CTA size), root at 1. The tree is stored
-// word-major (word j of node i at sm[j * 2 T + i]) so that lanes hit distinct banks.
+// hands in one z != 0 (1 if it has nothing to invert) and gets 1/z back, for ONE round of field inversions
+// per CTA plus 2 (log2(CTA size) - 5) products per thread — instead of one inversion per thread, which was
+// 12 % of a verification and half of a signature.
+// Node i has children 2i and 2i+1, leaves at T + tid (T = CTA size). The tree stops at the level of 32
+// nodes (32 .. 63): the 32 lanes of warp 0 invert one node each, in lock-step — the latency of one
+// inversion, five tree levels (ten dependent products and fifteen barriers) fewer than a tree that ends in a
+// single root, and 32 different operands keep the iteration on the vector pipe (with one active thread
+// ptxas proves the operand warp-uniform and moves the whole inversion to the uniform datapath — UIMAD /
+// ULOP3 / USHF — which runs this dependent chain slower: signing 242 -> 236 M/s, measured).
+// The tree is stored word-major (word j of node i at sm[j * 2 T + i]) so that lanes hit distinct banks.
 // Must be reached by ALL threads of the CTA (it synchronises).
 #define BIGN_TREE_WORDS(N) (2 * BIGN_T(N) * (N))
 template <int N> __device__ __forceinline__ void tree_put(u32* sm, int i, const fe<N>& a)
@@ -376,6 +381,9 @@ template <int N, bool CT = true> __device__ __noinline__ fe<N> block_inv(const f
 {
 	const int tid = threadIdx.x;
 	fe<N> a, b;
+#ifdef BIGN_FAKE_TREE   /* timing experiment only: no tree, no barriers, no inversion (wrong results) */
+	return z;
+#endif
 	tree_put<N>(sm, BIGN_T(N) + tid, z);
 	// a CTA may be launched with fewer than BIGN_T(N) threads (bign_shape: balanced grids for small
 	// batches), at least BIGN_T(N) / 2: the missing leaves are 1
@@ -387,7 +395,7 @@ template <int N, bool CT = true> __device__ __noinline__ fe<N> block_inv(const f
 	__syncthreads();
 	// up: products of the children
 #pragma unroll 1
-	for (int s = BIGN_T(N) / 2; s >= 1; s >>= 1)
+	for (int s = BIGN_T(N) / 2; s >= 32; s >>= 1)
 	{
 		if (tid < s)
 		{
@@ -398,17 +406,17 @@ template <int N, bool CT = true> __device__ __noinline__ fe<N> block_inv(const f
 		__syncthreads();
 	}
 #ifndef BIGN_FAKE_INV   /* timing experiment only: skips the inversion (wrong results) */
-	if (tid == 0)
+	if (tid < 32)
 	{
-		tree_get<N>(a, sm, 1);
+		tree_get<N>(a, sm, 32 + tid);
 		fe_inv<N, CT>(a, a);
-		tree_put<N>(sm, 1, a);
+		tree_put<N>(sm, 32 + tid, a);
 	}
 #endif
 	__syncthreads();
 	// down: 1/child = 1/parent * sibling
 #pragma unroll 1
-	for (int s = 2; s <= BIGN_T(N); s <<= 1)
+	for (int s = 64; s <= BIGN_T(N); s <<= 1)
 	{
 		const bool on = tid < s;
 		if (on)

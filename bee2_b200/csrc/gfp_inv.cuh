@@ -16,9 +16,13 @@
 //
 // Step count: for f, g < 2^d the iteration ends within floor((49 d + 57) / 17) steps (Bernstein–Yang,
 // Theorem 11.2, d >= 46): 741 / 1110 / 1479 for d = 256 / 384 / 512 -> 25 / 37 / 50 batches of 30.
-// CT = true always runs them all (the instruction stream does not depend on a: secret-dependent inputs —
+// For 256-bit moduli the variant that starts from delta = 1/2 is known to end within 590 steps (the
+// convex-hull bound libsecp256k1's modinv32 relies on: 20 batches of 30); it differs in one line — the
+// update of eta = -(delta + 1/2) — and is what N = 8 uses. The wider fields keep delta = 1 and the theorem.
+// CT = true always runs all batches (the instruction stream does not depend on a: secret-dependent inputs —
 // the Z coordinates of k G in the signing kernels); CT = false stops at the first batch that ends with
-// g = 0 (public inputs: verification).
+// g = 0 (public inputs: verification). Either way the loop goes on while g != 0, so the RESULT never
+// depends on a step bound being right — only the claim of a fixed instruction count does.
 #pragma once
 #include "common.cuh"
 
@@ -32,27 +36,30 @@ typedef int64_t i64;
 template <int N> struct inv30
 {
 	static constexpr int L = (32 * N + 2 + 29) / 30;               // 9 / 13 / 18 limbs
-	static constexpr int BATCHES = ((49 * 32 * N + 57) / 17 + 29) / 30;
+	static constexpr bool HALF_DELTA = N == 8;                      // delta starts at 1/2 (256-bit bound: 590 steps)
+	static constexpr int BATCHES = HALF_DELTA ? 20 : ((49 * 32 * N + 57) / 17 + 29) / 30;
 	static constexpr i32 M30 = (i32)0x3FFFFFFF;
 };
 
 struct inv_mat { i32 u, v, q, r; };
 
-// 30 division steps on the low bits; eta = -delta. Branch-free.
-GFP_INV_HD i32 inv_divsteps30(i32 eta, u32 f0, u32 g0, inv_mat& t)
+// 30 division steps on the low bits; eta = -delta (HALF: eta = -(delta + 1/2)). Branch-free.
+template <bool HALF> GFP_INV_HD i32 inv_divsteps30(i32 eta, u32 f0, u32 g0, inv_mat& t)
 {
 	u32 u = 1, v = 0, q = 0, r = 1;
 	u32 f = f0, g = g0;
 #pragma unroll 6
 	for (int i = 0; i < 30; ++i)
 	{
-		u32 c1 = (u32)(eta >> 31);          // delta > 0
+		const u32 c1 = (u32)(eta >> 31);    // delta > 0
 		const u32 c2 = 0u - (g & 1u);       // g odd
-		const u32 x = (f ^ c1) - c1, y = (u ^ c1) - c1, z = (v ^ c1) - c1;   // -f, -u, -v when delta > 0
-		g += x & c2, q += y & c2, r += z & c2;
-		c1 &= c2;                           // swap case
-		eta = (i32)(((u32)eta ^ c1) - (c1 + 1u));
-		f += g & c1, u += q & c1, v += r & c1;
+		const u32 c3 = c1 & c2;             // swap case
+		const u32 one = c3 & 1u;
+		// g, q, r += (delta > 0 ? -(f, u, v) : (f, u, v)) if g is odd; -x = (x ^ ~0) + 1: one LOP3 + one IADD3 each
+		g += ((f ^ c1) & c2) + one, q += ((u ^ c1) & c2) + one, r += ((v ^ c1) & c2) + one;
+		// swap: delta <- 1 - delta, else delta <- 1 + delta
+		eta = HALF ? (i32)(((u32)eta ^ c3) - 1u) : (i32)(((u32)eta ^ c3) - (c3 + 1u));
+		f += g & c3, u += q & c3, v += r & c3;
 		g >>= 1, u <<= 1, v <<= 1;
 	}
 	t.u = (i32)u, t.v = (i32)v, t.q = (i32)q, t.r = (i32)r;
@@ -134,14 +141,15 @@ template <int N, bool CT> GFP_INV_HD void inv_safegcd(u32* r, const u32* a, u32 
 	minv &= (u32)M30;
 	i32 eta = -1;
 #pragma unroll 1
-	for (int b = 0; b < inv30<N>::BATCHES; ++b)
+	for (int b = 0;; ++b)
 	{
 		inv_mat t;
-		eta = inv_divsteps30(eta, (u32)f[0] | (u32)f[1] << 30, (u32)g[0] | (u32)g[1] << 30, t);
+		eta = inv_divsteps30<inv30<N>::HALF_DELTA>(eta, (u32)f[0] | (u32)f[1] << 30, (u32)g[0] | (u32)g[1] << 30, t);
 		inv_update_de<L>(d, e, t, m, minv);
 		inv_update_fg<L>(f, g, t);
-		if (!CT)
+		if (!CT || b >= inv30<N>::BATCHES - 1)
 		{
+			// CT: only looked at after the last scheduled batch (g = 0 by then: never another round)
 			i32 z = 0;
 #pragma unroll
 			for (int i = 0; i < L; ++i) z |= g[i];

@@ -40,7 +40,7 @@ def exe():
     out = os.path.join(HERE, "_build", "host_gfp_test")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     src = os.path.join(HERE, "host_gfp_test.cu")
-    deps = [src] + [os.path.join(HERE, "..", "bee2_b200", "csrc", f) for f in ("gfp.cuh", "gfp_asm.cuh", "ecp.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "bee2_b200", "csrc", f) for f in ("gfp.cuh", "gfp_asm.cuh", "gfp_inv.cuh", "ecp.cuh", "common.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.run([NVCC, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-diag-suppress", "20044",
                         "-o", out, src], check=True)
