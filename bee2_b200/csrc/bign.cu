@@ -268,8 +268,12 @@ template <int N> __device__ __forceinline__ void load_scalar(sc<N>& k, const u8*
 // not depend on the scalar. The ADDRESS of the table read still does (13 bits of the scalar select one of
 // 8192 entries of a 10 MiB table): a cache-timing channel the reference's masked wwSel scan does not have;
 // scanning 8192 entries per window is not an option here, see DESIGN.md "Secret scalars".
-template <int N, bool CT = false> __device__ __noinline__ void pt_add_mul_base(pt<N>& acc, const sc<N> ks, const uint4* __restrict__ gtab)
+// FRESH = true (with CT): acc is the point at infinity on entry and need not be initialised — window 0 only
+// loads its table entry (Z = 1, or 0 by a mask if the digit is 0) instead of running an addition whose first
+// operand is O: one of the 16 / 30 / 40 mixed additions of k G saved.
+template <int N, bool CT = false, bool FRESH = false> __device__ __noinline__ void pt_add_mul_base(pt<N>& acc, const sc<N> ks, const uint4* __restrict__ gtab)
 {
+	static_assert(CT || !FRESH, "the direct form adds onto a running point");
 	const u32* k = ks.w;
 #pragma unroll 1
 	for (int i = 0; i < BIGN_GN(N); ++i)
@@ -288,6 +292,12 @@ template <int N, bool CT = false> __device__ __noinline__ void pt_add_mul_base(p
 				const uint4 a = __ldg(e + j), b = __ldg(e + N / 4 + j);
 				x.v[4 * j] = a.x, x.v[4 * j + 1] = a.y, x.v[4 * j + 2] = a.z, x.v[4 * j + 3] = a.w;
 				y.v[4 * j] = b.x, y.v[4 * j + 1] = b.y, y.v[4 * j + 2] = b.z, y.v[4 * j + 3] = b.w;
+			}
+			if (FRESH && i == 0)
+			{
+				acc.X = x, acc.Y = y;
+				fe_set_u32<N>(acc.Z, (u32)(d != 0));
+				continue;
 			}
 			pt<N> S;
 			pt_madd<N>(S, acc, x, y);
@@ -770,12 +780,11 @@ bign_sign2_kernel(u32* __restrict__ status, u8* __restrict__ sigs, const u8* __r
 			while (uN_is_zero<N>(k) || geq_q<N>(k));
 		}
 		// R <- k G (:219-224)
-		pt_set_inf<N>(R);
 		{
 			sc<N> ks;
 #pragma unroll
 			for (int j = 0; j < N; ++j) ks.w[j] = k[j];
-			pt_add_mul_base<N, true>(R, ks, gtab);   // the one-time key is secret: regular form
+			pt_add_mul_base<N, true, true>(R, ks, gtab);   // the one-time key is secret: regular form
 		}
 		if (pt_is_inf<N>(R))
 			st = B2G_BAD_PARAMS, live = false;
@@ -887,11 +896,10 @@ bign_pubkey_kernel(u32* __restrict__ status, u8* __restrict__ pubkeys, const u8*
 			st = B2G_BAD_PRIVKEY, live = false;
 		else
 		{
-			pt_set_inf<N>(R);
 			sc<N> ks;
 #pragma unroll
 			for (int j = 0; j < N; ++j) ks.w[j] = d[j];
-			pt_add_mul_base<N, true>(R, ks, gtab);   // the private key is secret: regular form
+			pt_add_mul_base<N, true, true>(R, ks, gtab);   // the private key is secret: regular form
 			if (pt_is_inf<N>(R))
 				st = B2G_BAD_PARAMS, live = false;
 		}
