@@ -121,6 +121,28 @@ template <int N> static std::string run(const std::string& op, std::istringstrea
 					same = same && R.X.v[i] == C.X.v[i] && R.Y.v[i] == C.Y.v[i] && R.Z.v[i] == C.Z.v[i];
 			if (!same) return "ct-mismatch";
 		}
+		{
+			// the form with the window table in a caller-provided scratch area (win_global: the layout of the
+			// verification kernel, here as thread 5 of a pretend CTA of 7 threads) must land there too
+			constexpr int T = 7, tid = 5;
+			static u8 area[win_global<N>::ITEM_BYTES * T + 64];
+			u8* al = area + ((32 - ((uintptr_t)area & 31)) & 31);
+			memset(area, 0xEE, sizeof area);
+			win_global<N> W;
+			W.base = al + 32 * tid, W.stride = 32 * T;
+			pt<N> G;
+			pt_mul_var_g<N>(G, k, nbits, x, y, W);
+			bool same = pt_is_inf<N>(R) == pt_is_inf<N>(G);
+			if (same && !pt_is_inf<N>(R))
+				for (int i = 0; i < N; ++i)
+					same = same && R.X.v[i] == G.X.v[i] && R.Y.v[i] == G.Y.v[i] && R.Z.v[i] == G.Z.v[i];
+			if (!same) return "wg-mismatch";
+			// only this thread's granules were written: every other 32-octet granule is untouched
+			for (size_t g = 0; g < win_global<N>::ITEM_BYTES * T / 32; ++g)
+				if ((int)(g % T) != tid)
+					for (int b = 0; b < 32; ++b)
+						if (al[32 * g + b] != 0xEE) return "wg-overrun";
+		}
 		if (pt_is_inf<N>(R)) return "inf";
 		pt_to_affine<N>(x, y, R);
 		return to_hex(x.v, N) + " " + to_hex(y.v, N);
