@@ -204,19 +204,9 @@ belt_ecb_kernel(uint4* dst, const uint4* src, const uint4* __restrict__ keys, u6
 #endif
 // ---------------------------------------------------------------- belt-hash batch
 // One message per thread; messages of equal length msg_len at msgs + i*stride.
-__global__ void __launch_bounds__(256)
-belt_hash_kernel(u8* __restrict__ hashes, const u8* __restrict__ msgs, u64 msg_len, u64 stride,
-	u64 count)
+template <class SB> __device__ __forceinline__ void belt_hash_msg(const SB& S, u8* __restrict__ o, const u8* __restrict__ m,
+	u64 msg_len, bool al4)
 {
-	__shared__ u32 tab[BELT_HASH_SBOX::WORDS];
-	BELT_HASH_SBOX::fill(tab);
-	__syncthreads();
-	const BELT_HASH_SBOX S(tab);
-	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= count)
-		return;
-	const u8* m = msgs + i * stride;
-	const bool al4 = (((uintptr_t)msgs | stride) & 3) == 0;
 	u32 h[8], ls[8] = {0, 0, 0, 0, 0, 0, 0, 0}, X[8];
 	belt_hash_init(h);
 	u64 off = 0;
@@ -250,10 +240,36 @@ belt_hash_kernel(u8* __restrict__ hashes, const u8* __restrict__ msgs, u64 msg_l
 	// length in bits as a 128-bit LE integer (belt_lcl.c:25-48)
 	ls[0] = (u32)(msg_len << 3), ls[1] = (u32)(msg_len >> 29), ls[2] = (u32)(msg_len >> 61), ls[3] = 0;
 	belt_compress(S, (u32*)0, h, ls);
-	u8* o = hashes + 32 * i;
 #pragma unroll
 	for (int j = 0; j < 8; ++j)
 		reinterpret_cast<u32*>(o)[j] = h[j];
+}
+// small batches: 256-thread CTAs with the four 1 KiB tables (random bank conflicts, cheap to set up)
+__global__ void __launch_bounds__(256)
+belt_hash_kernel(u8* __restrict__ hashes, const u8* __restrict__ msgs, u64 msg_len, u64 stride,
+	u64 count)
+{
+	__shared__ u32 tab[BELT_HASH_SBOX::WORDS];
+	BELT_HASH_SBOX::fill(tab);
+	__syncthreads();
+	const BELT_HASH_SBOX S(tab);
+	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+		return;
+	belt_hash_msg(S, hashes + 32 * i, msgs + i * stride, msg_len, (((uintptr_t)msgs | stride) & 3) == 0);
+}
+// large batches: the shape of the CTR kernel — one persistent 1024-thread CTA per SM with the bank-replicated
+// 128 KiB tables (every S-box read conflict-free), grid-stride over the messages
+__global__ void __launch_bounds__(BELT_THREADS, 1)
+belt_hash_big_kernel(u8* __restrict__ hashes, const u8* __restrict__ msgs, u64 msg_len, u64 stride, u64 count)
+{
+	extern __shared__ __align__(1024) u8 sm[];
+	BeltBigT::fill(sm);
+	__syncthreads();
+	const BeltBigT S(sm);
+	const bool al4 = (((uintptr_t)msgs | stride) & 3) == 0;
+	for (u64 i = (u64)blockIdx.x * BELT_THREADS + threadIdx.x; i < count; i += (u64)gridDim.x * BELT_THREADS)
+		belt_hash_msg(S, hashes + 32 * i, msgs + i * stride, msg_len, al4);
 }
 
 // ---------------------------------------------------------------- launchers (C ABI)
@@ -270,7 +286,7 @@ static u32 belt_optin_all(void)
 	const void* ks[] = {(const void*)belt_ctr_kernel<true>, (const void*)belt_ctr_kernel<false>,
 		(const void*)belt_che_kernel<true>, (const void*)belt_che_kernel<false>,
 		(const void*)belt_ecb_kernel<false, false>, (const void*)belt_ecb_kernel<true, false>,
-		(const void*)belt_ecb_kernel<false, true>};
+		(const void*)belt_ecb_kernel<false, true>, (const void*)belt_hash_big_kernel};
 	for (size_t i = 0; i < sizeof ks / sizeof ks[0]; ++i)
 		if (cudaFuncSetAttribute(ks[i], cudaFuncAttributeMaxDynamicSharedMemorySize, BELT_BIGT_BYTES) != cudaSuccess)
 			return b2g_check_launch("cudaFuncSetAttribute(belt)");
@@ -475,6 +491,16 @@ extern "C" u32 b2g_beltHashBatch_dev(void* d_hashes, const void* d_msgs, size_t 
 	if (e) return e;
 	if (count == 0) return B2G_OK;
 	if ((uintptr_t)d_hashes & 3) return B2G_BAD_INPUT;
+	// from half a wave of the persistent shape on (and messages long enough to pay for filling the 128 KiB tables)
+	if (count >= (size_t)b2g_sm_count() * BELT_THREADS / 2 && msg_len >= 64)
+	{
+		const u64 ctas = (count + BELT_THREADS - 1) / BELT_THREADS;
+		const u32 grid = (u32)(ctas < (u64)b2g_sm_count() ? ctas : (u64)b2g_sm_count());
+		belt_hash_big_kernel<<<grid, BELT_THREADS, BELT_BIGT_BYTES, (cudaStream_t)stream>>>((u8*)d_hashes, (const u8*)d_msgs,
+			msg_len, stride, count);
+		b2g_note_launch();
+		return b2g_check_launch("belt_hash_big_kernel");
+	}
 	const u32 grid = (u32)((count + 255) / 256);
 	belt_hash_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((u8*)d_hashes, (const u8*)d_msgs, msg_len, stride, count);
 	b2g_note_launch();

@@ -279,6 +279,20 @@ def test_hash_batch_random():
             assert got[i].tobytes() == o.beltHash(msgs[i].tobytes())
 
 
+def test_hash_batch_large_persistent_kernel():
+    """Batches of at least half a wave run the persistent shape (bank-replicated tables, grid-stride over the
+    messages): ragged count, aligned and unaligned message lengths / strides, sampled against the oracle and — all
+    of them — against the small-batch kernel (the same messages hashed in slices of 1000)."""
+    rng = np.random.default_rng(44)
+    for n, mlen in ((160_001, 96), (80_000, 203)):
+        msgs = rng.integers(0, 256, (n, mlen), dtype=np.uint8)
+        got = b.beltHashBatch(msgs)
+        for i in list(range(0, n, n // 40)) + [n - 1]:
+            assert got[i].tobytes() == o.beltHash(msgs[i].tobytes())
+        for lo in range(0, n, 20_000):
+            assert np.array_equal(b.beltHashBatch(msgs[lo:lo + 1000]), got[lo:lo + 1000])
+
+
 def test_config2_shape_device_level():
     """BASELINE config 2 shape on device-resident buffers (256 MiB here; bench.py runs the full
     1 GiB): keystream equals the oracle on the head, offsets are consistent, and E(E(x)) = x."""
