@@ -189,3 +189,35 @@ def test_concurrent_host_threads():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_bash_prg_blocks_batch_matches_single_automata():
+    """b2g_bashPrgBlocks_dev over many automata (the batch of SURVEY §8f rank 3): every automaton's state and
+    data must come out as when it is run alone (count = 1 — the path the bashPrg* drop-ins use, which the A.4–A.6
+    vectors and the random programs pin on the oracle). Whole-word rates (64-bit fast path) and a ragged rate /
+    unaligned stride (octet path), all four commands."""
+    import ctypes as C
+    torch = pytest.importorskip("torch")
+    L = b.lib()
+    L.b2g_bashPrgBlocks_dev.restype = C.c_uint32
+    L.b2g_bashPrgBlocks_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
+                                         C.c_size_t, C.c_void_p]
+    stream = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(99)
+    n, blocks = 300, 3
+    for buf_len, pad in ((160, 0), (64, 8), (156, 0), (168, 3)):
+        stride = blocks * buf_len + pad
+        for mode in range(4):
+            states = rng.integers(0, 256, (n, 192), dtype=np.uint8)
+            data = rng.integers(0, 256, (n, stride), dtype=np.uint8)
+            ds, dd = torch.from_numpy(states).cuda(), torch.from_numpy(data).cuda()
+            assert L.b2g_bashPrgBlocks_dev(ds.data_ptr(), dd.data_ptr(), stride, blocks, buf_len, mode, mode & 1, n, stream) == 0
+            gs, gd = ds.cpu().numpy(), dd.cpu().numpy()
+            for i in (0, 1, 31, 32, 127, 128, 299):
+                s1, d1 = torch.from_numpy(states[i].copy()).cuda(), torch.from_numpy(data[i].copy()).cuda()
+                assert L.b2g_bashPrgBlocks_dev(s1.data_ptr(), d1.data_ptr(), stride, blocks, buf_len, mode, mode & 1, 1, stream) == 0
+                assert np.array_equal(s1.cpu().numpy(), gs[i]) and np.array_equal(d1.cpu().numpy(), gd[i]), (buf_len, mode, i)
+            if mode == 0:
+                assert np.array_equal(gd, data)                      # absorb leaves the data alone
+            else:
+                assert np.array_equal(gd[:, blocks * buf_len:], data[:, blocks * buf_len:])   # nothing past the blocks
