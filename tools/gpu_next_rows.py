@@ -155,7 +155,8 @@ for l in (128, 192, 256):
         # key pairs from the caller's generator (drawn on the host exactly as zzRandNZMod does), then the same kernel
         stream_bytes = rng.integers(0, 256, 40 * n, dtype=np.uint8).tobytes()
         t = host_time(lambda: b.bignKeypairGenBatch(p, stream_bytes, n))
-        row("bignKeypairGen batch, l = 128, 2^16 pairs (generator calls on the host)", "pairs/s", n / t, "host-pointer call")
+        row("bignKeypairGen batch, l = 128, 2^16 pairs (generator calls on the host)", "pairs/s", n / t, "host-pointer call",
+            note="bound by the generator: here a Python ctypes callback per draw (gen_i, defs.h:520-524), not by the device")
         # Diffie-Hellman: d Q, regular variable-base ladder with masked table scan
         other = np.roll(pubs, 1, axis=0).copy()
         t = host_time(lambda: b.bignDHBatch(p, priv, other, 32))
