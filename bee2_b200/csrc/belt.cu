@@ -215,9 +215,20 @@ template <class SB> __device__ __forceinline__ void belt_hash_msg(const SB& S, u
 	{
 		if (al4 && off + 32 <= msg_len)
 		{
+			if ((reinterpret_cast<uintptr_t>(m) & 15) == 0)
+			{
+				// two 128-bit loads per block: every lane reads its own message, so a load instruction costs one LSU
+				// wavefront per lane whatever its width — eight 32-bit loads were 256 wavefronts per block and
+				// warp on top of the 672 of the S-box reads
+				const uint4 lo = ldg_stream(reinterpret_cast<const uint4*>(m + off)), hi = ldg_stream(reinterpret_cast<const uint4*>(m + off) + 1);
+				X[0] = lo.x, X[1] = lo.y, X[2] = lo.z, X[3] = lo.w, X[4] = hi.x, X[5] = hi.y, X[6] = hi.z, X[7] = hi.w;
+			}
+			else
+			{
 #pragma unroll
-			for (int j = 0; j < 8; ++j)
-				X[j] = reinterpret_cast<const u32*>(m + off)[j];
+				for (int j = 0; j < 8; ++j)
+					X[j] = reinterpret_cast<const u32*>(m + off)[j];
+			}
 		}
 		else
 		{
