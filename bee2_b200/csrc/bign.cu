@@ -237,6 +237,44 @@ template <int N> __device__ __forceinline__ void modq_reduce(u32* r, const u32* 
 	}
 }
 
+// r = (t + h 2^(32N)) mod q for an N-limb t and a small h (the scalars of the fixed-base table entries)
+template <int N> __device__ __forceinline__ void modq_fold_top(u32* r, const u32* t, u32 h)
+{
+	constexpr int CL = bign_qc<N>::CL;
+	u32 c[CL], x[N + 1];
+	{
+		u32 cy = 1;
+#pragma unroll
+		for (int i = 0; i < CL; ++i)
+		{
+			const u64 v = (u64)(~bign_c<N>::q()[i]) + cy;
+			c[i] = (u32)v, cy = (u32)(v >> 32);
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < N; ++i) x[i] = t[i];
+	x[N] = h;
+	// h c < 2^(32 CL + 32) <= 2^(32N): after the first fold at most one bit is left above, after the second none
+#pragma unroll
+	for (int round = 0; round < 3; ++round)
+	{
+		const u32 hh = x[N];
+		u64 cy = 0;
+#pragma unroll
+		for (int i = 0; i < N; ++i)
+		{
+			const u64 v = (i < CL ? (u64)hh * c[i] : 0ull) + x[i] + cy;
+			x[i] = (u32)v, cy = v >> 32;
+		}
+		x[N] = (u32)cy;
+	}
+	u32 u[N], q[N];
+	load_q<N>(q);
+	const u32 m = sub_n<N>(u, x, q);
+#pragma unroll
+	for (int i = 0; i < N; ++i) r[i] = m ? x[i] : u[i];
+}
+
 template <int N> __device__ __forceinline__ void load_uN(u32* r, const u8* p)
 {
 	fe<N> t;
@@ -261,61 +299,50 @@ template <int N> __device__ __forceinline__ void load_scalar(sc<N>& k, const u8*
 }
 
 // ---------------------------------------------------------------- fixed-base multiplication
-// acc += k * G for a 32N-bit k (little-endian limbs) through the fixed-base window table
-// CT = true (secret scalars: the one-time key of bignSign / bignSign2, the private key of bignPubkeyCalc /
-// bignKeypairGen; the reference's bignMulBase is regular, ec.c:892-964): a zero digit does not skip the
-// addition — entry 1 of the window is added and the sum dropped by a mask — so the instruction stream does
-// not depend on the scalar. The ADDRESS of the table read still does (13 bits of the scalar select one of
-// 8192 entries of a 10 MiB table): a cache-timing channel the reference's masked wwSel scan does not have;
-// scanning 8192 entries per window is not an option here, see DESIGN.md "Secret scalars".
-// FRESH = true (with CT): acc is the point at infinity on entry and need not be initialised — window 0 only
-// loads its table entry (Z = 1, or 0 by a mask if the digit is 0) instead of running an addition whose first
-// operand is O: one of the 16 / 30 / 40 mixed additions of k G saved.
-template <int N, bool CT = false, bool FRESH = false> __device__ __noinline__ void pt_add_mul_base(pt<N>& acc, const sc<N> ks, const uint4* __restrict__ gtab)
+// acc (+)= k * G for a 32N-bit k (little-endian limbs) through the fixed-base window table.
+// OFFSET WINDOWS: entry (i, d) of the table is not d 2^(w i) G but (d + 2^w) 2^(w i) G, and the scalar that is
+// cut into w-bit digits is k' = k - K mod q with K = sum_i 2^w 2^(w i): then sum_i entry(i, d_i(k')) =
+// (k' + K) G = k G. No digit selects the point at infinity, so every window is one unconditional mixed
+// addition — no skipped zero digits (the public-scalar form of round 1), no dummy addition dropped by a masked
+// select (the regular form the secret scalars used since: it kept the old and the new accumulator alive across
+// the eleven product calls of the addition; that glue was 17 % of the instructions of a signature). The
+// instruction stream is the same for every scalar; the reference's bignMulBase is regular too (ec.c:892-964).
+// What still depends on the scalar is the ADDRESS of the table read (a cache-timing channel the reference's
+// masked wwSel scan does not have; scanning 2^w entries per window is not an option here, DESIGN.md "Secret
+// scalars") and the exceptional branches of the complete addition (probability ~2^-250 per addition).
+// FRESH: acc is the point at infinity on entry and need not be initialised — window 0 only loads its entry.
+// K (N limbs, < q) lies behind the table.
+#define BIGN_GTAB_UINT4(N) ((size_t)BIGN_GN(N) * BIGN_GE(N) * ((N) / 2))
+template <int N, bool FRESH = false> __device__ __noinline__ void pt_add_mul_base(pt<N>& acc, const sc<N> ks, const uint4* __restrict__ gtab)
 {
-	static_assert(CT || !FRESH, "the direct form adds onto a running point");
-	const u32* k = ks.w;
+	u32 k[N];
+	{
+		u32 K[N];
+		const u32* Kp = reinterpret_cast<const u32*>(gtab + BIGN_GTAB_UINT4(N));
+#pragma unroll
+		for (int i = 0; i < N; ++i) K[i] = __ldg(Kp + i);
+		// (k - K) mod 2^(32N), + q if it borrowed: congruent to k - K for every k < 2^(32N) (K < q)
+		modq_sub<N>(k, ks.w, K);
+	}
 #pragma unroll 1
 	for (int i = 0; i < BIGN_GN(N); ++i)
 	{
 		const int bit = BIGN_GWN(N) * i, limb = bit >> 5;
 		const u64 w = (u64)k[limb] | (limb < N - 1 ? (u64)k[limb + 1] << 32 : 0);
 		const u32 d = (u32)(w >> (bit & 31)) & (BIGN_GE(N) - 1);
-		if (CT)
-		{
-			const u32 dd = d | (u32)(d == 0);
-			const uint4* e = gtab + ((size_t)i * BIGN_GE(N) + dd) * (N / 2);
-			fe<N> x, y;
+		const uint4* e = gtab + ((size_t)i * BIGN_GE(N) + d) * (N / 2);
+		fe<N> x, y;
 #pragma unroll
-			for (int j = 0; j < N / 4; ++j)
-			{
-				const uint4 a = __ldg(e + j), b = __ldg(e + N / 4 + j);
-				x.v[4 * j] = a.x, x.v[4 * j + 1] = a.y, x.v[4 * j + 2] = a.z, x.v[4 * j + 3] = a.w;
-				y.v[4 * j] = b.x, y.v[4 * j + 1] = b.y, y.v[4 * j + 2] = b.z, y.v[4 * j + 3] = b.w;
-			}
-			if (FRESH && i == 0)
-			{
-				acc.X = x, acc.Y = y;
-				fe_set_u32<N>(acc.Z, (u32)(d != 0));
-				continue;
-			}
-			pt<N> S;
-			pt_madd<N>(S, acc, x, y);
-			pt_select<N>(acc, S, 0u - (u32)(d != 0));
+		for (int j = 0; j < N / 4; ++j)
+		{
+			const uint4 a = __ldg(e + j), b = __ldg(e + N / 4 + j);
+			x.v[4 * j] = a.x, x.v[4 * j + 1] = a.y, x.v[4 * j + 2] = a.z, x.v[4 * j + 3] = a.w;
+			y.v[4 * j] = b.x, y.v[4 * j + 1] = b.y, y.v[4 * j + 2] = b.z, y.v[4 * j + 3] = b.w;
 		}
-		else if (d)
-		{
-			const uint4* e = gtab + ((size_t)i * BIGN_GE(N) + d) * (N / 2);
-			fe<N> x, y;
-#pragma unroll
-			for (int j = 0; j < N / 4; ++j)
-			{
-				const uint4 a = __ldg(e + j), b = __ldg(e + N / 4 + j);
-				x.v[4 * j] = a.x, x.v[4 * j + 1] = a.y, x.v[4 * j + 2] = a.z, x.v[4 * j + 3] = a.w;
-				y.v[4 * j] = b.x, y.v[4 * j + 1] = b.y, y.v[4 * j + 2] = b.z, y.v[4 * j + 3] = b.w;
-			}
+		if (FRESH && i == 0)
+			pt_set_affine<N>(acc, x, y);
+		else
 			pt_madd<N>(acc, acc, x, y);
-		}
 	}
 }
 
@@ -461,6 +488,33 @@ template <int N> __device__ __forceinline__ void pt_affine_xy_zi(fe<N>& x, fe<N>
 
 // ---------------------------------------------------------------- kernels
 // Table of fixed-base multiples: entry (i, j) = j * 2^(BIGN_GW i) * G, affine.
+// scalar of table entry (i, j): (j + 2^w) 2^(w i) mod q — never 0 (q is a prime above 2^(w + 1))
+template <int N> __device__ __forceinline__ void gtab_scalar(sc<N>& k, int i, u32 j)
+{
+	const int bit = BIGN_GWN(N) * i, limb = bit >> 5;
+	const u64 w = (u64)(j + BIGN_GE(N)) << (bit & 31);   // 17 + 31 bits at most
+	u32 t[N];
+#pragma unroll
+	for (int l = 0; l < N; ++l)
+		t[l] = l == limb ? (u32)w : (l == limb + 1 ? (u32)(w >> 32) : 0u);
+	// what does not fit the N limbs folds back: 2^(32N) = c (mod q)
+	modq_fold_top<N>(k.w, t, limb + 1 == N ? (u32)(w >> 32) : 0u);
+}
+// K = sum_i 2^w 2^(w i) mod q, stored behind the table (pt_add_mul_base)
+template <int N> __global__ void bign_gtab_k_kernel(uint4* gtab)
+{
+	u32 K[N];
+#pragma unroll
+	for (int l = 0; l < N; ++l) K[l] = 0;
+	for (int i = 0; i < BIGN_GN(N); ++i)
+	{
+		sc<N> t;
+		gtab_scalar<N>(t, i, 0);
+		modq_add<N>(K, K, t.w);
+	}
+	u32* out = reinterpret_cast<u32*>(gtab + BIGN_GTAB_UINT4(N));
+	for (int l = 0; l < N; ++l) out[l] = K[l];
+}
 template <int N> __global__ void __launch_bounds__(128) bign_gtab_kernel(uint4* gtab)
 {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -468,21 +522,8 @@ template <int N> __global__ void __launch_bounds__(128) bign_gtab_kernel(uint4* 
 		return;
 	const int i = idx / BIGN_GE(N), j = idx % BIGN_GE(N);
 	uint4* e = gtab + (size_t)idx * (N / 2);
-	// k = j << (BIGN_GW * i); digits whose bits would pass 2^(32N) cannot occur in a 32N-bit
-	// scalar, such entries are never read
-	const int bit = BIGN_GWN(N) * i, limb = bit >> 5;
-	if (j == 0 || bit + 32 - __clz(j) > 32 * N)
-	{
-		for (int l = 0; l < N / 2; ++l) e[l] = make_uint4(0, 0, 0, 0);
-		return;
-	}
 	sc<N> k;
-	{
-		const u64 w = (u64)j << (bit & 31);
-#pragma unroll
-		for (int l = 0; l < N; ++l)
-			k.w[l] = l == limb ? (u32)w : (l == limb + 1 ? (u32)(w >> 32) : 0u);
-	}
+	gtab_scalar<N>(k, i, (u32)j);
 	fe<N> gx, gy, x, y;
 	fe_set_u32<N>(gx, 0);
 #pragma unroll
@@ -626,7 +667,7 @@ bign_verify_kernel(u32* __restrict__ status, const u8* __restrict__ hashes, cons
 			sc<N> ks;
 #pragma unroll
 			for (int k = 0; k < N; ++k) ks.w[k] = s1[k];
-			pt_add_mul_base<N>(R, ks, gtab);
+			pt_add_mul_base<N>(R, ks, gtab);   // public scalar, same regular form
 		}
 		if (pt_is_inf<N>(R))
 			st = B2G_BAD_SIG, live = false;
@@ -784,7 +825,7 @@ bign_sign2_kernel(u32* __restrict__ status, u8* __restrict__ sigs, const u8* __r
 			sc<N> ks;
 #pragma unroll
 			for (int j = 0; j < N; ++j) ks.w[j] = k[j];
-			pt_add_mul_base<N, true, true>(R, ks, gtab);   // the one-time key is secret: regular form
+			pt_add_mul_base<N, true>(R, ks, gtab);   // the one-time key is secret: the form is regular
 		}
 		if (pt_is_inf<N>(R))
 			st = B2G_BAD_PARAMS, live = false;
@@ -899,7 +940,7 @@ bign_pubkey_kernel(u32* __restrict__ status, u8* __restrict__ pubkeys, const u8*
 			sc<N> ks;
 #pragma unroll
 			for (int j = 0; j < N; ++j) ks.w[j] = d[j];
-			pt_add_mul_base<N, true, true>(R, ks, gtab);   // the private key is secret: regular form
+			pt_add_mul_base<N, true>(R, ks, gtab);   // the private key is secret: the form is regular
 			if (pt_is_inf<N>(R))
 				st = B2G_BAD_PARAMS, live = false;
 		}
@@ -944,7 +985,7 @@ ecp_mul_kernel(u8* __restrict__ out, int* __restrict__ ok, const u8* __restrict_
 		{
 			sc<N> kg;
 			load_uN<N>(kg.w, kbase + NO * i);
-			pt_add_mul_base<N, true>(R, kg, gtab);
+			pt_add_mul_base<N>(R, kg, gtab);
 		}
 		live = !pt_is_inf<N>(R);
 	}
@@ -1076,9 +1117,10 @@ template <int N> static u32 bign_build_gtab(cudaStream_t st, uint4** out)
 {
 	uint4* p = 0;
 	const size_t entries = (size_t)BIGN_GN(N) * BIGN_GE(N);
-	if (cudaMalloc(&p, entries * 8 * N) != cudaSuccess)
+	if (cudaMalloc(&p, entries * 8 * N + 4 * N) != cudaSuccess)   /* + K behind the table */
 		return b2g_check_launch("cudaMalloc(gtab)");
 	bign_gtab_kernel<N><<<(u32)((entries + 127) / 128), 128, 0, st>>>(p);
+	bign_gtab_k_kernel<N><<<1, 1, 0, st>>>(p);
 	b2g_note_launch();
 	u32 e = b2g_check_launch("bign_gtab_kernel");
 	if (e)
