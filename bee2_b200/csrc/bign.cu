@@ -12,9 +12,9 @@
 // elements as N x u32 in registers. Scalar multiplication is REGULAR so that all lanes of a
 // warp execute the same doublings and additions in lock-step:
 //   * fixed base G: 16 / 13 / 13-bit windows over a device-resident table GTAB[GN][2^w] of
-//     affine multiples j * 2^(w i) * G (67 / 24 / 42 MiB; generated once per process, device
-//     and level by bign_gtab_kernel with the same point code) -> 16 / 30 / 40 mixed
-//     additions, no doublings;
+//     affine points (d + 2^w) * 2^(w i) * G ("offset windows": with the scalar k - K, K = sum 2^w 2^(w i),
+//     no digit means the point at infinity; 67 / 24 / 42 MiB; generated once per process, device and level
+//     by bign_gtab_kernel with the same point code) -> 16 / 30 / 40 unconditional mixed additions, no doublings;
 //   * variable base Q: signed 5-bit windows, per-thread table {1..16}Q in local memory
 //     (ecp.cuh pt_mul_var) -> 5 doublings + 1 addition per window.
 // The reference's interleaved wNAF (ec.c:1206-1268) is irregular and would diverge.
