@@ -61,7 +61,7 @@ CFG = {
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the bench
 # configuration, from the committed `ncu --set full` captures (profiles/r02_ncu_raw_*.csv)
 NCU_BIGN_WIDE_PER_VERIFY = 96884    # IMAD.WIDE(.X) executed per verify (profiles/r02_bign_opcode_mix.json)
-NCU_TRAFFIC = {"bign_sign2": 4.9547e+08, "belt_dwp": 1.0774e+09, "belt_ecb": 4.2638e+09, "belt_ctr": 1.0135e+09, "bash512": 4.4449e+09, "bign_verify": 3.1663e+09}
+NCU_TRAFFIC = {"bign_sign2": 4.2928e+08, "belt_dwp": 1.0774e+09, "belt_ecb": 4.2638e+09, "belt_ctr": 1.0135e+09, "bash512": 4.4449e+09, "bign_verify": 3.1637e+09}
 
 
 def hbm_peak():
