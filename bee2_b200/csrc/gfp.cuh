@@ -338,7 +338,7 @@ template <int N> __host__ __device__ __noinline__ fe<N> fe_inv_fermat_fn(const f
 	return t;
 }
 // r = 1/a (0 -> 0), canonical. The kernels use the division-step form (gfp_inv.cuh: a third of the power's
-// instructions and short dependent chains — it runs on one thread per CTA while the others wait); the power
+// instructions and short dependent chains — one warp per CTA runs it while the others wait); the power
 // stays as the cross-check of the host tests. CT = true: fixed step count (secret-dependent inputs).
 template <int N, bool CT> __host__ __device__ __noinline__ fe<N> fe_inv_fn(const fe<N> a)
 {

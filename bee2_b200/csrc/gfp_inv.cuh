@@ -1,9 +1,10 @@
 // gfp_inv.cuh — field inversion by Bernstein–Yang division steps ("safegcd", 2019), one thread per element.
 //
 // Replaces the power a^(p-2) that gfpInv computes (gfp.c:33-44, qr.c power ladder): for p = 2^256 - 189 that
-// is 255 squarings + 13 multiplications = 33 000 dependent-chain instructions, and it runs on ONE thread of
-// the CTA while the others wait at a barrier (bign.cu block_inv). The division-step iteration needs ~11 000
-// instructions with short dependent chains — a third of the latency budget.
+// is 255 squarings + 13 multiplications = 33 000 dependent-chain instructions, and it sits on the critical path
+// of every CTA of the bign kernels (bign.cu block_inv: one warp inverts the 32 nodes at which the CTA's product
+// tree ends while the other warps wait at a barrier). The division-step iteration needs ~12 000 instructions
+// (l = 128) with short dependent chains.
 //
 //   divstep(delta, f, g) = (1 - delta, g, (g - f) / 2)          if delta > 0 and g odd
 //                          (1 + delta, f, (g + (g mod 2) f) / 2) otherwise
