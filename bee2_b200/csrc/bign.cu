@@ -1120,6 +1120,7 @@ template <int N> static u32 bign_build_gtab(cudaStream_t st, uint4** out)
 	if (cudaMalloc(&p, entries * 8 * N + 4 * N) != cudaSuccess)   /* + K behind the table */
 		return b2g_check_launch("cudaMalloc(gtab)");
 	bign_gtab_kernel<N><<<(u32)((entries + 127) / 128), 128, 0, st>>>(p);
+	b2g_note_launch();
 	bign_gtab_k_kernel<N><<<1, 1, 0, st>>>(p);
 	b2g_note_launch();
 	u32 e = b2g_check_launch("bign_gtab_kernel");
