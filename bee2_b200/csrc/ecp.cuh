@@ -71,17 +71,17 @@ template <int N, bool INL> PT_OP void pt_dbl_t(pt<N>& R, const pt<N>& P)
 	PS(delta, P.Z);
 	PS(gamma, P.Y);
 	fe_add<N>(t, P.Y, P.Z), PS(t, t);
-	fe_sub<N>(t, t, gamma), fe_sub<N>(t, t, delta);               // Z3 = (Y + Z)^2 - Y^2 - Z^2
+	fe_sub2<N>(t, t, gamma, delta);                               // Z3 = (Y + Z)^2 - Y^2 - Z^2
 	fe_sub<N>(u, P.X, delta), fe_add<N>(delta, P.X, delta);
 	R.Z = t;
 	PM(alpha, u, delta);
-	fe_dbl<N>(t, alpha), fe_add<N>(alpha, alpha, t);              // 3 (X - Z^2)(X + Z^2)
+	fe_mul3<N>(alpha, alpha);                                     // 3 (X - Z^2)(X + Z^2)
 	PM(beta, P.X, gamma);
 	fe_shl<2, N>(beta, beta);                                     // 4 beta
 	PS(gamma, gamma);
 	fe_shl<3, N>(gamma, gamma);                                   // 8 gamma^2
 	PS(t, alpha);
-	fe_sub<N>(t, t, beta), fe_sub<N>(t, t, beta);                 // X3 = alpha^2 - 8 beta
+	fe_sub2<N>(t, t, beta, beta);                                 // X3 = alpha^2 - 8 beta
 	R.X = t;
 	fe_sub<N>(t, beta, t), PM(t, alpha, t);
 	fe_sub<N>(R.Y, t, gamma);                                     // Y3 = alpha (4 beta - X3) - 8 gamma^2
@@ -130,10 +130,10 @@ template <int N> PT_OP void pt_madd(pt<N>& R, const pt<N>& P, const fe<N>& x2, c
 	fe_mul<N>(j, h, i);
 	fe_mul<N>(v, P.X, i);
 	fe_add<N>(t, P.Z, h), fe_sqr<N>(t, t);
-	fe_sub<N>(t, t, z1z1), fe_sub<N>(t, t, hh);                   // Z3 = (Z1 + H)^2 - Z1Z1 - HH
+	fe_sub2<N>(t, t, z1z1, hh);                                   // Z3 = (Z1 + H)^2 - Z1Z1 - HH
 	fe<N> z3 = t;
 	fe_sqr<N>(t, r);
-	fe_sub<N>(t, t, j), fe_sub<N>(t, t, v), fe_sub<N>(t, t, v);   // X3 = r^2 - J - 2V
+	fe_sub2<N>(t, t, j, v), fe_sub<N>(t, t, v);                   // X3 = r^2 - J - 2V
 	fe<N> x3 = t;
 	fe_sub<N>(t, v, x3), fe_mul<N>(t, r, t);
 	fe_mul<N>(j, P.Y, j), fe_dbl<N>(j, j);
@@ -169,11 +169,11 @@ template <int N> PT_OP void pt_add(pt<N>& R, const pt<N>& P, const pt<N>& Q)
 	fe_mul<N>(j, h, i);
 	fe_mul<N>(v, u1, i);
 	fe_add<N>(t, P.Z, Q.Z), fe_sqr<N>(t, t);
-	fe_sub<N>(t, t, z1z1), fe_sub<N>(t, t, z2z2);
+	fe_sub2<N>(t, t, z1z1, z2z2);
 	fe<N> z3;
 	fe_mul<N>(z3, t, h);                                          // Z3 = ((Z1 + Z2)^2 - Z1Z1 - Z2Z2) H
 	fe_sqr<N>(t, r);
-	fe_sub<N>(t, t, j), fe_sub<N>(t, t, v), fe_sub<N>(t, t, v);   // X3 = r^2 - J - 2V
+	fe_sub2<N>(t, t, j, v), fe_sub<N>(t, t, v);                   // X3 = r^2 - J - 2V
 	fe<N> x3 = t;
 	fe_sub<N>(t, v, x3), fe_mul<N>(t, r, t);
 	fe_mul<N>(j, s1, j), fe_dbl<N>(j, j);

@@ -224,6 +224,33 @@ template <int N> GFP_HD void fe_sub(fe<N>& r, const fe<N>& a, const fe<N>& b)
 	for (int i = 0; i < N; ++i) r.v[i] = t[i];
 }
 
+// r = a - b - c (weak): two borrow chains, ONE fold — every borrow stands for + 2^(32N) = + c (mod p), both are taken
+// back together (a fold is six instructions with its rare-ripple guard; the point formulas are full of a - b - c)
+template <int N> GFP_HD void fe_sub2(fe<N>& r, const fe<N>& a, const fe<N>& b, const fe<N>& c)
+{
+	u32 t[N], u[N];
+	const u32 m1 = sub_n<N>(t, a.v, b.v);
+	const u32 m2 = sub_n<N>(u, t, c.v);
+	fe_fold_out<N>(u, ((m1 & 1u) + (m2 & 1u)) * fe_param<N>::C);
+#pragma unroll
+	for (int i = 0; i < N; ++i) r.v[i] = u[i];
+}
+
+// r = 3 a (weak): 2a by a funnel-shift pass, + a by one carry chain, ONE fold for the bit shifted out and the carry
+template <int N> GFP_HD void fe_mul3(fe<N>& r, const fe<N>& a)
+{
+	u32 d[N], t[N];
+	const u32 top = a.v[N - 1] >> 31;
+#pragma unroll
+	for (int k = N - 1; k > 0; --k)
+		d[k] = gfp_funnel_l(a.v[k - 1], a.v[k], 1);
+	d[0] = a.v[0] << 1;
+	const u32 c = add_n<N>(t, d, a.v);
+	fe_fold_in<N>(t, (top + c) * fe_param<N>::C);
+#pragma unroll
+	for (int i = 0; i < N; ++i) r.v[i] = t[i];
+}
+
 // r = 2^K a (weak), K = 1, 2, 3: one funnel-shift pass, the K bits shifted out fold back as * c
 template <int K, int N> GFP_HD void fe_shl(fe<N>& r, const fe<N>& a)
 {

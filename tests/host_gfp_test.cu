@@ -42,6 +42,21 @@ template <int N> static std::string run(const std::string& op, std::istringstrea
 		else fe_sub<N>(r, a, b);
 		return to_hex(r.v, N);
 	}
+	if (op == "sub2")
+	{
+		in >> ha >> hb >> hc;
+		fe<N> c;
+		from_hex<N>(a.v, ha), from_hex<N>(b.v, hb), from_hex<N>(c.v, hc);
+		fe_sub2<N>(r, a, b, c);
+		return to_hex(r.v, N);
+	}
+	if (op == "mul3")
+	{
+		in >> ha;
+		from_hex<N>(a.v, ha);
+		fe_mul3<N>(r, a);
+		return to_hex(r.v, N);
+	}
 	if (op == "sqr" || op == "inv" || op == "shl1" || op == "shl2" || op == "shl3" || op == "canon" || op == "iszero")
 	{
 		in >> ha;

@@ -90,6 +90,12 @@ def test_field_ops(exe, n):
             lines.append(f"shl{k} {n} {a:x}"), want.append(("mod", (a << k) % p))
         lines.append(f"canon {n} {a:x}"), want.append(("raw", a % p if a < 2 * p else None))
         lines.append(f"iszero {n} {a:x}"), want.append(("raw", 1 if a % p == 0 else 0))
+    # the fused forms of the point formulas: a - b - c with one fold (0, 1 or 2 borrows), 3a with one fold
+    for a in vals[:26]:
+        lines.append(f"mul3 {n} {a:x}"), want.append(("mod", 3 * a % p))
+        for b2 in vals[:26]:
+            for c2 in (vals[0], vals[5], vals[9], vals[10], vals[11], rng.choice(vals)):
+                lines.append(f"sub2 {n} {a:x} {b2:x} {c2:x}"), want.append(("mod", (a - b2 - c2) % p))
     for a in vals + [rng.getrandbits(32 * n) for _ in range(200)]:
         # canonical result (gfp_inv.cuh); 0 and p (the other weak form of 0) invert to 0
         lines.append(f"inv {n} {a:x}"), want.append(("raw", pow(a, -1, p) if a % p else 0))
