@@ -112,7 +112,7 @@ template <int L> GFP_INV_HD void inv_update_de(i32* d, i32* e, const inv_mat& t,
 }
 
 // r = 1/a mod p for p = 2^(32N) - c, a any N-limb value (0 -> 0); the result is canonical (< p)
-template <int N, bool CT> GFP_INV_HD void inv_safegcd(u32* r, const u32* a, u32 c)
+template <int N, bool CT> GFP_INV_HD void inv_safegcd(u32* r, const u32* a, u32 c, int* batches_used = 0)
 {
 	constexpr int L = inv30<N>::L;
 	constexpr i32 M30 = inv30<N>::M30;
@@ -155,7 +155,11 @@ template <int N, bool CT> GFP_INV_HD void inv_safegcd(u32* r, const u32* a, u32 
 #pragma unroll
 			for (int i = 0; i < L; ++i) z |= g[i];
 			if (z == 0)
+			{
+				if (batches_used)   // tests: how many batches the iteration needed (early-exit form)
+					*batches_used = b + 1;
 				break;
+			}
 		}
 	}
 	// now f = +-1 and d = +-1/a in (-2p, p): d <- d + p if negative; d <- -d if f < 0; d <- d + p if negative

@@ -50,6 +50,16 @@ template <int N> static std::string run(const std::string& op, std::istringstrea
 		fe_sub2<N>(r, a, b, c);
 		return to_hex(r.v, N);
 	}
+	if (op == "invbatches")
+	{
+		// batches of 30 division steps the early-exit form needs, and the scheduled count of the fixed form
+		in >> ha;
+		from_hex<N>(a.v, ha);
+		fe_canon<N>(a);
+		int used = 0;
+		inv_safegcd<N, false>(r.v, a.v, fe_param<N>::C, &used);
+		return std::to_string(used) + " " + std::to_string(inv30<N>::BATCHES);
+	}
 	if (op == "mul3")
 	{
 		in >> ha;

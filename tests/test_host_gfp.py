@@ -205,3 +205,19 @@ def test_generated_header_is_current():
     out = subprocess.run([sys.executable, os.path.join(HERE, "..", "tools", "gen_gfp_asm.py")], capture_output=True,
                          text=True, check=True).stdout
     assert out == open(os.path.join(HERE, "..", "bee2_b200", "csrc", "gfp_asm.cuh")).read()
+
+
+@pytest.mark.parametrize("n", [8, 12, 16])
+def test_inversion_step_bound_holds_on_samples(exe, n):
+    """gfp_inv.cuh runs a fixed number of batches for secret-dependent inputs (20 for the 256-bit field: the
+    590-step bound of the delta = 1/2 variant; 37 / 50 from Theorem 11.2 for the wider fields). The result does not
+    depend on the bound (the loop goes on while g != 0) but the fixed instruction count does: on 3000 random
+    elements plus the edge values the early-exit form must never need more batches than are scheduled."""
+    rng = random.Random(4000 + n)
+    vals = [v for v in edge_values(n, rng) if v % CURVES[n][0]] + [rng.getrandbits(32 * n) for _ in range(3000)]
+    got = run(exe, [f"invbatches {n} {a:x}" for a in vals])
+    used = [int(g.split()[0]) for g in got]
+    sched = int(got[0].split()[1])
+    assert sched == {8: 20, 12: 37, 16: 50}[n]
+    assert max(used) <= sched, (max(used), sched)
+    assert min(used) >= 1
