@@ -124,21 +124,21 @@ template <int N> PT_OP void pt_madd(pt<N>& R, const pt<N>& P, const fe<N>& x2, c
 			pt_set_inf<N>(R);
 		return;
 	}
+	// (order of the calls chosen for short live ranges, as in pt_dbl_t: Z3 first, then z1z1 and hh are dead;
+	// R may alias P: Z3 is written after the last read of P.Z, X3 / Y3 after the last reads of P.X / P.Y)
 	fe_dbl<N>(r, r);
 	fe_sqr<N>(hh, h);
+	fe_add<N>(t, P.Z, h), fe_sqr<N>(t, t);
+	fe_sub2<N>(R.Z, t, z1z1, hh);                                 // Z3 = (Z1 + H)^2 - Z1Z1 - HH
 	fe_shl<2, N>(i, hh);                                          // I = 4 HH
 	fe_mul<N>(j, h, i);
 	fe_mul<N>(v, P.X, i);
-	fe_add<N>(t, P.Z, h), fe_sqr<N>(t, t);
-	fe_sub2<N>(t, t, z1z1, hh);                                   // Z3 = (Z1 + H)^2 - Z1Z1 - HH
-	fe<N> z3 = t;
 	fe_sqr<N>(t, r);
 	fe_sub2<N>(t, t, j, v), fe_sub<N>(t, t, v);                   // X3 = r^2 - J - 2V
-	fe<N> x3 = t;
-	fe_sub<N>(t, v, x3), fe_mul<N>(t, r, t);
 	fe_mul<N>(j, P.Y, j), fe_dbl<N>(j, j);
+	R.X = t;
+	fe_sub<N>(t, v, t), fe_mul<N>(t, r, t);
 	fe_sub<N>(R.Y, t, j);                                         // Y3 = r (V - X3) - 2 Y1 J
-	R.X = x3, R.Z = z3;
 }
 
 // R = P + Q, both Jacobian (11M + 5S)
@@ -164,21 +164,20 @@ template <int N> PT_OP void pt_add(pt<N>& R, const pt<N>& P, const pt<N>& Q)
 			pt_set_inf<N>(R);
 		return;
 	}
+	// (Z3 first: z1z1, z2z2 and both Z die; from here on P and Q are no longer read, so R may be written)
 	fe_dbl<N>(r, r);
+	fe_add<N>(t, P.Z, Q.Z), fe_sqr<N>(t, t);
+	fe_sub2<N>(t, t, z1z1, z2z2);
+	fe_mul<N>(R.Z, t, h);                                         // Z3 = ((Z1 + Z2)^2 - Z1Z1 - Z2Z2) H
 	fe_dbl<N>(t, h), fe_sqr<N>(i, t);                             // I = (2H)^2
 	fe_mul<N>(j, h, i);
 	fe_mul<N>(v, u1, i);
-	fe_add<N>(t, P.Z, Q.Z), fe_sqr<N>(t, t);
-	fe_sub2<N>(t, t, z1z1, z2z2);
-	fe<N> z3;
-	fe_mul<N>(z3, t, h);                                          // Z3 = ((Z1 + Z2)^2 - Z1Z1 - Z2Z2) H
 	fe_sqr<N>(t, r);
 	fe_sub2<N>(t, t, j, v), fe_sub<N>(t, t, v);                   // X3 = r^2 - J - 2V
-	fe<N> x3 = t;
-	fe_sub<N>(t, v, x3), fe_mul<N>(t, r, t);
 	fe_mul<N>(j, s1, j), fe_dbl<N>(j, j);
+	R.X = t;
+	fe_sub<N>(t, v, t), fe_mul<N>(t, r, t);
 	fe_sub<N>(R.Y, t, j);                                         // Y3 = r (V - X3) - 2 S1 J
-	R.X = x3, R.Z = z3;
 }
 
 // affine coordinates of a finite point, canonical residues (ecp_j.c:104-133)
