@@ -145,10 +145,13 @@ template <int N> PT_OP void pt_madd(pt<N>& R, const pt<N>& P, const fe<N>& x2, c
 template <int N> PT_OP void pt_add(pt<N>& R, const pt<N>& P, const pt<N>& Q)
 {
 	fe<N> z1z1, z2z2, u1, u2, s1, s2, h, i, j, r, v, t;
-	fe_sqr<N>(z1z1, P.Z), fe_sqr<N>(z2z2, Q.Z);
-	fe_mul<N>(u1, P.X, z2z2), fe_mul<N>(u2, Q.X, z1z1);
-	fe_mul<N>(t, Q.Z, z2z2), fe_mul<N>(s1, P.Y, t);
+	// (first everything that reads Q.X and Q.Y — the table entry sits in registers, P in memory)
+	fe_sqr<N>(z1z1, P.Z);
+	fe_mul<N>(u2, Q.X, z1z1);
 	fe_mul<N>(t, P.Z, z1z1), fe_mul<N>(s2, Q.Y, t);
+	fe_sqr<N>(z2z2, Q.Z);
+	fe_mul<N>(u1, P.X, z2z2);
+	fe_mul<N>(t, Q.Z, z2z2), fe_mul<N>(s1, P.Y, t);
 	fe_sub<N>(h, u2, u1);
 	fe_sub<N>(r, s2, s1);
 	const bool p_inf = fe_is_zero<N>(P.Z), q_inf = fe_is_zero<N>(Q.Z);
